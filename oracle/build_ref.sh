@@ -1,0 +1,63 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE ONLY.
+# Builds the UNMODIFIED reference (intel/yask) hot path out-of-tree into oracle/_ref/
+# from the sources where they lie under /root/reference, plus oracle/ref_driver.cpp
+# against each resulting kernel library.  Nothing is copied from /root/reference and
+# nothing is written there (YASK_OUTPUT_DIR keeps all outputs under oracle/_ref/yask,
+# see /root/reference/src/common/common.mk:38-55).
+#
+# NOTE (see DESIGN.md "Oracle"): the reference's hot path is *generated* code (its
+# stencil compiler + perl loop generators run at build time), so it cannot be built by
+# "gcc on a few source files".  We therefore drive the reference's own makefiles, in
+# this container only; the GPU box uses the prebuilt oracle/_ref/ files (git-ignored,
+# but shipped by gpurun) and never needs /root/reference.
+#
+# usage: oracle/build_ref.sh [arch]     (arch: avx512 (default) | avx2 | intel64)
+set -e
+REF=${YASK_REFERENCE:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref/yask
+ARCH=${1:-avx512}
+J=${JOBS:-8}
+
+if [ ! -d "$REF/src/kernel" ]; then
+    echo "build_ref.sh: $REF not present (GPU box?) -- using prebuilt oracle/_ref as is"
+    exit 0
+fi
+mkdir -p "$OUT"
+LOG=$HERE/_ref/build.log
+: > "$LOG"
+
+if [ ! -x "$OUT/bin/yask_compiler.exe" ]; then
+    echo "[build_ref] yask compiler"
+    make -C "$REF/src/compiler" YASK_OUTPUT_DIR="$OUT" mpi=0 arch=$ARCH -j$J compiler >> "$LOG" 2>&1
+fi
+
+# stencil  suffix  real_bytes  extra-make-args
+build_kernel() {
+    local st=$1 suf=$2 rb=$3; shift 3
+    local tag="$st$suf.$ARCH"
+    if [ ! -f "$OUT/lib/libyask_kernel.$tag.so" ] || [ ! -x "$OUT/bin/yask_kernel.$tag.exe" ]; then
+        echo "[build_ref] kernel $tag"
+        make -C "$REF/src/kernel" YASK_OUTPUT_DIR="$OUT" stencil=$st YK_STENCIL_SUFFIX=$suf arch=$ARCH \
+            mpi=0 numa=0 real_bytes=$rb -j$J "$@" default >> "$LOG" 2>&1
+    fi
+    if [ ! -x "$OUT/bin/ref_driver.$tag" ] || [ "$HERE/ref_driver.cpp" -nt "$OUT/bin/ref_driver.$tag" ]; then
+        g++ -std=c++17 -O2 -fopenmp -I"$REF/include" "$HERE/ref_driver.cpp" \
+            -L"$OUT/lib" -Wl,-rpath,'$ORIGIN/../lib' -lyask_kernel.$tag -lrt -o "$OUT/bin/ref_driver.$tag"
+    fi
+}
+
+# Default flags (GCC -O3 => -ffp-contract=fast: FMAs formed by the host compiler) and
+# "-strict" (-ffp-contract=off: pure IEEE mul/add in DSL order), SURVEY.md section 7 hard part 1.
+build_kernel iso3dfd ""        4
+build_kernel iso3dfd "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+if [ "${REF_ALL:-1}" = "1" ]; then
+    build_kernel awp_elastic ""        4
+    build_kernel awp_elastic "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+    build_kernel ssg "-fp64"        8
+    build_kernel ssg "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+fi
+# Drop the (large) intermediate build tree; keep bin/ and lib/ only.
+if [ "${KEEP_BUILD:-0}" != "1" ]; then rm -rf "$OUT/build"; fi
+echo "[build_ref] done: $(ls "$OUT/bin" | tr '\n' ' ')"

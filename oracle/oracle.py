@@ -1,0 +1,135 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes wrapper around oracle/libyask_oracle.so and a runner for
+the prebuilt reference binaries under oracle/_ref (built by oracle/build_ref.sh).
+
+Never imported by the product package (yask_b200)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build() -> str:
+    """Compile the C restatement (gcc, seconds)."""
+    subprocess.run(["make", "-s", "-C", HERE], check=True, env={**os.environ, "CC": "gcc"})
+    return os.path.join(HERE, "libyask_oracle.so")
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(HERE, "libyask_oracle.so")
+        src = os.path.join(HERE, "yask_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        _LIB = ctypes.CDLL(path)
+        _LIB.yo_iso3dfd_coeffs.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        _LIB.yo_const_roundtrip.argtypes = [ctypes.c_double]
+        _LIB.yo_const_roundtrip.restype = ctypes.c_double
+        for nm in ("yo_iso3dfd_run_f32", "yo_iso3dfd_run_f64"):
+            f = getattr(_LIB, nm)
+            f.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int64] * 4 + [ctypes.c_int] * 3
+            f.restype = ctypes.c_int
+    return _LIB
+
+
+def iso3dfd_coeffs(radius: int) -> np.ndarray:
+    c = np.zeros(radius + 1, dtype=np.float64)
+    rc = lib().yo_iso3dfd_coeffs(c.ctypes.data, radius)
+    assert rc == 0
+    return c
+
+
+def iso3dfd_run(p0: np.ndarray, p1: np.ndarray, v: np.ndarray, radius: int, steps: int, contract: bool) -> np.ndarray:
+    """p0/p1: (nx+2h, ny+2h, nz+2h) API steps 0 and 1 incl. halo h; v: (nx,ny,nz).
+    Returns the final p (domain + untouched halo) after `steps` steps; inputs are not modified."""
+    assert p0.dtype == p1.dtype == v.dtype and p0.shape == p1.shape
+    nx, ny, nz = v.shape
+    h = (p0.shape[0] - nx) // 2
+    assert h >= radius and p0.shape == (nx + 2 * h, ny + 2 * h, nz + 2 * h)
+    a = np.ascontiguousarray(p0).copy()
+    b = np.ascontiguousarray(p1).copy()
+    vv = np.ascontiguousarray(v)
+    fn = lib().yo_iso3dfd_run_f32 if p0.dtype == np.float32 else lib().yo_iso3dfd_run_f64
+    which = fn(a.ctypes.data, b.ctypes.data, vv.ctypes.data, nx, ny, nz, h, radius, steps, int(contract))
+    assert which in (0, 1)
+    return a if which == 0 else b
+
+
+# ---------------------------------------------------------------------------------------
+# Prebuilt reference (oracle/_ref): only usable where build_ref.sh has been run.
+# ---------------------------------------------------------------------------------------
+REF_BIN = os.path.join(HERE, "_ref", "yask", "bin")
+
+
+def ref_available(tag: str) -> bool:
+    return os.path.exists(os.path.join(REF_BIN, f"ref_driver.{tag}"))
+
+
+def _parse_manifest(text: str) -> dict:
+    out = {"vars": {}}
+    for line in text.splitlines():
+        tok = line.split()
+        if not tok:
+            continue
+        if tok[0] == "solution":
+            out["name"] = tok[1]
+            out["elem_bytes"] = int(tok[3])
+        elif tok[0] == "var":
+            name = tok[1]
+            nd = int(tok[3])
+            i = 5
+            dims = tok[i:i + nd]
+            i += nd
+            has_step = int(tok[i + 1])
+            steps = (int(tok[i + 3]), int(tok[i + 4]))
+            i += 5
+            nb = nd - has_step
+            boxes = {}
+            for key in ("in_first", "in_last", "out_first", "out_last"):
+                assert tok[i] == key, (tok[i], key)
+                boxes[key] = [int(t) for t in tok[i + 1:i + 1 + nb]]
+                i += 1 + nb
+            out["vars"][name] = dict(dims=dims, has_step=bool(has_step), steps=steps, **boxes)
+    return out
+
+
+def ref_info(tag: str, n) -> dict:
+    r = subprocess.run([os.path.join(REF_BIN, f"ref_driver.{tag}"), "info"] + [str(int(i)) for i in n],
+                       check=True, capture_output=True, text=True)
+    return _parse_manifest(r.stdout)
+
+
+def ref_run(tag: str, n, steps: int, inputs: dict, threads: int | None = None) -> tuple[dict, dict]:
+    """inputs: {(var, step): ndarray over the var's in-box}.  Returns ({(var, step): ndarray over
+    the out-box}, manifest-after-run)."""
+    info = ref_info(tag, n)
+    dt = np.float32 if info["elem_bytes"] == 4 else np.float64
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    with tempfile.TemporaryDirectory() as d:
+        for name, g in info["vars"].items():
+            t0, t1 = g["steps"] if g["has_step"] else (0, 0)
+            shape = [l - f + 1 for f, l in zip(g["in_first"], g["in_last"])]
+            for t in range(t0, t1 + 1):
+                a = np.ascontiguousarray(inputs[(name, t)], dtype=dt)
+                assert list(a.shape) == shape or (not shape and a.size == 1), (name, a.shape, shape)
+                a.tofile(os.path.join(d, f"{name}.t{t}.in"))
+        r = subprocess.run([os.path.join(REF_BIN, f"ref_driver.{tag}"), "run"] + [str(int(i)) for i in n] + [str(steps), d],
+                           check=True, capture_output=True, text=True, env=env)
+        after = _parse_manifest(r.stdout)
+        outs = {}
+        for name, g in after["vars"].items():
+            t0, t1 = g["steps"] if g["has_step"] else (0, 0)
+            shape = [l - f + 1 for f, l in zip(g["out_first"], g["out_last"])]
+            for t in range(t0, t1 + 1):
+                a = np.fromfile(os.path.join(d, f"{name}.t{t}.out"), dtype=dt)
+                outs[(name, t)] = a.reshape(shape) if shape else a
+    return outs, after

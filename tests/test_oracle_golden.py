@@ -1,0 +1,37 @@
+"""CPU: pin the oracle (oracle/yask_oracle.c) against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py via oracle/ref_driver.cpp)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import contract_mode_of, golden_cases, load_golden, regen_inputs
+
+
+def test_fd_coefficients_match_generated_literals():
+    # Literals as printed into the reference's generated kernel for iso3dfd radius 8
+    # (oracle/_ref/.../gen/yask_stencil_code.hpp, emitted by src/compiler/lib/Cpp.cpp:39-53).
+    lit = ["-3.665812925170066e-03", "7.111111111111103e-04", "-1.244444444444443e-04", "3.016835016835014e-05",
+           "-7.070707070707062e-06", "1.392385392385389e-06", "-2.072002072002067e-07", "2.029716315430595e-08",
+           "-9.712509712509679e-10"]
+    c = O.iso3dfd_coeffs(8)
+    assert [float(s) for s in lit] == list(c)
+    # radius 2 literals from the "-target pseudo" listing in SURVEY.md Appendix A (6 digits).
+    c2 = O.iso3dfd_coeffs(2)
+    assert abs(c2[0] - (-3.0e-3)) < 1e-9 and abs(c2[1] - 0.000533333) < 1e-9 and abs(c2[2] - (-3.333333e-05)) < 1e-11
+
+
+@pytest.mark.parametrize("path", golden_cases("iso3dfd"))
+def test_iso3dfd_oracle_bit_exact_vs_reference(path):
+    meta, arrays = load_golden(path)
+    ins = regen_inputs(meta)
+    mode = contract_mode_of(meta["ref_tag"])
+    out = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], 8, meta["steps"], mode)
+    t_last = meta["vars"]["p"]["steps"][1]
+    ref = arrays[f"p.t{t_last}"]
+    got = out[8:-8, 8:-8, 8:-8]
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # and the other contraction mode must NOT be what this build does (guards the fixture labels)
+    if meta["steps"] >= 2:
+        other = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], 8, meta["steps"], 2 - mode)
+        assert not np.array_equal(other[8:-8, 8:-8, 8:-8].view(np.uint32), ref.view(np.uint32))
