@@ -1,0 +1,51 @@
+"""CPU: the C-ABI library loads, exports every symbol include/yask_b200.h declares, and the host-side
+logic that needs no device behaves like the reference API (errors, settings)."""
+import os
+import re
+
+import pytest
+
+from yask_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = capi.lib()
+    hdr = open(os.path.join(ROOT, "include", "yask_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(yb_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(capi.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_version_and_registry():
+    assert capi.version().startswith("4.05.04")
+    L = capi.lib()
+    names = [L.yb_stencil_name(i).decode() for i in range(L.yb_num_stencils())]
+    assert "iso3dfd" in names
+
+
+def test_solution_settings_and_errors_without_device():
+    s = capi.Solution("iso3dfd")
+    assert s.get_name() == "iso3dfd" and s.get_target() == "sm_100a" and s.get_element_bytes() == 4
+    assert s.get_domain_dim_names() == ["x", "y", "z"] and s.get_step_dim_name() == "t"
+    s.set_overall_domain_size_vec([64, 48, 32])
+    assert s.get_overall_domain_size_vec() == [64, 48, 32]
+    p = s.get_var("p")
+    assert p.get_dim_names() == ["t", "x", "y", "z"]
+    vi = p.info
+    assert vi.step_alloc == 2 and vi.dims[1].left_halo == 8 and vi.dims[3].right_halo == 8 and vi.halo_exchange_l1_norm == 1
+    with pytest.raises(capi.YaskError):   # unknown var (reference: context.hpp:631-636)
+        s.get_var("nope")
+    with pytest.raises(capi.YaskError):   # run before prepare (reference: context.cpp:265-266)
+        s.run_solution(0, 1)
+    with pytest.raises(capi.YaskError):
+        capi.Solution("no_such_stencil")
+    with pytest.raises(capi.YaskError):
+        s.set_option("fp_mode", "7")
+    if capi.device_count() == 0:
+        with pytest.raises(capi.YaskError) as e:   # no CPU fallback: must fail loudly
+            s.prepare_solution(0)
+        assert "no CUDA device" in str(e.value)
+    s.close()

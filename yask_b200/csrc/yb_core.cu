@@ -1,0 +1,654 @@
+// C ABI of libyask_b200 (include/yask_b200.h): solution life cycle, rank geometry, var storage in
+// HBM, slice copies, the run loop and stats.  Host-side counterpart of the reference's
+// StencilContext (/root/reference/src/kernel/lib/{context,soln_apis,setup}.cpp) -- integer
+// bookkeeping only; all arithmetic happens in the engines' CUDA kernels.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "yb_core.h"
+#include "yb_halo.h"
+
+namespace yb {
+
+static thread_local char g_err[1024] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+Solution::~Solution() {
+    if (device >= 0) {
+        cudaSetDevice(device);
+        halo_free(halo); halo = nullptr;
+        for (auto& v : vars)
+            if (v.dev) cudaFree(v.dev);
+        for (auto& pe : pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+        if (stage_dev) cudaFree(stage_dev);
+        if (stage_host) cudaFreeHost(stage_host);
+        if (own_stream) cudaStreamDestroy(own_stream);
+        if (comm_stream) cudaStreamDestroy(comm_stream);
+    }
+}
+
+static int check_dim(const Solution* s, int dim) {
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (dim < 0 || dim >= s->ndd) return set_error(YB_EINVAL, "domain dim index %d out of range [0,%d)", dim, s->ndd);
+    return 0;
+}
+static int check_var(const Solution* s, int var) {
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (var < 0 || var >= int(s->vars.size())) return set_error(YB_EINVAL, "var index %d out of range", var);
+    return 0;
+}
+
+// ---- geometry (setup_rank + update_var_info + YkVarBase::resize) ------------------------------------
+// Per-rank sizes follow /root/reference/src/kernel/lib/setup.cpp:462-503: when only the overall
+// size is given, every rank gets ceil(overall/nranks) and the last one the remainder.
+static int compute_rank_geometry(Solution& s) {
+    for (int d = 0; d < s.ndd; d++) {
+        int64_t nr = s.num_ranks[d], ri = s.rank_index[d];
+        if (nr < 1) return set_error(YB_EINVAL, "num_ranks must be >= 1");
+        if (ri < 0 || ri >= nr) return set_error(YB_EINVAL, "rank index %lld out of range [0,%lld)", (long long)ri, (long long)nr);
+        int64_t rs = s.req_rank_size[d], os = s.req_overall_size[d];
+        if (rs > 0 && os <= 0) {
+            // rank size given: all ranks are assumed to use the same size
+            s.rank_size[d] = rs;
+            s.overall_size[d] = rs * nr;
+            s.rank_offset[d] = rs * ri;
+        } else if (os > 0) {
+            int64_t per = (os + nr - 1) / nr;
+            int64_t last = os - per * (nr - 1);
+            if (last <= 0) return set_error(YB_EINVAL, "overall size %lld too small for %lld ranks", (long long)os, (long long)nr);
+            if (rs > 0 && rs * nr != os && nr > 1)
+                return set_error(YB_EINVAL, "rank size and overall size are inconsistent in dim %d", d);
+            s.rank_size[d] = (rs > 0 && nr == 1) ? os : (ri == nr - 1 ? last : per);
+            s.overall_size[d] = os;
+            s.rank_offset[d] = per * ri;
+        } else {
+            return set_error(YB_EINVAL, "domain size of dim '%s' was not set", s.spec.domain_dims[d].c_str());
+        }
+    }
+    return 0;
+}
+
+static void compute_var_geometry(Solution& s, Var& v) {
+    const int align_elems = 128 / v.elem_bytes;  // 128-B rows
+    int nd = int(v.dims.size());
+    int last_domain = -1;
+    for (int i = 0; i < nd; i++)
+        if (v.dims[i].spec.kind == DIM_DOMAIN) last_domain = i;
+    for (int i = 0; i < nd; i++) {
+        Dim& d = v.dims[i];
+        if (d.spec.kind == DIM_STEP) { d.domain = v.spec.step_alloc; d.alloc = d.domain; d.stride = 0; continue; }
+        if (d.spec.kind == DIM_MISC) { d.domain = d.spec.misc_size; d.alloc = d.domain; d.pad_l = d.pad_r = 0; continue; }
+        int dd = d.spec.domain_index;
+        d.domain = s.rank_size[dd];
+        d.rank_offset = s.rank_offset[dd];
+        int64_t pl = std::max({d.spec.halo_l, d.min_pad_l, s.min_pad[dd]});
+        int64_t pr = std::max({d.spec.halo_r, d.min_pad_r, s.min_pad[dd]});
+        if (i == nd - 1 && i == last_domain) {
+            // unit-stride dim: domain origin on a 128-B boundary, pitch a multiple of 128 B
+            pl = (pl + align_elems - 1) / align_elems * align_elems;
+            int64_t a = pl + d.domain + pr;
+            a = (a + align_elems - 1) / align_elems * align_elems;
+            pr = a - pl - d.domain;
+        }
+        d.pad_l = pl; d.pad_r = pr;
+        d.alloc = pl + d.domain + pr;
+    }
+    int64_t stride = 1;
+    for (int i = nd - 1; i >= 0; i--) {
+        Dim& d = v.dims[i];
+        if (d.spec.kind == DIM_STEP) continue;
+        d.stride = stride;
+        stride *= d.alloc;
+    }
+    v.slot_elems = std::max<int64_t>(stride, 1);
+    // keep every slot 256-B aligned
+    int64_t a256 = 256 / v.elem_bytes;
+    v.slot_elems = (v.slot_elems + a256 - 1) / a256 * a256;
+    v.first_valid_step = 0;
+}
+
+static int ensure_stage(Solution& s, size_t bytes) {
+    if (s.stage_bytes >= bytes) return 0;
+    if (s.stage_dev) cudaFree(s.stage_dev);
+    s.stage_dev = nullptr; s.stage_bytes = 0;
+    YB_CUDA(cudaMalloc(&s.stage_dev, bytes));
+    s.stage_bytes = bytes;
+    return 0;
+}
+
+// Resolve a [first,last] slice (global indices, step first) into step range + BoxCopy.
+struct Slice {
+    int64_t t0 = 0, t1 = 0;
+    BoxCopy bc{};
+    int64_t elems_per_step = 1;
+    int64_t g0[3] = {0, 0, 0};
+};
+
+static int resolve_slice(const Solution& s, const Var& v, const int64_t* first, const int64_t* last, bool check_steps, Slice& sl) {
+    int nd = int(v.dims.size());
+    int k = 0;
+    sl.bc.nd = 0; sl.bc.var_off = 0; sl.elems_per_step = 1;
+    int nns = nd - (v.has_step() ? 1 : 0);
+    if (nns > 4) return set_error(YB_EUNSUPPORTED, "var '%s': more than 4 non-step dims", v.spec.name.c_str());
+    for (int i = 0; i < nd; i++) {
+        const Dim& d = v.dims[i];
+        int64_t f = first[i], l = last[i];
+        if (l < f) return set_error(YB_ERANGE, "var '%s' dim '%s': last index %lld < first %lld", v.spec.name.c_str(), d.spec.name.c_str(), (long long)l, (long long)f);
+        if (d.spec.kind == DIM_STEP) {
+            if (check_steps && (f < v.first_valid_step || l > v.last_valid_step()))
+                return set_error(YB_ERANGE, "var '%s': step indices [%lld,%lld] outside the valid steps [%lld,%lld]", v.spec.name.c_str(),
+                                 (long long)f, (long long)l, (long long)v.first_valid_step, (long long)v.last_valid_step());
+            if (l - f + 1 > v.step_alloc())
+                return set_error(YB_ERANGE, "var '%s': step range longer than the %d allocated steps", v.spec.name.c_str(), v.step_alloc());
+            sl.t0 = f; sl.t1 = l;
+            continue;
+        }
+        int64_t lo, hi;  // first/last local (allocated) global index
+        if (d.spec.kind == DIM_DOMAIN) { lo = d.rank_offset - d.pad_l; hi = d.rank_offset + d.domain + d.pad_r - 1; }
+        else { lo = d.spec.misc_first; hi = d.spec.misc_first + d.domain - 1; }
+        if (f < lo || l > hi)
+            return set_error(YB_ERANGE, "var '%s' dim '%s': indices [%lld,%lld] outside the allocation [%lld,%lld]", v.spec.name.c_str(),
+                             d.spec.name.c_str(), (long long)f, (long long)l, (long long)lo, (long long)hi);
+        sl.bc.n[k] = l - f + 1;
+        sl.bc.var_stride[k] = d.stride;
+        sl.bc.var_off += (f - lo) * d.stride;
+        sl.elems_per_step *= sl.bc.n[k];
+        k++;
+    }
+    sl.bc.nd = k;
+    // global index triple of the box origin (left padded with 0)
+    int kk = 0;
+    for (int i = 0; i < nd; i++) {
+        if (v.dims[i].spec.kind == DIM_STEP) continue;
+        if (k <= 3) sl.g0[3 - k + kk] = first[i];
+        kk++;
+    }
+    (void)s;
+    return 0;
+}
+
+static int slice_copy(Solution& s, int var, void* buf, const int64_t* first, const int64_t* last, int64_t* n_done, bool to_var, bool buf_on_device) {
+    if (int rc = check_var(&s, var)) return rc;
+    if (!s.prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
+    if (!buf) return set_error(YB_EINVAL, "null buffer");
+    Var& v = s.vars[var];
+    Slice sl;
+    // writes do not check the step window (set_element semantics); reads do.
+    if (int rc = resolve_slice(s, v, first, last, !to_var, sl)) return rc;
+    YB_CUDA(cudaSetDevice(s.device));
+    cudaStream_t st = s.stream();
+    const int eb = v.elem_bytes;
+    int64_t done = 0;
+    // chunk along the outermost box dim so the staging buffer stays bounded
+    const size_t CHUNK = size_t(256) << 20;
+    for (int64_t t = sl.t0; t <= sl.t1; t++) {
+        char* slot = v.slot_ptr(v.slot_of(t));
+        char* hb = static_cast<char*>(buf) + size_t(t - sl.t0) * sl.elems_per_step * eb;
+        if (buf_on_device) {
+            if (int rc = launch_box_copy(slot, hb, sl.bc, eb, to_var, st)) return rc;
+        } else if (sl.bc.nd == 0) {
+            if (to_var) YB_CUDA(cudaMemcpyAsync(slot + sl.bc.var_off * eb, hb, eb, cudaMemcpyHostToDevice, st));
+            else YB_CUDA(cudaMemcpyAsync(hb, slot + sl.bc.var_off * eb, eb, cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaStreamSynchronize(st));
+        } else {
+            int64_t inner = sl.elems_per_step / sl.bc.n[0];
+            int64_t rows_per_chunk = std::max<int64_t>(1, int64_t(CHUNK / std::max<size_t>(1, size_t(inner) * eb)));
+            rows_per_chunk = std::min(rows_per_chunk, sl.bc.n[0]);
+            if (int rc = ensure_stage(s, size_t(rows_per_chunk) * inner * eb)) return rc;
+            for (int64_t r0 = 0; r0 < sl.bc.n[0]; r0 += rows_per_chunk) {
+                int64_t nr = std::min(rows_per_chunk, sl.bc.n[0] - r0);
+                BoxCopy bc = sl.bc;
+                bc.n[0] = nr;
+                bc.var_off += r0 * sl.bc.var_stride[0];
+                size_t nb = size_t(nr) * inner * eb;
+                char* hchunk = hb + size_t(r0) * inner * eb;
+                if (to_var) {
+                    YB_CUDA(cudaMemcpyAsync(s.stage_dev, hchunk, nb, cudaMemcpyHostToDevice, st));
+                    if (int rc = launch_box_copy(slot, s.stage_dev, bc, eb, true, st)) return rc;
+                } else {
+                    if (int rc = launch_box_copy(slot, s.stage_dev, bc, eb, false, st)) return rc;
+                    YB_CUDA(cudaMemcpyAsync(hchunk, s.stage_dev, nb, cudaMemcpyDeviceToHost, st));
+                }
+                YB_CUDA(cudaStreamSynchronize(st));  // staging buffer is reused
+            }
+        }
+        done += sl.elems_per_step;
+        if (to_var) v.update_valid_step(t);
+    }
+    if (to_var && s.halo) halo_mark_dirty(s, var);
+    if (n_done) *n_done = done;
+    return 0;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+// ===============================================================================================
+// C ABI
+// ===============================================================================================
+extern "C" {
+
+const char* yb_version_string(void) { return "4.05.04-b200.r1"; }
+const char* yb_last_error(void) { return g_err; }
+
+int yb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+int yb_num_stencils(void) { return registry_size(); }
+const char* yb_stencil_name(int i) { return registry_name(i); }
+
+int yb_solution_create(yb_solution** out, const char* stencil, int radius, int elem_bytes) {
+    if (!out || !stencil) return set_error(YB_EINVAL, "null argument");
+    *out = nullptr;
+    auto s = std::make_unique<Solution>();
+    if (elem_bytes == 0) elem_bytes = 4;
+    if (elem_bytes != 4 && elem_bytes != 8) return set_error(YB_EINVAL, "element bytes must be 4 or 8");
+    if (int rc = registry_create(stencil, radius, elem_bytes, s->spec, s->engine)) return rc;
+    s->ndd = int(s->spec.domain_dims.size());
+    for (auto& vs : s->spec.vars) {
+        Var v;
+        v.spec = vs;
+        v.elem_bytes = s->spec.elem_bytes;
+        for (auto& ds : vs.dims) { Dim d; d.spec = ds; v.dims.push_back(d); }
+        s->vars.push_back(std::move(v));
+    }
+    *out = reinterpret_cast<yb_solution*>(s.release());
+    return 0;
+}
+
+#define SOL(s) reinterpret_cast<Solution*>(s)
+#define CSOL(s) reinterpret_cast<const Solution*>(s)
+
+int yb_solution_destroy(yb_solution* s) {
+    delete SOL(s);
+    return 0;
+}
+const char* yb_solution_name(const yb_solution* s) { return s ? CSOL(s)->spec.name.c_str() : ""; }
+const char* yb_solution_target(const yb_solution*) { return "sm_100a"; }
+int yb_solution_elem_bytes(const yb_solution* s) { return s ? CSOL(s)->spec.elem_bytes : 0; }
+int yb_solution_num_domain_dims(const yb_solution* s) { return s ? CSOL(s)->ndd : 0; }
+const char* yb_solution_domain_dim_name(const yb_solution* s, int i) {
+    if (check_dim(CSOL(s), i)) return "";
+    return CSOL(s)->spec.domain_dims[i].c_str();
+}
+const char* yb_solution_step_dim_name(const yb_solution* s) { return s ? CSOL(s)->spec.step_dim.c_str() : ""; }
+
+static int not_prepared(Solution* s, const char* what) {
+    if (s->prepared) return set_error(YB_ESTATE, "%s is not allowed after prepare_solution()", what);
+    return 0;
+}
+
+int yb_set_rank_domain_size(yb_solution* s_, int dim, int64_t n) {
+    Solution* s = SOL(s_);
+    if (int rc = check_dim(s, dim)) return rc;
+    if (int rc = not_prepared(s, "set_rank_domain_size")) return rc;
+    if (n < 1) return set_error(YB_EINVAL, "domain size must be positive");
+    s->req_rank_size[dim] = n; s->req_overall_size[dim] = 0;
+    return 0;
+}
+int yb_set_overall_domain_size(yb_solution* s_, int dim, int64_t n) {
+    Solution* s = SOL(s_);
+    if (int rc = check_dim(s, dim)) return rc;
+    if (int rc = not_prepared(s, "set_overall_domain_size")) return rc;
+    if (n < 1) return set_error(YB_EINVAL, "domain size must be positive");
+    s->req_overall_size[dim] = n; s->req_rank_size[dim] = 0;
+    return 0;
+}
+int yb_set_num_ranks(yb_solution* s_, int dim, int64_t n) {
+    Solution* s = SOL(s_);
+    if (int rc = check_dim(s, dim)) return rc;
+    if (int rc = not_prepared(s, "set_num_ranks")) return rc;
+    if (n < 1) return set_error(YB_EINVAL, "number of ranks must be positive");
+    s->num_ranks[dim] = n;
+    return 0;
+}
+int yb_set_rank_index(yb_solution* s_, int dim, int64_t i) {
+    Solution* s = SOL(s_);
+    if (int rc = check_dim(s, dim)) return rc;
+    if (int rc = not_prepared(s, "set_rank_index")) return rc;
+    s->rank_index[dim] = i;
+    return 0;
+}
+int yb_set_min_pad_size(yb_solution* s_, int dim, int64_t n) {
+    Solution* s = SOL(s_);
+    if (int rc = check_dim(s, dim)) return rc;
+    if (int rc = not_prepared(s, "set_min_pad_size")) return rc;
+    if (n < 0) return set_error(YB_EINVAL, "pad must be non-negative");
+    s->min_pad[dim] = n;
+    return 0;
+}
+int64_t yb_get_rank_domain_size(const yb_solution* s, int dim) {
+    if (check_dim(CSOL(s), dim)) return -1;
+    return CSOL(s)->prepared ? CSOL(s)->rank_size[dim] : CSOL(s)->req_rank_size[dim];
+}
+int64_t yb_get_overall_domain_size(const yb_solution* s, int dim) {
+    if (check_dim(CSOL(s), dim)) return -1;
+    return CSOL(s)->prepared ? CSOL(s)->overall_size[dim] : CSOL(s)->req_overall_size[dim];
+}
+int64_t yb_get_num_ranks(const yb_solution* s, int dim) { return check_dim(CSOL(s), dim) ? -1 : CSOL(s)->num_ranks[dim]; }
+int64_t yb_get_rank_index(const yb_solution* s, int dim) { return check_dim(CSOL(s), dim) ? -1 : CSOL(s)->rank_index[dim]; }
+int64_t yb_get_first_rank_domain_index(const yb_solution* s, int dim) { return check_dim(CSOL(s), dim) ? -1 : CSOL(s)->rank_offset[dim]; }
+int64_t yb_get_last_rank_domain_index(const yb_solution* s, int dim) {
+    return check_dim(CSOL(s), dim) ? -1 : CSOL(s)->rank_offset[dim] + CSOL(s)->rank_size[dim] - 1;
+}
+
+int yb_set_option(yb_solution* s_, const char* key, const char* value) {
+    Solution* s = SOL(s_);
+    if (!s || !key || !value) return set_error(YB_EINVAL, "null argument");
+    std::string k = key, v = value;
+    if (k == "fp_mode") {
+        int m = atoi(value);
+        if (m < 0 || m > 2) return set_error(YB_EINVAL, "fp_mode must be 0, 1 or 2");
+        s->fp_mode = m;
+    } else if (k == "overlap_comms" || k == "min_exterior") {
+        // consumed by the halo engine at run time
+    } else if (s->engine->set_option(*s, k, v) != 0) {
+        return set_error(YB_EINVAL, "unknown option '%s'", key);
+    }
+    s->options[k] = v;
+    return 0;
+}
+int yb_get_option(const yb_solution* s_, const char* key, char* value, size_t n) {
+    const Solution* s = CSOL(s_);
+    if (!s || !key || !value || !n) return set_error(YB_EINVAL, "null argument");
+    std::string v;
+    if (std::string(key) == "fp_mode") v = std::to_string(s->fp_mode);
+    else if (!s->engine->get_option(*s, key, v)) {
+        auto it = s->options.find(key);
+        if (it == s->options.end()) return set_error(YB_EINVAL, "unknown option '%s'", key);
+        v = it->second;
+    }
+    snprintf(value, n, "%s", v.c_str());
+    return 0;
+}
+int yb_set_stream(yb_solution* s_, void* st) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    s->user_stream = static_cast<cudaStream_t>(st);
+    s->use_user_stream = true;
+    return 0;
+}
+
+int yb_solution_prepare(yb_solution* s_, int device) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (s->prepared) return set_error(YB_ESTATE, "solution already prepared");
+    int ndev = yb_device_count();
+    if (ndev <= 0) return set_error(YB_ECUDA, "no CUDA device available: the B200 engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return set_error(YB_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    if (int rc = compute_rank_geometry(*s)) return rc;
+    YB_CUDA(cudaSetDevice(device));
+    s->device = device;
+    if (!s->own_stream) YB_CUDA(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    if (!s->comm_stream) YB_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    for (auto& v : s->vars) {
+        compute_var_geometry(*s, v);
+        YB_CUDA(cudaMalloc(&v.dev, v.bytes()));
+        // the reference zero-initialises storage (alloc.cpp); halo cells outside the global domain
+        // keep whatever the user wrote there.
+        YB_CUDA(cudaMemsetAsync(v.dev, 0, v.bytes(), s->stream()));
+    }
+    if (int rc = s->engine->prepare(*s)) return rc;
+    if (s->multi_rank()) {
+        if (int rc = halo_prepare(*s)) return rc;
+    }
+    YB_CUDA(cudaStreamSynchronize(s->stream()));
+    s->prepared = true;
+    memset(&s->stats, 0, sizeof s->stats);
+    return 0;
+}
+int yb_solution_is_prepared(const yb_solution* s) { return s && CSOL(s)->prepared; }
+
+int yb_num_vars(const yb_solution* s) { return s ? int(CSOL(s)->vars.size()) : 0; }
+int yb_var_index(const yb_solution* s, const char* name) {
+    if (!s || !name) return set_error(YB_EINVAL, "null argument");
+    for (size_t i = 0; i < CSOL(s)->vars.size(); i++)
+        if (CSOL(s)->vars[i].spec.name == name) return int(i);
+    return set_error(YB_EINVAL, "var '%s' not found in solution '%s'", name, CSOL(s)->spec.name.c_str());
+}
+
+int yb_var_info_get(const yb_solution* s_, int var, yb_var_info* out) {
+    const Solution* s = CSOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!out) return set_error(YB_EINVAL, "null output");
+    const Var& v = s->vars[var];
+    memset(out, 0, sizeof *out);
+    snprintf(out->name, YB_NAME_LEN, "%s", v.spec.name.c_str());
+    out->num_dims = int(v.dims.size());
+    out->elem_bytes = v.elem_bytes;
+    out->has_step = v.has_step();
+    out->step_alloc = v.step_alloc();
+    out->first_valid_step = v.first_valid_step;
+    out->last_valid_step = v.last_valid_step();
+    out->is_output = v.spec.is_output;
+    out->halo_exchange_l1_norm = v.spec.l1_norm;
+    out->slot_elems = v.slot_elems;
+    out->storage_bytes = int64_t(v.bytes());
+    for (int i = 0; i < out->num_dims && i < YB_MAX_DIMS; i++) {
+        const Dim& d = v.dims[i];
+        yb_dim_info& o = out->dims[i];
+        snprintf(o.name, YB_NAME_LEN, "%s", d.spec.name.c_str());
+        o.kind = d.spec.kind;
+        o.domain_index = d.spec.kind == DIM_DOMAIN ? d.spec.domain_index : -1;
+        o.rank_offset = d.rank_offset;
+        o.domain_size = d.spec.kind == DIM_STEP ? v.step_alloc() : (d.spec.kind == DIM_MISC ? d.spec.misc_size : d.domain);
+        o.left_halo = d.spec.halo_l; o.right_halo = d.spec.halo_r;
+        o.left_pad = d.pad_l; o.right_pad = d.pad_r;
+        o.alloc_size = d.alloc;
+        o.first_misc_index = d.spec.misc_first;
+        o.stride = d.stride;
+    }
+    return 0;
+}
+
+int yb_var_set_min_pad(yb_solution* s_, int var, int dim, int64_t left, int64_t right) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (int rc = not_prepared(s, "set_min_pad_size")) return rc;
+    Var& v = s->vars[var];
+    if (dim < 0 || dim >= int(v.dims.size()) || v.dims[dim].spec.kind != DIM_DOMAIN)
+        return set_error(YB_EINVAL, "var '%s': dim %d is not a domain dim", v.spec.name.c_str(), dim);
+    if (left >= 0) v.dims[dim].min_pad_l = left;
+    if (right >= 0) v.dims[dim].min_pad_r = right;
+    return 0;
+}
+
+int yb_var_set_slice(yb_solution* s, int var, const void* buf, const int64_t* first, const int64_t* last, int64_t* n) {
+    return slice_copy(*SOL(s), var, const_cast<void*>(buf), first, last, n, true, false);
+}
+int yb_var_get_slice(yb_solution* s, int var, void* buf, const int64_t* first, const int64_t* last, int64_t* n) {
+    return slice_copy(*SOL(s), var, buf, first, last, n, false, false);
+}
+int yb_var_set_slice_device(yb_solution* s, int var, const void* buf, const int64_t* first, const int64_t* last, int64_t* n) {
+    return slice_copy(*SOL(s), var, const_cast<void*>(buf), first, last, n, true, true);
+}
+int yb_var_get_slice_device(yb_solution* s, int var, void* buf, const int64_t* first, const int64_t* last, int64_t* n) {
+    return slice_copy(*SOL(s), var, buf, first, last, n, false, true);
+}
+
+int yb_var_set_all_same(yb_solution* s_, int var, double value) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
+    Var& v = s->vars[var];
+    YB_CUDA(cudaSetDevice(s->device));
+    if (int rc = launch_fill_all(v.dev, v.slot_elems * v.step_alloc(), v.elem_bytes, value, s->stream())) return rc;
+    if (s->halo) halo_mark_dirty(*s, var);
+    return 0;
+}
+
+int yb_var_set_slice_same(yb_solution* s_, int var, double value, const int64_t* first, const int64_t* last, int64_t* n_done) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
+    Var& v = s->vars[var];
+    Slice sl;
+    if (int rc = resolve_slice(*s, v, first, last, false, sl)) return rc;
+    YB_CUDA(cudaSetDevice(s->device));
+    for (int64_t t = sl.t0; t <= sl.t1; t++) {
+        if (int rc = launch_box_fill(v.slot_ptr(v.slot_of(t)), sl.bc, v.elem_bytes, value, s->stream())) return rc;
+        v.update_valid_step(t);
+    }
+    if (s->halo) halo_mark_dirty(*s, var);
+    if (n_done) *n_done = sl.elems_per_step * (sl.t1 - sl.t0 + 1);
+    return 0;
+}
+
+// first/last of the rank "halo box" (domain + halos) or domain box of a var at one step
+static void var_box(const Var& v, int64_t step, bool with_halo, int64_t* first, int64_t* last) {
+    for (size_t i = 0; i < v.dims.size(); i++) {
+        const Dim& d = v.dims[i];
+        if (d.spec.kind == DIM_STEP) { first[i] = last[i] = step; }
+        else if (d.spec.kind == DIM_MISC) { first[i] = d.spec.misc_first; last[i] = d.spec.misc_first + d.domain - 1; }
+        else {
+            first[i] = d.rank_offset - (with_halo ? d.spec.halo_l : 0);
+            last[i] = d.rank_offset + d.domain - 1 + (with_halo ? d.spec.halo_r : 0);
+        }
+    }
+}
+
+int yb_var_fill_hash(yb_solution* s_, int var, int64_t step, uint32_t seed, uint32_t salt, double lo, double hi) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
+    Var& v = s->vars[var];
+    int64_t first[YB_MAX_DIMS], last[YB_MAX_DIMS];
+    var_box(v, step, true, first, last);
+    Slice sl;
+    if (int rc = resolve_slice(*s, v, first, last, false, sl)) return rc;
+    YB_CUDA(cudaSetDevice(s->device));
+    if (int rc = launch_hash_fill(v.slot_ptr(v.slot_of(step)), sl.bc, sl.g0, v.elem_bytes, seed, salt, lo, hi, s->stream())) return rc;
+    v.update_valid_step(step);
+    if (s->halo) halo_mark_dirty(*s, var);
+    return 0;
+}
+
+int yb_var_checksum(yb_solution* s_, int var, int64_t step, uint64_t* out) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
+    if (!out) return set_error(YB_EINVAL, "null output");
+    Var& v = s->vars[var];
+    int64_t first[YB_MAX_DIMS], last[YB_MAX_DIMS];
+    var_box(v, step, false, first, last);
+    Slice sl;
+    if (int rc = resolve_slice(*s, v, first, last, true, sl)) return rc;
+    YB_CUDA(cudaSetDevice(s->device));
+    if (int rc = ensure_stage(*s, 256)) return rc;
+    if (int rc = launch_checksum(v.slot_ptr(v.slot_of(step)), sl.bc, sl.g0, v.elem_bytes, (unsigned long long*)s->stage_dev, s->stream())) return rc;
+    unsigned long long h = 0;
+    YB_CUDA(cudaMemcpyAsync(&h, s->stage_dev, 8, cudaMemcpyDeviceToHost, s->stream()));
+    YB_CUDA(cudaStreamSynchronize(s->stream()));
+    *out = h;
+    return 0;
+}
+
+int yb_var_device_ptr(yb_solution* s_, int var, int64_t step, void** out) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated");
+    if (!out) return set_error(YB_EINVAL, "null output");
+    Var& v = s->vars[var];
+    *out = v.slot_ptr(v.slot_of(step));
+    return 0;
+}
+
+// ---- run_solution ----------------------------------------------------------------------------------
+// Mirrors /root/reference/src/kernel/lib/context.cpp:220-624 for the no-wave-front case: for each
+// step, for each stage: [exterior slabs -> start exchange] -> interior -> finish exchange.
+int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (!s->prepared) return set_error(YB_ESTATE, "run_solution() called without calling prepare_solution() first");
+    if (last_step < first_step) return set_error(YB_EUNSUPPORTED, "reverse-time stepping is not supported by this engine");
+    YB_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream();
+    cudaEvent_t e0, e1;
+    YB_CUDA(cudaEventCreate(&e0));
+    YB_CUDA(cudaEventCreate(&e1));
+    YB_CUDA(cudaEventRecord(e0, st));
+    Box whole;
+    for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = d < s->ndd ? s->rank_size[d] : 1; }
+    int64_t pts = whole.points();
+    int rc = 0;
+    if (s->halo) rc = halo_exchange_all(*s, st);  // initial exchange of everything dirty (context.cpp:346)
+    for (int64_t t = first_step; t <= last_step && rc >= 0; t++) {
+        for (size_t sg = 0; sg < s->spec.stages.size() && rc >= 0; sg++) {
+            if (s->halo) {
+                rc = halo_run_stage(*s, int(sg), t, st);
+            } else {
+                rc = s->engine->launch(*s, int(sg), t, whole, st);
+                if (rc > 0) s->stats.kernel_launches += rc;
+            }
+            const StageSpec& sp = s->spec.stages[sg];
+            s->stats.num_writes_done += sp.writes * pts;
+            s->stats.num_reads_done += sp.reads * pts;
+            s->stats.est_fp_ops_done += sp.fp_ops * pts;
+            for (int vi : sp.outputs) s->vars[vi].update_valid_step(t + 1);
+        }
+        s->stats.num_steps_done++;
+    }
+    YB_CUDA(cudaEventRecord(e1, st));
+    s->pending_events.emplace_back(e0, e1);
+    return rc < 0 ? rc : 0;
+}
+
+int yb_solution_sync(yb_solution* s_) {
+    Solution* s = SOL(s_);
+    if (!s || !s->prepared) return set_error(YB_ESTATE, "solution not prepared");
+    YB_CUDA(cudaSetDevice(s->device));
+    YB_CUDA(cudaStreamSynchronize(s->stream()));
+    YB_CUDA(cudaStreamSynchronize(s->comm_stream));
+    return 0;
+}
+
+static int drain_events(Solution* s) {
+    for (auto& pe : s->pending_events) {
+        YB_CUDA(cudaEventSynchronize(pe.second));
+        float ms = 0;
+        YB_CUDA(cudaEventElapsedTime(&ms, pe.first, pe.second));
+        s->stats.elapsed_secs += double(ms) * 1e-3;
+        cudaEventDestroy(pe.first);
+        cudaEventDestroy(pe.second);
+    }
+    s->pending_events.clear();
+    return 0;
+}
+
+int yb_get_stats(yb_solution* s_, yb_stats* out) {
+    Solution* s = SOL(s_);
+    if (!s || !out) return set_error(YB_EINVAL, "null argument");
+    if (!s->prepared) return set_error(YB_ESTATE, "solution not prepared");
+    YB_CUDA(cudaSetDevice(s->device));
+    if (int rc = drain_events(s)) return rc;
+    s->stats.num_elements = 1;
+    for (int d = 0; d < s->ndd; d++) s->stats.num_elements *= s->overall_size[d];
+    *out = s->stats;
+    return 0;
+}
+
+int yb_clear_stats(yb_solution* s_) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (s->prepared) {
+        YB_CUDA(cudaSetDevice(s->device));
+        if (int rc = drain_events(s)) return rc;
+    }
+    memset(&s->stats, 0, sizeof s->stats);
+    return 0;
+}
+
+}  // extern "C"

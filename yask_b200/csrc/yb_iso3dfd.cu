@@ -1,0 +1,299 @@
+// iso3dfd engine: spec (what the reference compiler derives from
+// /root/reference/src/stencils/Iso3dfdStencil.cpp), FD coefficients,
+// TMA tensor maps and kernel launch logic.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "yb_core.h"
+#include "yb_iso3dfd.cuh"
+
+namespace yb {
+
+// ---- FD coefficients ----------------------------------------------------------------------------------
+// Fornberg's recurrence with the same operation order as the reference
+// (/root/reference/src/contrib/coefficients/fd_coeff.cpp:53-101, called through
+// get_center_fd_coefficients, /root/reference/src/common/fd_coeff2.cpp:49-57), then the x3 centre
+// weight and /50^2 scaling of Iso3dfdStencil.cpp:68-88, then the 16-significant-digit print/parse
+// round trip every constant takes through the reference's generated source (Cpp.cpp:39-53).
+static void center_fd_coeffs(int order, int radius, std::vector<double>& out) {
+    const int np = 2 * radius + 1;
+    std::vector<double> pts(np);
+    for (int i = 0; i < np; i++) pts[i] = double(i - radius);
+    // w[m][n][k]: weight of point k for derivative m using points 0..n
+    std::vector<double> w(size_t(order + 1) * np * np, 0.0);
+    auto W = [&](int m, int n, int k) -> double& { return w[(size_t(m) * np + n) * np + k]; };
+    W(0, 0, 0) = 1.0;
+    double c1 = 1.0;
+    for (int n = 1; n < np; n++) {
+        double c2 = 1.0;
+        const int mmax = std::min(n, order);
+        for (int k = 0; k < n; k++) {
+            const double c3 = pts[n] - pts[k];
+            c2 = c2 * c3;
+            for (int m = 0; m <= mmax; m++) {
+                double t = (pts[n] - 0.0) * W(m, n - 1, k);
+                if (m > 0) t -= m * W(m - 1, n - 1, k);
+                t *= 1.0 / c3;
+                if (t == 0.0) t = 0.0;
+                W(m, n, k) = t;
+            }
+        }
+        for (int m = 0; m <= mmax; m++) {
+            double t = 0.0;
+            if (m > 0) t += m * W(m - 1, n - 1, n - 1);
+            t -= (pts[n - 1] - 0.0) * W(m, n - 1, n - 1);
+            t *= c1 / c2;
+            if (t == 0.0) t = 0.0;
+            W(m, n, n) = t;
+        }
+        c1 = c2;
+    }
+    out.resize(np);
+    for (int i = 0; i < np; i++) out[i] = W(order, np - 1, i);
+}
+
+static double const_roundtrip(double v) {
+    if (double(int(v)) == v) return v;
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.15e", v);
+    return strtod(buf, nullptr);
+}
+
+void iso3dfd_coeffs(int radius, double* c) {
+    std::vector<double> full;
+    center_fd_coeffs(2, radius, full);
+    const double d2 = 50.0 * 50.0;
+    for (int i = 0; i <= 2 * radius; i++) {
+        if (i == radius) full[i] *= 3.0;
+        full[i] /= d2;
+    }
+    for (int r = 0; r <= radius; r++) c[r] = const_roundtrip(full[radius + r]);
+}
+
+StencilSpec iso3dfd_spec(int radius, int elem_bytes, bool) {
+    StencilSpec sp;
+    sp.name = "iso3dfd";
+    sp.description = "isotropic 3-D finite-difference wave equation, 2nd order in time, order 2*radius in space";
+    sp.domain_dims = {"x", "y", "z"};
+    sp.radius = radius;
+    sp.elem_bytes = elem_bytes;
+    VarSpec p;
+    p.name = "p";
+    p.step_alloc = 2;   // write-back of t+1 over t-1
+    p.is_output = true;
+    p.l1_norm = 1;
+    DimSpec t; t.name = "t"; t.kind = DIM_STEP;
+    p.dims.push_back(t);
+    const char* dn[3] = {"x", "y", "z"};
+    for (int d = 0; d < 3; d++) {
+        DimSpec ds; ds.name = dn[d]; ds.kind = DIM_DOMAIN; ds.domain_index = d; ds.halo_l = ds.halo_r = radius;
+        p.dims.push_back(ds);
+    }
+    VarSpec v;
+    v.name = "v";
+    v.step_alloc = 1;
+    for (int d = 0; d < 3; d++) {
+        DimSpec ds; ds.name = dn[d]; ds.kind = DIM_DOMAIN; ds.domain_index = d;
+        v.dims.push_back(ds);
+    }
+    sp.vars = {p, v};
+    StageSpec st;
+    st.name = "stage_1";
+    st.outputs = {0};
+    st.inputs = {0, 1};
+    // reference compiler counts for radius r: reads 6r+3, writes 1, fp ops 7r+5 (r=8: 51/1/61)
+    st.reads = 6 * radius + 3;
+    st.writes = 1;
+    st.fp_ops = 7 * radius + 5;
+    sp.stages = {st};
+    return sp;
+}
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D tiled map over one step slot of a var (dims x,y,z; z unit stride) with box (bz, by, 1).
+int make_map(CUtensorMap* map, const Var& v, int slot, int bz, int by) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return set_error(YB_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const Dim* dx = v.domain_dim(0);
+    const Dim* dy = v.domain_dim(1);
+    const Dim* dz = v.domain_dim(2);
+    cuuint64_t gdim[3] = {cuuint64_t(dz->alloc), cuuint64_t(dy->alloc), cuuint64_t(dx->alloc)};
+    cuuint64_t gstr[2] = {cuuint64_t(dy->stride) * 4, cuuint64_t(dx->stride) * 4};
+    cuuint32_t box[3] = {cuuint32_t(bz), cuuint32_t(by), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, v.slot_ptr(slot), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(YB_ECUDA, "cuTensorMapEncodeTiled failed with code %d", int(r));
+    return 0;
+}
+
+// Tile configurations of the TMA kernel that are compiled in.
+using TileA = IsoTile<8, 32, 16, 5>;   // 32 rows x 64 z, 512 threads, 5-stage ring (default)
+using TileB = IsoTile<8, 16, 32, 5>;   // 16 rows x 128 z
+
+template <class T>
+struct TileLaunch {
+    static int set_attr(int mode) {
+        cudaError_t e;
+        switch (mode) {
+            case 0: e = cudaFuncSetAttribute(iso3dfd_tma_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES); break;
+            case 1: e = cudaFuncSetAttribute(iso3dfd_tma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES); break;
+            default: e = cudaFuncSetAttribute(iso3dfd_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES); break;
+        }
+        if (e != cudaSuccess) return set_error(YB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return 0;
+    }
+    static void launch(int mode, int grid, cudaStream_t st, const IsoMaps& m, const IsoParams& p) {
+        switch (mode) {
+            case 0: iso3dfd_tma_kernel<T, 0><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(m, p); break;
+            case 1: iso3dfd_tma_kernel<T, 1><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(m, p); break;
+            default: iso3dfd_tma_kernel<T, 2><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(m, p); break;
+        }
+    }
+};
+
+struct IsoEngine : Engine {
+    int radius = 8;
+    double coef[ISO_MAX_R + 1] = {0};
+    std::string kernel = "auto";   // auto | tma | direct
+    int tile = 0;                  // 0 = TileA, 1 = TileB
+    int lx = 128;                  // planes per sweep chunk
+    int grid_override = 0;
+    int num_sms = 148;
+    bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
+    IsoMaps maps[2][2];            // [tile][cur slot]
+    bool maps_ok = false;
+
+    int set_option(Solution&, const std::string& k, const std::string& v) override {
+        if (k == "kernel") {
+            if (v != "auto" && v != "tma" && v != "direct") return YB_EINVAL;
+            kernel = v;
+        } else if (k == "tile") { tile = atoi(v.c_str()) ? 1 : 0; }
+        else if (k == "lx") { lx = std::max(1, atoi(v.c_str())); }
+        else if (k == "grid") { grid_override = std::max(0, atoi(v.c_str())); }
+        else return YB_EINVAL;
+        return 0;
+    }
+    bool get_option(const Solution&, const std::string& k, std::string& v) const override {
+        if (k == "kernel") v = kernel;
+        else if (k == "tile") v = std::to_string(tile);
+        else if (k == "lx") v = std::to_string(lx);
+        else if (k == "grid") v = std::to_string(grid_override);
+        else return false;
+        return true;
+    }
+
+    int prepare(Solution& s) override {
+        radius = s.spec.radius;
+        if (radius < 1 || radius > ISO_MAX_R) return set_error(YB_EUNSUPPORTED, "iso3dfd radius must be in 1..%d", ISO_MAX_R);
+        if (s.spec.elem_bytes != 4) return set_error(YB_EUNSUPPORTED, "iso3dfd: only 4-byte elements are implemented in this round");
+        iso3dfd_coeffs(radius, coef);
+        cudaDeviceProp prop;
+        YB_CUDA(cudaGetDeviceProperties(&prop, s.device));
+        num_sms = prop.multiProcessorCount;
+        maps_ok = false;
+        if (radius == 8 && prop.major >= 9) {
+            const Var& p = s.vars[0];
+            const Var& v = s.vars[1];
+            for (int tl = 0; tl < 2; tl++) {
+                const int TY = tl ? TileB::TY : TileA::TY, TZ = tl ? TileB::TZ : TileA::TZ;
+                const int HP = tl ? TileB::HP : TileA::HP, HR = tl ? TileB::HROWS : TileA::HROWS;
+                for (int cur = 0; cur < 2; cur++) {
+                    IsoMaps& m = maps[tl][cur];
+                    if (int rc = make_map(&m.h, p, cur, HP, HR)) return rc;
+                    if (int rc = make_map(&m.c, p, cur, TZ, TY)) return rc;
+                    if (int rc = make_map(&m.p, p, 1 - cur, TZ, TY)) return rc;
+                    if (int rc = make_map(&m.v, v, 0, TZ, TY)) return rc;
+                }
+            }
+            maps_ok = true;
+        }
+        return 0;
+    }
+
+    void fill_params(const Solution& s, int cur, const Box& box, IsoParams& P) const {
+        const Var& p = s.vars[0];
+        const Var& v = s.vars[1];
+        const Dim *px = p.domain_dim(0), *py = p.domain_dim(1), *pz = p.domain_dim(2);
+        const Dim *vx = v.domain_dim(0), *vy = v.domain_dim(1), *vz = v.domain_dim(2);
+        P.out = reinterpret_cast<float*>(p.slot_ptr(1 - cur)) + p.origin_offset();
+        P.cur = reinterpret_cast<const float*>(p.slot_ptr(cur)) + p.origin_offset();
+        P.vel = reinterpret_cast<const float*>(v.slot_ptr(0)) + v.origin_offset();
+        P.out_sx = px->stride; P.out_sy = py->stride;
+        P.v_sx = vx->stride; P.v_sy = vy->stride;
+        P.nx = int(px->domain); P.ny = int(py->domain); P.nz = int(pz->domain);
+        P.x_begin = int(box.b[0]); P.x_end = int(box.e[0]);
+        P.y_begin = int(box.b[1]); P.y_end = int(box.e[1]);
+        P.z_begin = int(box.b[2]); P.z_end = int(box.e[2]);
+        P.pad_x = int(px->pad_l); P.pad_y = int(py->pad_l); P.pad_z = int(pz->pad_l);
+        P.vpad_x = int(vx->pad_l); P.vpad_y = int(vy->pad_l); P.vpad_z = int(vz->pad_l);
+        for (int r = 0; r <= ISO_MAX_R; r++) P.c[r] = r <= radius ? float(coef[r]) : 0.f;
+    }
+
+    int launch(Solution& s, int, int64_t t, const Box& box, cudaStream_t st) override {
+        if (box.empty()) return 0;
+        const Var& p = s.vars[0];
+        const int cur = p.slot_of(t);
+        IsoParams P{};
+        fill_params(s, cur, box, P);
+        const int mode = s.fp_mode;
+        bool use_tma = maps_ok && kernel != "direct";
+        if (kernel == "auto") {
+            // thin slabs in y/z (halo faces) are not worth a tile sweep
+            if (box.e[1] - box.b[1] < 8 || box.e[2] - box.b[2] < 16) use_tma = false;
+        }
+        if (kernel == "tma" && !maps_ok) return set_error(YB_EUNSUPPORTED, "TMA kernel needs radius 8 and sm_90+");
+        if (use_tma) {
+            const int TY = tile ? TileB::TY : TileA::TY, TZ = tile ? TileB::TZ : TileA::TZ;
+            P.nty = int((box.e[1] - box.b[1] + TY - 1) / TY);
+            P.ntz = int((box.e[2] - box.b[2] + TZ - 1) / TZ);
+            const int64_t nxb = box.e[0] - box.b[0];
+            P.lx = int(std::min<int64_t>(lx, nxb));
+            P.nchunks = int((nxb + P.lx - 1) / P.lx);
+            const int64_t nunits = int64_t(P.nty) * P.ntz * P.nchunks;
+            int grid = int(std::min<int64_t>(nunits, grid_override > 0 ? grid_override : num_sms));
+            if (!attr_set[tile][mode]) {
+                int rc = tile ? TileLaunch<TileB>::set_attr(mode) : TileLaunch<TileA>::set_attr(mode);
+                if (rc) return rc;
+                attr_set[tile][mode] = true;
+            }
+            if (tile) TileLaunch<TileB>::launch(mode, grid, st, maps[1][cur], P);
+            else TileLaunch<TileA>::launch(mode, grid, st, maps[0][cur], P);
+        } else {
+            dim3 blk(128, 1, 1);
+            dim3 grd(unsigned((box.e[2] - box.b[2] + 127) / 128), unsigned(box.e[1] - box.b[1]), unsigned(box.e[0] - box.b[0]));
+            if (grd.y > 65535 || grd.z > 65535) return set_error(YB_EUNSUPPORTED, "direct kernel: domain too large in x or y");
+            switch (mode) {
+                case 0: iso3dfd_direct_kernel<0><<<grd, blk, 0, st>>>(P, radius); break;
+                case 1: iso3dfd_direct_kernel<1><<<grd, blk, 0, st>>>(P, radius); break;
+                default: iso3dfd_direct_kernel<2><<<grd, blk, 0, st>>>(P, radius); break;
+            }
+        }
+        YB_CUDA(cudaGetLastError());
+        return 1;
+    }
+};
+
+}  // namespace
+
+std::unique_ptr<Engine> make_iso3dfd_engine() { return std::unique_ptr<Engine>(new IsoEngine()); }
+
+}  // namespace yb

@@ -1,0 +1,304 @@
+// iso3dfd point-update kernels for sm_100a.
+//
+// Equation and association order: /root/reference/src/stencils/Iso3dfdStencil.cpp:63-137
+// (get_next_p) as canonicalised by the reference compiler ("-target pseudo", SURVEY.md
+// Appendix A) -- this replaces the generated stencil_iso3dfd_part_1::calc_vectors()
+// (emitter: /root/reference/src/compiler/lib/Cpp.cpp:377-1175) and the loop hierarchy that
+// calls it (/root/reference/src/kernel/lib/context.cpp:631-1174, stencil_calc.hpp:444-860).
+//
+//   acc = p*c0;  r=1..R: acc += (((((p[x-r]+p[x+r])+p[y-r])+p[y+r])+p[z-r])+p[z+r]) * c_r
+//   p(t+1) = ((2*p) - p(t-1)) + acc*v
+//
+// FP modes (see oracle/yask_oracle.c): 0 strict IEEE mul/add, 1 canonical FMA,
+// 2 = FMA pattern GCC 13 emits for the reference's default build (bit-exact vs it).
+#pragma once
+#include "yb_ptx.cuh"
+
+namespace yb {
+
+constexpr int ISO_MAX_R = 8;
+
+struct IsoParams {
+    float* out;             // &p_next[domain origin]; written in place over p(t-1)
+    long long out_sx, out_sy;  // element strides of the p arrays (z stride is 1)
+    const float* cur;       // &p_cur[domain origin]  (naive kernel only)
+    const float* vel;       // &v[domain origin]      (naive kernel only)
+    long long v_sx, v_sy;
+    int nx, ny, nz;         // rank-domain sizes
+    int x_begin, x_end;     // sub-range of x planes to compute (boundary/interior split)
+    int y_begin, y_end;
+    int z_begin, z_end;
+    int pad_x, pad_y, pad_z;    // p arrays: alloc index of domain origin (TMA coordinates)
+    int vpad_x, vpad_y, vpad_z; // v array: same
+    int nty, ntz, nchunks, lx;  // tiling of [begin,end): tiles in y,z; chunks of lx planes in x
+    float c[ISO_MAX_R + 1];
+};
+
+template <int MODE>
+__device__ __forceinline__ float iso_group(float acc, float pc, float c0, float cr, float xm, float xp, float ym, float yp,
+                                           float zm, float zp, bool first) {
+    float s = __fadd_rn(xm, xp);
+    s = __fadd_rn(s, ym);
+    s = __fadd_rn(s, yp);
+    s = __fadd_rn(s, zm);
+    s = __fadd_rn(s, zp);
+    if (MODE == 0) {
+        if (first) acc = __fmul_rn(pc, c0);
+        return __fadd_rn(acc, __fmul_rn(s, cr));
+    } else if (MODE == 1) {
+        if (first) acc = __fmul_rn(pc, c0);
+        return __fmaf_rn(s, cr, acc);
+    } else {
+        if (first) return __fmaf_rn(pc, c0, __fmul_rn(s, cr));
+        return __fmaf_rn(s, cr, acc);
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float iso_final(float acc, float pc, float prev, float v) {
+    // 2*p is exact, so fma(2,p,-prev) == round((2*p) - prev): one instruction, same bits.
+    float lhs = __fmaf_rn(2.0f, pc, -prev);
+    if (MODE == 0) return __fadd_rn(lhs, __fmul_rn(acc, v));
+    return __fmaf_rn(acc, v, lhs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Reference-order direct kernel: one thread per point, straight global loads (through L1/L2).
+// Used for radii/shapes the tiled kernel does not cover and as the on-device cross-check of the
+// tiled kernel at sizes the CPU oracle cannot reach.  Any radius 1..8.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) iso3dfd_direct_kernel(IsoParams P, int R) {
+    const int z = P.z_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = P.y_begin + blockIdx.y;
+    const int x = P.x_begin + blockIdx.z;
+    if (z >= P.z_end || y >= P.y_end || x >= P.x_end) return;
+    const long long o = (long long)x * P.out_sx + (long long)y * P.out_sy + z;
+    const float* pc = P.cur + o;
+    const float center = pc[0];
+    float acc = 0.f;
+    for (int r = 1; r <= R; r++) {
+        acc = iso_group<MODE>(acc, center, P.c[0], P.c[r], pc[-r * P.out_sx], pc[r * P.out_sx], pc[-r * P.out_sy],
+                              pc[r * P.out_sy], pc[-r], pc[r], r == 1);
+    }
+    const float v = P.vel[(long long)x * P.v_sx + (long long)y * P.v_sy + z];
+    P.out[o] = iso_final<MODE>(acc, center, P.out[o], v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tiled TMA kernel ("2.5-D sweep").
+//
+// A CTA owns a (TY x TZ) column of the (y,z) plane and sweeps it along x (the outermost,
+// largest-stride axis) over a chunk of `lx` planes.  Thread (row j, quad l) computes the four
+// z-consecutive points z0+4l..+3 of row j for every plane of the sweep.
+//
+//   * x neighbours: a 2R+1 deep register queue of the thread's own quad, rotated by *static*
+//     renaming (the sweep loop is unrolled 2R+1 times) -- no data movement.
+//   * y,z neighbours: the current plane with halo, (TY+2R) x (TZ+2HZ) floats, staged in shared
+//     memory by ONE TMA box load (cp.async.bulk.tensor.3d, box depth 1).
+//   * the queue is fed by a second, halo-less TMA box R planes ahead of the current one;
+//     p(t-1) and v tiles arrive the same way (evict-first: they are streamed exactly once).
+//   * a ring of STAGES such stage buffers is filled by one elected producer thread running
+//     STAGES-1 sweep steps ahead; full/empty mbarriers, no __syncthreads in the sweep loop.
+//   * results leave as 128-bit coalesced stores straight over p(t-1) (the reference's
+//     2-slot write-back, /root/reference/src/compiler/lib/Var.cpp:435-464).
+//
+// Persistent grid: one CTA per SM; work units (y-tile, z-tile, x-chunk) are dealt round-robin so
+// that the units in flight at any time are neighbours in (y,z) and share their halos through L2.
+// ---------------------------------------------------------------------------------------------
+template <int R_, int TY_, int TZQ_, int STAGES_>
+struct IsoTile {
+    static constexpr int R = R_, TY = TY_, TZQ = TZQ_, STAGES = STAGES_;
+    static constexpr int TZ = 4 * TZQ;
+    static constexpr int HZ = (R + 3) / 4 * 4;      // z halo kept in smem (multiple of 4 for LDS.128 alignment)
+    static constexpr int ZQ = HZ / 4;               // halo quads each side
+    static constexpr int HP = TZ + 2 * HZ;          // pitch of the haloed plane
+    static constexpr int HROWS = TY + 2 * R;
+    static constexpr int THREADS = TY * TZQ;
+    static constexpr int NWARPS = THREADS / 32;
+    static constexpr int QN = 2 * R + 1;            // register queue depth
+    static constexpr uint32_t H_BYTES = HROWS * HP * 4;
+    static constexpr uint32_t C_BYTES = TY * TZ * 4;
+    static constexpr uint32_t H_OFF = 0;
+    static constexpr uint32_t C_OFF = (H_BYTES + 127) / 128 * 128;
+    static constexpr uint32_t P_OFF = C_OFF + C_BYTES;
+    static constexpr uint32_t V_OFF = P_OFF + C_BYTES;
+    static constexpr uint32_t STAGE_BYTES = V_OFF + C_BYTES;
+    static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr uint32_t SMEM_BYTES = BAR_OFF + 2 * STAGES * 8 + 128;  // +128: manual alignment slack
+    static_assert(THREADS % 32 == 0, "whole warps");
+    static_assert(C_BYTES % 128 == 0, "TMA destination alignment");
+};
+
+struct IsoMaps {
+    CUtensorMap h;  // p_cur, box (TZ+2HZ, TY+2R, 1)
+    CUtensorMap c;  // p_cur, box (TZ, TY, 1)
+    CUtensorMap p;  // p_prev, box (TZ, TY, 1)
+    CUtensorMap v;  // v,      box (TZ, TY, 1)
+};
+
+// Sweep position of a CTA in its flattened (unit, iteration) sequence.
+struct IsoCursor {
+    int unit;      // current work unit
+    int it;        // iteration within unit: 0 .. n_it-1
+    int n_it;      // lx_unit + 2R
+    int x0, y0, z0;  // unit origin (domain coordinates)
+    int stage;
+    uint32_t phase;
+};
+
+template <class T>
+__device__ __forceinline__ void iso_unit_setup(IsoCursor& cu, const IsoParams& P) {
+    int u = cu.unit;
+    const int tz = u % P.ntz; u /= P.ntz;
+    const int ty = u % P.nty; u /= P.nty;
+    cu.z0 = P.z_begin + tz * T::TZ;
+    cu.y0 = P.y_begin + ty * T::TY;
+    cu.x0 = P.x_begin + u * P.lx;
+    const int lxu = min(P.lx, P.x_end - cu.x0);
+    cu.n_it = lxu + 2 * T::R;
+    cu.it = 0;
+}
+
+template <class T, int MODE>
+__global__ void __launch_bounds__(T::THREADS, 1)
+iso3dfd_tma_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ IsoParams P) {
+    constexpr int R = T::R, QN = T::QN, ZQ = T::ZQ;
+    extern __shared__ uint8_t smem_raw[];
+    // 128-B align the dynamic smem base (TMA destinations need it).
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbase + T::BAR_OFF);
+    uint64_t* empty_bar = full_bar + T::STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int nunits = P.nty * P.ntz * P.nchunks;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&M.h); tma_prefetch_desc(&M.c); tma_prefetch_desc(&M.p); tma_prefetch_desc(&M.v);
+        for (int s = 0; s < T::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], T::NWARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // ---- producer state (thread 0 only) -------------------------------------------------
+    IsoCursor pr;
+    pr.unit = blockIdx.x; pr.stage = 0; pr.phase = 0;
+    const uint64_t pol_stream = l2_policy_evict_first();
+    bool pr_live = (tid == 0) && (pr.unit < nunits);
+    if (pr_live) iso_unit_setup<T>(pr, P);
+
+    auto produce_one = [&]() {
+        // wait until every consumer warp released this stage (first pass: passes immediately)
+        mbar_wait(&empty_bar[pr.stage], pr.phase ^ 1u);
+        uint8_t* st = sbase + pr.stage * T::STAGE_BYTES;
+        uint64_t* fb = &full_bar[pr.stage];
+        const bool compute = pr.it >= 2 * R;
+        mbar_arrive_expect_tx(fb, compute ? (T::H_BYTES + 3 * T::C_BYTES) : T::C_BYTES);
+        const int xc = pr.x0 - R + pr.it;  // plane entering the x queue
+        tma_load_3d(st + T::C_OFF, &M.c, fb, P.pad_z + pr.z0, P.pad_y + pr.y0, P.pad_x + xc);
+        if (compute) {
+            const int xo = pr.x0 + pr.it - 2 * R;  // plane being computed
+            tma_load_3d(st + T::H_OFF, &M.h, fb, P.pad_z + pr.z0 - T::HZ, P.pad_y + pr.y0 - R, P.pad_x + xo);
+            tma_load_3d_hint(st + T::P_OFF, &M.p, fb, P.pad_z + pr.z0, P.pad_y + pr.y0, P.pad_x + xo, pol_stream);
+            tma_load_3d_hint(st + T::V_OFF, &M.v, fb, P.vpad_z + pr.z0, P.vpad_y + pr.y0, P.vpad_x + xo, pol_stream);
+        }
+        if (++pr.stage == T::STAGES) { pr.stage = 0; pr.phase ^= 1u; }
+        if (++pr.it == pr.n_it) {
+            pr.unit += gridDim.x;
+            if (pr.unit < nunits) iso_unit_setup<T>(pr, P); else pr_live = false;
+        }
+    };
+    if (tid == 0) {
+        for (int k = 0; k < T::STAGES - 1 && pr_live; k++) produce_one();
+    }
+
+    // ---- consumer -----------------------------------------------------------------------
+    const int row = tid / T::TZQ;          // 0..TY-1
+    const int quad = tid % T::TZQ;         // 0..TZQ-1
+    const uint32_t h_own = ((row + R) * T::HP + T::HZ + 4 * quad) * 4;  // byte offset of own quad in H
+    const uint32_t c_own = (row * T::TZ + 4 * quad) * 4;
+
+    IsoCursor cu;
+    cu.stage = 0; cu.phase = 0;
+    float4 q[QN];
+#pragma unroll
+    for (int k = 0; k < QN; k++) q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    for (cu.unit = blockIdx.x; cu.unit < nunits; cu.unit += gridDim.x) {
+        iso_unit_setup<T>(cu, P);
+        const int y = cu.y0 + row;
+        const int zq = cu.z0 + 4 * quad;
+        const bool row_ok = y < P.y_end;
+        const int nvalid = row_ok ? max(0, min(4, P.z_end - zq)) : 0;
+        float* out_col = P.out + (long long)y * P.out_sy + zq;
+
+        for (int itb = 0; itb < cu.n_it; itb += QN) {
+#pragma unroll
+            for (int u = 0; u < QN; u++) {
+                const int it = itb + u;
+                if (it >= cu.n_it) break;
+                // keep the ring full: issue the load STAGES-1 steps ahead
+                if (tid == 0 && pr_live) produce_one();
+
+                const uint8_t* st = sbase + cu.stage * T::STAGE_BYTES;
+                mbar_wait(&full_bar[cu.stage], cu.phase);
+
+                // newest plane (x0 - R + it) enters the queue slot u
+                q[u] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own);
+
+                if (it >= 2 * R) {
+                    const float* hp = reinterpret_cast<const float*>(st + T::H_OFF + h_own);
+                    // centre plane index in queue: it - R  -> slot (u - R) mod QN
+                    const float4 cen = q[(u + QN - R) % QN];
+                    // z window: quads -ZQ..+ZQ around own quad (centre taken from the queue)
+                    float zw[4 * (2 * ZQ + 1)];
+#pragma unroll
+                    for (int k = -ZQ; k <= ZQ; k++) {
+                        float4 t = (k == 0) ? cen : *reinterpret_cast<const float4*>(hp + 4 * k);
+                        zw[4 * (k + ZQ) + 0] = t.x; zw[4 * (k + ZQ) + 1] = t.y;
+                        zw[4 * (k + ZQ) + 2] = t.z; zw[4 * (k + ZQ) + 3] = t.w;
+                    }
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float pc[4] = {cen.x, cen.y, cen.z, cen.w};
+#pragma unroll
+                    for (int r = 1; r <= R; r++) {
+                        const float4 xm = q[(u + QN - R - r) % QN];
+                        const float4 xp = q[(u + QN - R + r) % QN];
+                        const float4 ym = *reinterpret_cast<const float4*>(hp - r * T::HP);
+                        const float4 yp = *reinterpret_cast<const float4*>(hp + r * T::HP);
+                        const float xm_[4] = {xm.x, xm.y, xm.z, xm.w}, xp_[4] = {xp.x, xp.y, xp.z, xp.w};
+                        const float ym_[4] = {ym.x, ym.y, ym.z, ym.w}, yp_[4] = {yp.x, yp.y, yp.z, yp.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            acc[i] = iso_group<MODE>(acc[i], pc[i], P.c[0], P.c[r], xm_[i], xp_[i], ym_[i], yp_[i],
+                                                     zw[4 * ZQ + i - r], zw[4 * ZQ + i + r], r == 1);
+                        }
+                    }
+                    const float4 pv = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own);
+                    const float4 vv = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own);
+                    float4 res;
+                    res.x = iso_final<MODE>(acc[0], pc[0], pv.x, vv.x);
+                    res.y = iso_final<MODE>(acc[1], pc[1], pv.y, vv.y);
+                    res.z = iso_final<MODE>(acc[2], pc[2], pv.z, vv.z);
+                    res.w = iso_final<MODE>(acc[3], pc[3], pv.w, vv.w);
+                    float* o = out_col + (long long)(cu.x0 + it - 2 * R) * P.out_sx;
+                    if (nvalid == 4) {
+                        stg128(o, res);
+                    } else if (nvalid > 0) {
+                        o[0] = res.x;
+                        if (nvalid > 1) o[1] = res.y;
+                        if (nvalid > 2) o[2] = res.z;
+                    }
+                }
+                // release the stage: one arrive per warp once all its lanes are done reading
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[cu.stage]);
+                if (++cu.stage == T::STAGES) { cu.stage = 0; cu.phase ^= 1u; }
+            }
+        }
+    }
+}
+
+}  // namespace yb
