@@ -58,6 +58,7 @@ if [ "${REF_ALL:-1}" = "1" ]; then
     build_kernel ssg "-fp64"        8
     build_kernel ssg "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
 fi
-# Drop the (large) intermediate build tree; keep bin/ and lib/ only.
+# Strip debug info (the reference builds with -g) and drop the (large) intermediate build tree.
+strip --strip-debug "$OUT"/lib/*.so "$OUT"/bin/*.exe "$OUT"/bin/ref_driver.* 2>/dev/null || true
 if [ "${KEEP_BUILD:-0}" != "1" ]; then rm -rf "$OUT/build"; fi
 echo "[build_ref] done: $(ls "$OUT/bin" | tr '\n' ' ')"

@@ -31,13 +31,13 @@ if __name__ == "__main__":
     n = (N, N, N)
     res = []
     base = None
-    for opts in [dict(kernel="direct"),
-                 dict(kernel="tma", tile=0, lx=128), dict(kernel="tma", tile=0, lx=64), dict(kernel="tma", tile=0, lx=256),
-                 dict(kernel="tma", tile=0, lx=1024),
-                 dict(kernel="tma", tile=1, lx=128), dict(kernel="tma", tile=1, lx=256),
-                 dict(kernel="tma", tile=0, lx=128, fp_mode=0),
-                 dict(kernel="tma", tile=0, lx=128, grid=296),
-                 ]:
+    import itertools
+    variants = [dict(kernel="tma", tile=0, lx=128)]
+    for tile in (2, 3):
+        for lx in (64, 128, 256, 1024):
+            variants.append(dict(kernel="tma", tile=tile, lx=lx))
+    variants += [dict(kernel="tma", tile=2, lx=128, fp_mode=0), dict(kernel="tma", tile=2, lx=128, grid=296)]
+    for opts in variants:
         steps = 3 if opts.get("kernel") == "direct" else 20
         g, ms, cs = run(n, steps, 3, **opts)
         print(json.dumps(dict(opts=opts, gpts=round(g, 2), ms_per_step=round(ms, 4), gbps=round(g*16, 1), checksum=cs)), flush=True)

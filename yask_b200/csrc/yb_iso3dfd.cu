@@ -145,48 +145,58 @@ int make_map(CUtensorMap* map, const Var& v, int slot, int bz, int by) {
     return 0;
 }
 
-// Tile configurations of the TMA kernel that are compiled in.
-using TileA = IsoTile<8, 32, 16, 5>;   // 32 rows x 64 z, 512 threads, 5-stage ring (default)
-using TileB = IsoTile<8, 16, 32, 5>;   // 16 rows x 128 z
+// Tile configurations of the TMA kernels that are compiled in.
+typedef void (*IsoKernelFn)(const IsoMaps, const IsoParams);
+struct TileCfg {
+    const char* name;
+    int ty, tz, hp, hrows, threads;
+    uint32_t smem;
+    IsoKernelFn fn[3];  // per FP mode
+};
 
 template <class T>
-struct TileLaunch {
-    static int set_attr(int mode) {
-        cudaError_t e;
-        switch (mode) {
-            case 0: e = cudaFuncSetAttribute(iso3dfd_tma_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES); break;
-            case 1: e = cudaFuncSetAttribute(iso3dfd_tma_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES); break;
-            default: e = cudaFuncSetAttribute(iso3dfd_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM_BYTES); break;
-        }
-        if (e != cudaSuccess) return set_error(YB_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        return 0;
-    }
-    static void launch(int mode, int grid, cudaStream_t st, const IsoMaps& m, const IsoParams& p) {
-        switch (mode) {
-            case 0: iso3dfd_tma_kernel<T, 0><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(m, p); break;
-            case 1: iso3dfd_tma_kernel<T, 1><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(m, p); break;
-            default: iso3dfd_tma_kernel<T, 2><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(m, p); break;
-        }
-    }
-};
+TileCfg cfg_gen1(const char* name) {
+    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
+                   {iso3dfd_tma_kernel<T, 0>, iso3dfd_tma_kernel<T, 1>, iso3dfd_tma_kernel<T, 2>}};
+}
+template <class T>
+TileCfg cfg_gen2(const char* name) {
+    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
+                   {iso3dfd_tma2_kernel<T, 0>, iso3dfd_tma2_kernel<T, 1>, iso3dfd_tma2_kernel<T, 2>}};
+}
+
+constexpr int NTILES = 4;
+const TileCfg& tile_cfg(int i) {
+    static const TileCfg cfgs[NTILES] = {
+        cfg_gen1<IsoTile<8, 32, 16, 5>>("gen1 32x64, 512 thr x 4 pts"),
+        cfg_gen1<IsoTile<8, 16, 32, 5>>("gen1 16x128, 512 thr x 4 pts"),
+        cfg_gen2<IsoTile2<8, 16, 16, 5>>("gen2 32x64, 256 thr x 8 pts (row pairs)"),
+        cfg_gen2<IsoTile2<8, 8, 32, 5>>("gen2 16x128, 256 thr x 8 pts (row pairs)"),
+    };
+    return cfgs[i];
+}
 
 struct IsoEngine : Engine {
     int radius = 8;
     double coef[ISO_MAX_R + 1] = {0};
     std::string kernel = "auto";   // auto | tma | direct
-    int tile = 0;                  // 0 = TileA, 1 = TileB
+    int tile = 2;                  // index into tile_cfg()
     int lx = 128;                  // planes per sweep chunk
     int grid_override = 0;
     int num_sms = 148;
-    bool attr_set[2][3] = {{false, false, false}, {false, false, false}};
-    IsoMaps maps[2][2];            // [tile][cur slot]
+    bool attr_set[NTILES][3] = {};
+    IsoMaps maps[NTILES][2];       // [tile][cur slot]
     bool maps_ok = false;
 
     int set_option(Solution&, const std::string& k, const std::string& v) override {
         if (k == "kernel") {
             if (v != "auto" && v != "tma" && v != "direct") return YB_EINVAL;
             kernel = v;
-        } else if (k == "tile") { tile = atoi(v.c_str()) ? 1 : 0; }
+        } else if (k == "tile") {
+            int t = atoi(v.c_str());
+            if (t < 0 || t >= NTILES) return YB_EINVAL;
+            tile = t;
+        }
         else if (k == "lx") { lx = std::max(1, atoi(v.c_str())); }
         else if (k == "grid") { grid_override = std::max(0, atoi(v.c_str())); }
         else return YB_EINVAL;
@@ -213,15 +223,14 @@ struct IsoEngine : Engine {
         if (radius == 8 && prop.major >= 9) {
             const Var& p = s.vars[0];
             const Var& v = s.vars[1];
-            for (int tl = 0; tl < 2; tl++) {
-                const int TY = tl ? TileB::TY : TileA::TY, TZ = tl ? TileB::TZ : TileA::TZ;
-                const int HP = tl ? TileB::HP : TileA::HP, HR = tl ? TileB::HROWS : TileA::HROWS;
+            for (int tl = 0; tl < NTILES; tl++) {
+                const TileCfg& c = tile_cfg(tl);
                 for (int cur = 0; cur < 2; cur++) {
                     IsoMaps& m = maps[tl][cur];
-                    if (int rc = make_map(&m.h, p, cur, HP, HR)) return rc;
-                    if (int rc = make_map(&m.c, p, cur, TZ, TY)) return rc;
-                    if (int rc = make_map(&m.p, p, 1 - cur, TZ, TY)) return rc;
-                    if (int rc = make_map(&m.v, v, 0, TZ, TY)) return rc;
+                    if (int rc = make_map(&m.h, p, cur, c.hp, c.hrows)) return rc;
+                    if (int rc = make_map(&m.c, p, cur, c.tz, c.ty)) return rc;
+                    if (int rc = make_map(&m.p, p, 1 - cur, c.tz, c.ty)) return rc;
+                    if (int rc = make_map(&m.v, v, 0, c.tz, c.ty)) return rc;
                 }
             }
             maps_ok = true;
@@ -262,21 +271,19 @@ struct IsoEngine : Engine {
         }
         if (kernel == "tma" && !maps_ok) return set_error(YB_EUNSUPPORTED, "TMA kernel needs radius 8 and sm_90+");
         if (use_tma) {
-            const int TY = tile ? TileB::TY : TileA::TY, TZ = tile ? TileB::TZ : TileA::TZ;
-            P.nty = int((box.e[1] - box.b[1] + TY - 1) / TY);
-            P.ntz = int((box.e[2] - box.b[2] + TZ - 1) / TZ);
+            const TileCfg& c = tile_cfg(tile);
+            P.nty = int((box.e[1] - box.b[1] + c.ty - 1) / c.ty);
+            P.ntz = int((box.e[2] - box.b[2] + c.tz - 1) / c.tz);
             const int64_t nxb = box.e[0] - box.b[0];
             P.lx = int(std::min<int64_t>(lx, nxb));
             P.nchunks = int((nxb + P.lx - 1) / P.lx);
             const int64_t nunits = int64_t(P.nty) * P.ntz * P.nchunks;
             int grid = int(std::min<int64_t>(nunits, grid_override > 0 ? grid_override : num_sms));
             if (!attr_set[tile][mode]) {
-                int rc = tile ? TileLaunch<TileB>::set_attr(mode) : TileLaunch<TileA>::set_attr(mode);
-                if (rc) return rc;
+                YB_CUDA(cudaFuncSetAttribute(c.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
                 attr_set[tile][mode] = true;
             }
-            if (tile) TileLaunch<TileB>::launch(mode, grid, st, maps[1][cur], P);
-            else TileLaunch<TileA>::launch(mode, grid, st, maps[0][cur], P);
+            c.fn[mode]<<<grid, c.threads, c.smem, st>>>(maps[tile][cur], P);
         } else {
             dim3 blk(128, 1, 1);
             dim3 grd(unsigned((box.e[2] - box.b[2] + 127) / 128), unsigned(box.e[1] - box.b[1]), unsigned(box.e[0] - box.b[0]));

@@ -233,6 +233,7 @@ iso3dfd_tma_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ Is
         const bool row_ok = y < P.y_end;
         const int nvalid = row_ok ? max(0, min(4, P.z_end - zq)) : 0;
         float* out_col = P.out + (long long)y * P.out_sy + zq;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_col) & 15) == 0);
 
         for (int itb = 0; itb < cu.n_it; itb += QN) {
 #pragma unroll
@@ -284,12 +285,13 @@ iso3dfd_tma_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ Is
                     res.z = iso_final<MODE>(acc[2], pc[2], pv.z, vv.z);
                     res.w = iso_final<MODE>(acc[3], pc[3], pv.w, vv.w);
                     float* o = out_col + (long long)(cu.x0 + it - 2 * R) * P.out_sx;
-                    if (nvalid == 4) {
+                    if (nvalid == 4 && vec_ok) {
                         stg128(o, res);
                     } else if (nvalid > 0) {
                         o[0] = res.x;
                         if (nvalid > 1) o[1] = res.y;
                         if (nvalid > 2) o[2] = res.z;
+                        if (nvalid > 3) o[3] = res.w;
                     }
                 }
                 // release the stage: one arrive per warp once all its lanes are done reading
@@ -297,6 +299,194 @@ iso3dfd_tma_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ Is
                 if (lane == 0) mbar_arrive(&empty_bar[cu.stage]);
                 if (++cu.stage == T::STAGES) { cu.stage = 0; cu.phase ^= 1u; }
             }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Tiled TMA kernel, generation 2 ("row-pair" threads).
+//
+// ncu on generation 1 (profiles/iso3dfd_r1_gen1.md) showed the sweep limited by shared-memory
+// wavefronts (23 LDS.128 per 4 points, every y neighbour loaded once per point) and by
+// instruction-cache misses of the 17x-unrolled body.  Generation 2 changes two things:
+//   * a thread owns TWO vertically adjacent rows x 4 z (8 points).  The y window of the pair is
+//     18 rows, each loaded ONCE and used by both rows: 16+8 neighbour loads per 8 points
+//     instead of 2 x 20 -- 40 % fewer shared-memory wavefronts per point;
+//   * the x queue is rotated by register moves (loop NOT unrolled 2R+1 times), so the whole
+//     sweep body fits the instruction cache.
+// Everything else (TMA stage ring, mbarriers, persistent unit scheduling, arithmetic order) is as
+// in generation 1.
+// ---------------------------------------------------------------------------------------------
+template <int R_, int TYP_, int TZQ_, int STAGES_>
+struct IsoTile2 {
+    static constexpr int R = R_, TYP = TYP_, TZQ = TZQ_, STAGES = STAGES_;
+    static constexpr int TY = 2 * TYP;
+    static constexpr int TZ = 4 * TZQ;
+    static constexpr int HZ = (R + 3) / 4 * 4;
+    static constexpr int ZQ = HZ / 4;
+    static constexpr int HP = TZ + 2 * HZ;
+    static constexpr int HROWS = TY + 2 * R;
+    static constexpr int THREADS = TYP * TZQ;
+    static constexpr int NWARPS = THREADS / 32;
+    static constexpr int QN = 2 * R + 1;
+    static constexpr uint32_t H_BYTES = HROWS * HP * 4;
+    static constexpr uint32_t C_BYTES = TY * TZ * 4;
+    static constexpr uint32_t H_OFF = 0;
+    static constexpr uint32_t C_OFF = (H_BYTES + 127) / 128 * 128;
+    static constexpr uint32_t P_OFF = C_OFF + C_BYTES;
+    static constexpr uint32_t V_OFF = P_OFF + C_BYTES;
+    static constexpr uint32_t STAGE_BYTES = V_OFF + C_BYTES;
+    static constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr uint32_t SMEM_BYTES = BAR_OFF + 2 * STAGES * 8 + 128;
+    static_assert(THREADS % 32 == 0, "whole warps");
+    static_assert(C_BYTES % 128 == 0, "TMA destination alignment");
+};
+
+__device__ __forceinline__ void f4_to_arr(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+
+template <class T, int MODE>
+__global__ void __launch_bounds__(T::THREADS, 1)
+iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ IsoParams P) {
+    constexpr int R = T::R, QN = T::QN, ZQ = T::ZQ;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbase + T::BAR_OFF);
+    uint64_t* empty_bar = full_bar + T::STAGES;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int nunits = P.nty * P.ntz * P.nchunks;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&M.h); tma_prefetch_desc(&M.c); tma_prefetch_desc(&M.p); tma_prefetch_desc(&M.v);
+        for (int s = 0; s < T::STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], T::NWARPS); }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // ---- producer (thread 0) -------------------------------------------------------------
+    IsoCursor pr;
+    pr.unit = blockIdx.x; pr.stage = 0; pr.phase = 0; pr.it = 0; pr.n_it = 0; pr.x0 = pr.y0 = pr.z0 = 0;
+    const uint64_t pol_stream = l2_policy_evict_first();
+    bool pr_live = (tid == 0) && (pr.unit < nunits);
+    if (pr_live) iso_unit_setup<T>(pr, P);
+
+    auto produce_one = [&]() {
+        mbar_wait(&empty_bar[pr.stage], pr.phase ^ 1u);
+        uint8_t* st = sbase + pr.stage * T::STAGE_BYTES;
+        uint64_t* fb = &full_bar[pr.stage];
+        const bool compute = pr.it >= 2 * R;
+        mbar_arrive_expect_tx(fb, compute ? (T::H_BYTES + 3 * T::C_BYTES) : T::C_BYTES);
+        const int cz = P.pad_z + pr.z0, cy = P.pad_y + pr.y0;
+        tma_load_3d(st + T::C_OFF, &M.c, fb, cz, cy, P.pad_x + pr.x0 - R + pr.it);
+        if (compute) {
+            const int xo = pr.x0 + pr.it - 2 * R;
+            tma_load_3d(st + T::H_OFF, &M.h, fb, cz - T::HZ, cy - R, P.pad_x + xo);
+            tma_load_3d_hint(st + T::P_OFF, &M.p, fb, cz, cy, P.pad_x + xo, pol_stream);
+            tma_load_3d_hint(st + T::V_OFF, &M.v, fb, P.vpad_z + pr.z0, P.vpad_y + pr.y0, P.vpad_x + xo, pol_stream);
+        }
+        if (++pr.stage == T::STAGES) { pr.stage = 0; pr.phase ^= 1u; }
+        if (++pr.it == pr.n_it) {
+            pr.unit += gridDim.x;
+            if (pr.unit < nunits) iso_unit_setup<T>(pr, P); else pr_live = false;
+        }
+    };
+    if (tid == 0) {
+        for (int k = 0; k < T::STAGES - 1 && pr_live; k++) produce_one();
+    }
+
+    // ---- consumer ------------------------------------------------------------------------
+    const int rp = tid / T::TZQ;           // row pair 0..TYP-1  (rows 2rp, 2rp+1)
+    const int quad = tid % T::TZQ;
+    const uint32_t h_own = ((2 * rp + R) * T::HP + T::HZ + 4 * quad) * 4;  // row a centre in H
+    const uint32_t c_own = (2 * rp * T::TZ + 4 * quad) * 4;               // row a in C/P/V tiles
+
+    IsoCursor cu;
+    cu.stage = 0; cu.phase = 0;
+    float4 qa[QN], qb[QN];
+#pragma unroll
+    for (int k = 0; k < QN; k++) { qa[k] = make_float4(0.f, 0.f, 0.f, 0.f); qb[k] = qa[k]; }
+
+    for (cu.unit = blockIdx.x; cu.unit < nunits; cu.unit += gridDim.x) {
+        iso_unit_setup<T>(cu, P);
+        const int ya = cu.y0 + 2 * rp;
+        const int zq = cu.z0 + 4 * quad;
+        const int nz_ok = max(0, min(4, P.z_end - zq));
+        const int nva = (ya < P.y_end) ? nz_ok : 0;
+        const int nvb = (ya + 1 < P.y_end) ? nz_ok : 0;
+        float* out_a = P.out + (long long)ya * P.out_sy + zq + (long long)(cu.x0 - 2 * R) * P.out_sx;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_a) & 15) == 0);
+
+#pragma unroll 1
+        for (int it = 0; it < cu.n_it; it++) {
+            if (tid == 0 && pr_live) produce_one();
+
+            const uint8_t* st = sbase + cu.stage * T::STAGE_BYTES;
+            mbar_wait(&full_bar[cu.stage], cu.phase);
+
+            // rotate the x queue (register moves) and push plane x0 - R + it
+#pragma unroll
+            for (int k = 0; k < QN - 1; k++) { qa[k] = qa[k + 1]; qb[k] = qb[k + 1]; }
+            qa[QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own);
+            qb[QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own + T::TZ * 4);
+
+            if (it >= 2 * R) {
+                const float* hp = reinterpret_cast<const float*>(st + T::H_OFF + h_own);
+                float pa[4], pb[4];
+                f4_to_arr(qa[R], pa);
+                f4_to_arr(qb[R], pb);
+                // z windows of both rows (centre quads come from the queue)
+                float za[4 * (2 * ZQ + 1)], zb[4 * (2 * ZQ + 1)];
+#pragma unroll
+                for (int k = -ZQ; k <= ZQ; k++) {
+                    if (k == 0) { f4_to_arr(qa[R], &za[4 * ZQ]); f4_to_arr(qb[R], &zb[4 * ZQ]); continue; }
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp + 4 * k), &za[4 * (k + ZQ)]);
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp + T::HP + 4 * k), &zb[4 * (k + ZQ)]);
+                }
+                float acca[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+                // y window: row index k <-> H row (2rp + k - R) ... w(k) = hp + (k - R) * HP ; row a centre = w(R), row b = w(R+1)
+                float wlo_prev[4], whi_prev[4];   // w(R - (r-1)) and w(R+1 + (r-1)) from the previous radius
+                f4_to_arr(qa[R], wlo_prev);       // r=1: row b's y-1 neighbour is row a's centre
+                f4_to_arr(qb[R], whi_prev);       //      row a's y+1 neighbour is row b's centre
+#pragma unroll
+                for (int r = 1; r <= R; r++) {
+                    float wlo[4], whi[4], xm[4], xp[4];
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp - r * T::HP), wlo);        // row a - r
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp + (r + 1) * T::HP), whi);  // row b + r
+                    f4_to_arr(qa[R - r], xm); f4_to_arr(qa[R + r], xp);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)   // row a: y-r = wlo, y+r = w(R+r) = previous whi
+                        acca[i] = iso_group<MODE>(acca[i], pa[i], P.c[0], P.c[r], xm[i], xp[i], wlo[i], whi_prev[i],
+                                                  za[4 * ZQ + i - r], za[4 * ZQ + i + r], r == 1);
+                    f4_to_arr(qb[R - r], xm); f4_to_arr(qb[R + r], xp);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)   // row b: y-r = w(R+1-r) = previous wlo, y+r = whi
+                        accb[i] = iso_group<MODE>(accb[i], pb[i], P.c[0], P.c[r], xm[i], xp[i], wlo_prev[i], whi[i],
+                                                  zb[4 * ZQ + i - r], zb[4 * ZQ + i + r], r == 1);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { wlo_prev[i] = wlo[i]; whi_prev[i] = whi[i]; }
+                }
+                const float4 pva = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own);
+                const float4 vva = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own);
+                const float4 pvb = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own + T::TZ * 4);
+                const float4 vvb = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own + T::TZ * 4);
+                float4 ra, rb;
+                ra.x = iso_final<MODE>(acca[0], pa[0], pva.x, vva.x); ra.y = iso_final<MODE>(acca[1], pa[1], pva.y, vva.y);
+                ra.z = iso_final<MODE>(acca[2], pa[2], pva.z, vva.z); ra.w = iso_final<MODE>(acca[3], pa[3], pva.w, vva.w);
+                rb.x = iso_final<MODE>(accb[0], pb[0], pvb.x, vvb.x); rb.y = iso_final<MODE>(accb[1], pb[1], pvb.y, vvb.y);
+                rb.z = iso_final<MODE>(accb[2], pb[2], pvb.z, vvb.z); rb.w = iso_final<MODE>(accb[3], pb[3], pvb.w, vvb.w);
+                float* oa = out_a + (long long)it * P.out_sx;
+                float* ob = oa + P.out_sy;
+                if (vec_ok && nva == 4) stg128(oa, ra);
+                else if (nva > 0) { oa[0] = ra.x; if (nva > 1) oa[1] = ra.y; if (nva > 2) oa[2] = ra.z; if (nva > 3) oa[3] = ra.w; }
+                if (vec_ok && nvb == 4) stg128(ob, rb);
+                else if (nvb > 0) { ob[0] = rb.x; if (nvb > 1) ob[1] = rb.y; if (nvb > 2) ob[2] = rb.z; if (nvb > 3) ob[3] = rb.w; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[cu.stage]);
+            if (++cu.stage == T::STAGES) { cu.stage = 0; cu.phase ^= 1u; }
         }
     }
 }
