@@ -1,0 +1,25 @@
+"""Condense an ncu report (raw page CSV) into the handful of numbers the roofline discussion needs."""
+import csv, subprocess, sys, json
+rep = sys.argv[1]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+KEYS = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum", "sm__inst_executed.sum.per_cycle_active",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__icc_request_hit_rate.pct", "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
+        "sm__cycles_elapsed.avg.per_second", "sm__cycles_active.avg"]
+STALL = "smsp__average_warps_issue_stalled_"
+for r in rows[2:]:
+    d = dict(zip(hdr, r))
+    print("== ", d.get("Kernel Name", "?")[:90])
+    for k in KEYS[1:]:
+        if k in d:
+            print(f"  {k:85s} {d[k]:>18s} {units[hdr.index(k)]}")
+    st = sorted(((float(v), k[len(STALL):-len('_per_issue_active.ratio')]) for k, v in d.items() if k.startswith(STALL) and k.endswith("_per_issue_active.ratio") and v not in ("", "n/a")), reverse=True)
+    print("  stalls (warps per issue):", ", ".join(f"{n}={v:.2f}" for v, n in st[:8]))

@@ -31,12 +31,11 @@ if __name__ == "__main__":
     n = (N, N, N)
     res = []
     base = None
-    import itertools
-    variants = [dict(kernel="tma", tile=0, lx=128)]
+    variants = []
     for tile in (2, 3):
-        for lx in (64, 128, 256, 1024):
-            variants.append(dict(kernel="tma", tile=tile, lx=lx))
-    variants += [dict(kernel="tma", tile=2, lx=128, fp_mode=0), dict(kernel="tma", tile=2, lx=128, grid=296)]
+        for (pc, ph) in ((0, 0), (2, 0), (2, 1), (0, 1), (2, 2)):
+            variants.append(dict(kernel="tma", tile=tile, lx=512, pol_c=pc, pol_h=ph))
+    variants += [dict(kernel="tma", tile=3, lx=512, pol_c=2, pol_h=0, mem_probe=1), dict(kernel="tma", tile=3, lx=512, pol_c=2, pol_h=1, mem_probe=1)]
     for opts in variants:
         steps = 3 if opts.get("kernel") == "direct" else 20
         g, ms, cs = run(n, steps, 3, **opts)

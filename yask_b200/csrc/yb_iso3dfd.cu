@@ -151,18 +151,18 @@ struct TileCfg {
     const char* name;
     int ty, tz, hp, hrows, threads;
     uint32_t smem;
-    IsoKernelFn fn[3];  // per FP mode
+    IsoKernelFn fn[4];  // per FP mode (3 = debug memory-only probe, gen2 only)
 };
 
 template <class T>
 TileCfg cfg_gen1(const char* name) {
     return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
-                   {iso3dfd_tma_kernel<T, 0>, iso3dfd_tma_kernel<T, 1>, iso3dfd_tma_kernel<T, 2>}};
+                   {iso3dfd_tma_kernel<T, 0>, iso3dfd_tma_kernel<T, 1>, iso3dfd_tma_kernel<T, 2>, nullptr}};
 }
 template <class T>
 TileCfg cfg_gen2(const char* name) {
     return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
-                   {iso3dfd_tma2_kernel<T, 0>, iso3dfd_tma2_kernel<T, 1>, iso3dfd_tma2_kernel<T, 2>}};
+                   {iso3dfd_tma2_kernel<T, 0>, iso3dfd_tma2_kernel<T, 1>, iso3dfd_tma2_kernel<T, 2>, iso3dfd_tma2_kernel<T, 3>}};
 }
 
 constexpr int NTILES = 4;
@@ -181,10 +181,12 @@ struct IsoEngine : Engine {
     double coef[ISO_MAX_R + 1] = {0};
     std::string kernel = "auto";   // auto | tma | direct
     int tile = 2;                  // index into tile_cfg()
-    int lx = 128;                  // planes per sweep chunk
+    int lx = 0;                    // planes per sweep chunk (0 = choose per launch)
     int grid_override = 0;
     int num_sms = 148;
-    bool attr_set[NTILES][3] = {};
+    bool attr_set[NTILES][4] = {};
+    int pol_c = 0, pol_h = 0, pol_pv = 1;
+    bool mem_probe = false;      // debug: fp_mode=3 style memory-only kernel
     IsoMaps maps[NTILES][2];       // [tile][cur slot]
     bool maps_ok = false;
 
@@ -197,8 +199,12 @@ struct IsoEngine : Engine {
             if (t < 0 || t >= NTILES) return YB_EINVAL;
             tile = t;
         }
-        else if (k == "lx") { lx = std::max(1, atoi(v.c_str())); }
+        else if (k == "lx") { lx = std::max(0, atoi(v.c_str())); }
         else if (k == "grid") { grid_override = std::max(0, atoi(v.c_str())); }
+        else if (k == "mem_probe") { mem_probe = atoi(v.c_str()) != 0; }
+        else if (k == "pol_c") { pol_c = atoi(v.c_str()); }
+        else if (k == "pol_h") { pol_h = atoi(v.c_str()); }
+        else if (k == "pol_pv") { pol_pv = atoi(v.c_str()); }
         else return YB_EINVAL;
         return 0;
     }
@@ -254,6 +260,7 @@ struct IsoEngine : Engine {
         P.z_begin = int(box.b[2]); P.z_end = int(box.e[2]);
         P.pad_x = int(px->pad_l); P.pad_y = int(py->pad_l); P.pad_z = int(pz->pad_l);
         P.vpad_x = int(vx->pad_l); P.vpad_y = int(vy->pad_l); P.vpad_z = int(vz->pad_l);
+        P.pol_c = pol_c; P.pol_h = pol_h; P.pol_pv = pol_pv;
         for (int r = 0; r <= ISO_MAX_R; r++) P.c[r] = r <= radius ? float(coef[r]) : 0.f;
     }
 
@@ -263,7 +270,7 @@ struct IsoEngine : Engine {
         const int cur = p.slot_of(t);
         IsoParams P{};
         fill_params(s, cur, box, P);
-        const int mode = s.fp_mode;
+        int mode = s.fp_mode;
         bool use_tma = maps_ok && kernel != "direct";
         if (kernel == "auto") {
             // thin slabs in y/z (halo faces) are not worth a tile sweep
@@ -272,13 +279,30 @@ struct IsoEngine : Engine {
         if (kernel == "tma" && !maps_ok) return set_error(YB_EUNSUPPORTED, "TMA kernel needs radius 8 and sm_90+");
         if (use_tma) {
             const TileCfg& c = tile_cfg(tile);
+            if (mem_probe && c.fn[3]) mode = 3;
             P.nty = int((box.e[1] - box.b[1] + c.ty - 1) / c.ty);
             P.ntz = int((box.e[2] - box.b[2] + c.tz - 1) / c.tz);
             const int64_t nxb = box.e[0] - box.b[0];
-            P.lx = int(std::min<int64_t>(lx, nxb));
+            const int gmax = grid_override > 0 ? grid_override : num_sms;
+            if (lx > 0) {
+                P.lx = int(std::min<int64_t>(lx, nxb));
+            } else {
+                // Pick the chunk count that minimises (rounds of units per CTA) x (chunk length + queue
+                // warm-up): long chunks amortise the 2R warm-up planes, short ones balance the last round.
+                const int64_t ntile = int64_t(P.nty) * P.ntz;
+                double best = 1e30;
+                int best_lx = int(nxb);
+                for (int nc = 1; nc <= 64 && nc <= nxb; nc++) {
+                    const int64_t l = (nxb + nc - 1) / nc;
+                    const int64_t rounds = (ntile * nc + gmax - 1) / gmax;
+                    const double cost = double(rounds) * (double(l) + 2 * radius * 0.4);
+                    if (cost < best * 0.999) { best = cost; best_lx = int(l); }
+                }
+                P.lx = best_lx;
+            }
             P.nchunks = int((nxb + P.lx - 1) / P.lx);
             const int64_t nunits = int64_t(P.nty) * P.ntz * P.nchunks;
-            int grid = int(std::min<int64_t>(nunits, grid_override > 0 ? grid_override : num_sms));
+            int grid = int(std::min<int64_t>(nunits, gmax));
             if (!attr_set[tile][mode]) {
                 YB_CUDA(cudaFuncSetAttribute(c.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
                 attr_set[tile][mode] = true;

@@ -31,6 +31,7 @@ struct IsoParams {
     int pad_x, pad_y, pad_z;    // p arrays: alloc index of domain origin (TMA coordinates)
     int vpad_x, vpad_y, vpad_z; // v array: same
     int nty, ntz, nchunks, lx;  // tiling of [begin,end): tiles in y,z; chunks of lx planes in x
+    int pol_c, pol_h, pol_pv;   // L2 eviction policy of the TMA streams: 0 normal, 1 evict_first, 2 evict_last
     float c[ISO_MAX_R + 1];
 };
 
@@ -369,7 +370,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
     // ---- producer (thread 0) -------------------------------------------------------------
     IsoCursor pr;
     pr.unit = blockIdx.x; pr.stage = 0; pr.phase = 0; pr.it = 0; pr.n_it = 0; pr.x0 = pr.y0 = pr.z0 = 0;
-    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_pv = l2_policy(P.pol_pv), pol_c = l2_policy(P.pol_c), pol_h = l2_policy(P.pol_h);
     bool pr_live = (tid == 0) && (pr.unit < nunits);
     if (pr_live) iso_unit_setup<T>(pr, P);
 
@@ -380,12 +381,12 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
         const bool compute = pr.it >= 2 * R;
         mbar_arrive_expect_tx(fb, compute ? (T::H_BYTES + 3 * T::C_BYTES) : T::C_BYTES);
         const int cz = P.pad_z + pr.z0, cy = P.pad_y + pr.y0;
-        tma_load_3d(st + T::C_OFF, &M.c, fb, cz, cy, P.pad_x + pr.x0 - R + pr.it);
+        tma_load_3d_hint(st + T::C_OFF, &M.c, fb, cz, cy, P.pad_x + pr.x0 - R + pr.it, pol_c);
         if (compute) {
             const int xo = pr.x0 + pr.it - 2 * R;
-            tma_load_3d(st + T::H_OFF, &M.h, fb, cz - T::HZ, cy - R, P.pad_x + xo);
-            tma_load_3d_hint(st + T::P_OFF, &M.p, fb, cz, cy, P.pad_x + xo, pol_stream);
-            tma_load_3d_hint(st + T::V_OFF, &M.v, fb, P.vpad_z + pr.z0, P.vpad_y + pr.y0, P.vpad_x + xo, pol_stream);
+            tma_load_3d_hint(st + T::H_OFF, &M.h, fb, cz - T::HZ, cy - R, P.pad_x + xo, pol_h);
+            tma_load_3d_hint(st + T::P_OFF, &M.p, fb, cz, cy, P.pad_x + xo, pol_pv);
+            tma_load_3d_hint(st + T::V_OFF, &M.v, fb, P.vpad_z + pr.z0, P.vpad_y + pr.y0, P.vpad_x + xo, pol_pv);
         }
         if (++pr.stage == T::STAGES) { pr.stage = 0; pr.phase ^= 1u; }
         if (++pr.it == pr.n_it) {
@@ -432,7 +433,21 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
             qa[QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own);
             qb[QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own + T::TZ * 4);
 
-            if (it >= 2 * R) {
+            if (MODE == 3) {
+                // DEBUG (fp_mode=3): memory-system ceiling probe -- same TMA traffic and stores, no stencil math.
+                if (it >= 2 * R) {
+                    const float4 pva = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own);
+                    const float4 vva = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own);
+                    const float4 pvb = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own + T::TZ * 4);
+                    const float4 vvb = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own + T::TZ * 4);
+                    const float4 ha = *reinterpret_cast<const float4*>(st + T::H_OFF + h_own);
+                    float4 ra = make_float4(pva.x + vva.x * qa[R].x, pva.y + vva.y * ha.y, pva.z + vva.z, pva.w + vva.w);
+                    float4 rb = make_float4(pvb.x + vvb.x * qb[R].x, pvb.y + vvb.y, pvb.z + vvb.z, pvb.w + vvb.w);
+                    float* oa = out_a + (long long)it * P.out_sx;
+                    if (vec_ok && nva == 4) stg128(oa, ra);
+                    if (vec_ok && nvb == 4) stg128(oa + P.out_sy, rb);
+                }
+            } else if (it >= 2 * R) {
                 const float* hp = reinterpret_cast<const float*>(st + T::H_OFF + h_own);
                 float pa[4], pb[4];
                 f4_to_arr(qa[R], pa);

@@ -81,6 +81,16 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
     return p;
 }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// 0 = evict_normal, 1 = evict_first, 2 = evict_last
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+    return kind == 1 ? l2_policy_evict_first() : (kind == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
