@@ -132,6 +132,10 @@ int yb_get_option(const yb_solution* s, const char* key, char* value, size_t val
 /* Run the kernels on this CUDA stream (a cudaStream_t cast to void*; NULL = the solution's own). */
 int yb_set_stream(yb_solution* s, void* cuda_stream);
 
+/* Host-only part of prepare (setup_rank, setup.cpp:462-503): derive this rank's domain size and
+ * offset from the overall size / rank grid / rank index.  Needs no device; prepare() calls it too. */
+int yb_solution_plan_geometry(yb_solution* s);
+
 /* ---- prepare: rank geometry + device allocation (prepare_solution, soln_apis.cpp:137-249) ---- */
 int yb_solution_prepare(yb_solution* s, int device);
 int yb_solution_is_prepared(const yb_solution* s);

@@ -1,0 +1,105 @@
+"""Multi-rank runs: the domain split over a rank grid must give bit-identical results to one rank.
+
+On the GPU box these run several ranks on ONE device in ONE process (peers wired with raw pointers
+instead of IPC handles; the kernels, geometry and epoch protocol are the same), plus -- if the box
+has it -- a true multi-process IPC run (world_size 2) launched through torch.multiprocessing."""
+import numpy as np
+import pytest
+
+from yask_b200 import capi, multi
+from yask_b200.synth import hash_field, var_salt
+
+pytestmark = pytest.mark.gpu
+
+
+def fill(s, seed):
+    p, v = s.get_var("p"), s.get_var("v")
+    for t in (0, 1):
+        p.fill_hash(t, seed, var_salt("p", t), -1.0, 1.0)
+    v.fill_hash(0, seed, var_salt("v", 0), 0.05, 0.3)
+
+
+def single_rank(n, steps, seed):
+    s = capi.Solution("iso3dfd")
+    s.set_overall_domain_size_vec(n)
+    s.prepare_solution(0)
+    fill(s, seed)
+    s.run_solution(0, steps - 1)
+    p = s.get_var("p")
+    out = p.get_elements_in_slice(*p.domain_box(p.get_last_valid_step_index()))
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("n,grid,steps", [((64, 48, 96), (2, 1, 1), 3), ((48, 64, 96), (1, 2, 1), 2), ((40, 40, 128), (1, 1, 2), 2),
+                                           ((70, 50, 100), (2, 2, 1), 3), ((64, 64, 128), (2, 2, 2), 2), ((150, 40, 64), (4, 1, 1), 4)])
+def test_rank_grid_matches_single_rank(n, grid, steps):
+    seed = 17
+    ref = single_rank(n, steps, seed)
+    world = grid[0] * grid[1] * grid[2]
+    solns = []
+    for r in range(world):
+        s = capi.Solution("iso3dfd")
+        s.set_overall_domain_size_vec(n)
+        s.set_num_ranks_vec(grid)
+        s.set_rank_index_vec(multi.grid_coords(r, grid))
+        s.prepare_solution(0)
+        solns.append(s)
+    multi.connect_local(solns)
+    for s in solns:
+        fill(s, seed)   # hash of GLOBAL indices: every rank fills its own part (and its halos) consistently
+    for s in solns:     # enqueue everything first: ranks wait for each other on the device
+        s.run_solution(0, steps - 1)
+    out = np.zeros(n, np.float32)
+    for s in solns:
+        s.sync()
+    for s in solns:
+        p = s.get_var("p")
+        f, l = p.domain_box(p.get_last_valid_step_index())
+        out[f[1]:l[1] + 1, f[2]:l[2] + 1, f[3]:l[3] + 1] = p.get_elements_in_slice(f, l)
+        s.close()
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def _ipc_worker(rank, world, n, steps, seed, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dev = rank % max(1, torch.cuda.device_count())
+    s = capi.Solution("iso3dfd")
+    s.set_overall_domain_size_vec(n)
+    s.set_num_ranks_vec([world, 1, 1])
+    s.set_rank_index_vec([rank, 0, 0])
+    s.prepare_solution(dev)
+    multi.connect(s, dist, rank, world)
+    fill(s, seed)
+    dist.barrier()
+    s.run_solution(0, steps - 1)
+    s.sync()
+    p = s.get_var("p")
+    f, l = p.domain_box(p.get_last_valid_step_index())
+    q.put((rank, f, l, p.get_elements_in_slice(f, l)))
+    dist.barrier()
+    s.close()
+    dist.destroy_process_group()
+
+
+def test_two_processes_cuda_ipc():
+    import torch.multiprocessing as mp
+    n, steps, seed = (96, 32, 64), 3, 23
+    ref = single_rank(n, steps, seed)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, 2, n, steps, seed, 29533, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    out = np.zeros(n, np.float32)
+    for _ in range(2):
+        rank, f, l, a = q.get(timeout=180)
+        out[f[1]:l[1] + 1, f[2]:l[2] + 1, f[3]:l[3] + 1] = a
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))

@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "yb_set_rank_domain_size", "yb_set_overall_domain_size", "yb_set_num_ranks", "yb_set_rank_index", "yb_set_min_pad_size",
     "yb_get_rank_domain_size", "yb_get_overall_domain_size", "yb_get_num_ranks", "yb_get_rank_index",
     "yb_get_first_rank_domain_index", "yb_get_last_rank_domain_index", "yb_set_option", "yb_get_option", "yb_set_stream",
-    "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_set_min_pad",
+    "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_set_min_pad",
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
     "yb_var_set_slice_same", "yb_var_fill_hash", "yb_var_checksum", "yb_var_device_ptr", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         L.yb_set_option.argtypes = [p, C.c_char_p, C.c_char_p]
         L.yb_get_option.argtypes = [p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.yb_set_stream.argtypes = [p, p]
+        L.yb_solution_plan_geometry.argtypes = [p]
         L.yb_solution_prepare.argtypes = [p, i32]
         L.yb_solution_is_prepared.argtypes = [p]
         L.yb_num_vars.argtypes = [p]
@@ -307,6 +308,9 @@ class Solution:
 
     def set_stream(self, cuda_stream: int):
         _chk(lib().yb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def plan_geometry(self):
+        _chk(lib().yb_solution_plan_geometry(self._h))
 
     def prepare_solution(self, device: int = 0):
         _chk(lib().yb_solution_prepare(self._h, device))

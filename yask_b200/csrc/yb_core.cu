@@ -332,11 +332,11 @@ int yb_set_min_pad_size(yb_solution* s_, int dim, int64_t n) {
 }
 int64_t yb_get_rank_domain_size(const yb_solution* s, int dim) {
     if (check_dim(CSOL(s), dim)) return -1;
-    return CSOL(s)->prepared ? CSOL(s)->rank_size[dim] : CSOL(s)->req_rank_size[dim];
+    return CSOL(s)->rank_size[dim] > 0 ? CSOL(s)->rank_size[dim] : CSOL(s)->req_rank_size[dim];
 }
 int64_t yb_get_overall_domain_size(const yb_solution* s, int dim) {
     if (check_dim(CSOL(s), dim)) return -1;
-    return CSOL(s)->prepared ? CSOL(s)->overall_size[dim] : CSOL(s)->req_overall_size[dim];
+    return CSOL(s)->overall_size[dim] > 0 ? CSOL(s)->overall_size[dim] : CSOL(s)->req_overall_size[dim];
 }
 int64_t yb_get_num_ranks(const yb_solution* s, int dim) { return check_dim(CSOL(s), dim) ? -1 : CSOL(s)->num_ranks[dim]; }
 int64_t yb_get_rank_index(const yb_solution* s, int dim) { return check_dim(CSOL(s), dim) ? -1 : CSOL(s)->rank_index[dim]; }
@@ -379,6 +379,15 @@ int yb_set_stream(yb_solution* s_, void* st) {
     if (!s) return set_error(YB_EINVAL, "null solution");
     s->user_stream = static_cast<cudaStream_t>(st);
     s->use_user_stream = true;
+    return 0;
+}
+
+int yb_solution_plan_geometry(yb_solution* s_) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (s->prepared) return 0;
+    if (int rc = compute_rank_geometry(*s)) return rc;
+    for (auto& v : s->vars) compute_var_geometry(*s, v);
     return 0;
 }
 
