@@ -63,6 +63,75 @@ def iso3dfd_run(p0: np.ndarray, p1: np.ndarray, v: np.ndarray, radius: int, step
 
 
 # ---------------------------------------------------------------------------------------
+# Emitter-generated solutions (oracle/gen/*.gen.h): generic runner
+# ---------------------------------------------------------------------------------------
+class _GenArgs(ctypes.Structure):
+    _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 32),
+                ("sx", ctypes.c_int64 * 32), ("sy", ctypes.c_int64 * 32), ("sz", ctypes.c_int64 * 32)]
+
+
+def gen_ir(stencil: str) -> dict:
+    import json
+    return json.load(open(os.path.join(os.path.dirname(HERE), "yask_b200", "csrc", "gen", f"{stencil}.json")))
+
+
+def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
+    """Run `steps` steps of a generated solution on the CPU.
+    inputs: {(var, api_step): ndarray over the var's rank halo box} (scalars: 0-d / size-1 arrays); API steps
+    0..alloc_t-1 for vars with a step dim.  Returns {var: (last_valid_step, ndarray over the halo box)} for every
+    written var.  Inputs are not modified."""
+    ir = gen_ir(stencil)
+    dd = ir["domain_dims"]
+    dt = np.float32 if ir["elem_bytes"] == 4 else np.float64
+    L = lib()
+    L.yo_gen_run_part.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_GenArgs)]
+    slots = {}      # var -> list of arrays per slot
+    meta = {}
+    for v in ir["vars"]:
+        has_step = bool(v["dims"]) and v["dims"][0] == ir["step_dim"]
+        a = v["alloc_t"] if has_step else 1
+        arrs = []
+        for t in range(a):
+            arr = np.array(inputs[(v["name"], t)], dtype=dt, copy=True, order="C")
+            arrs.append(arr)
+        # API step t lives in slot t % alloc_t (imod_flr)
+        slots[v["name"]] = [arrs[t % a] if a > 1 else arrs[0] for t in range(a)]
+        if a > 1:
+            slots[v["name"]] = [None] * a
+            for t in range(a):
+                slots[v["name"]][t % a] = arrs[t]
+        meta[v["name"]] = (v, has_step, a)
+    last = {}
+    nn = list(n) + [1] * (3 - len(n))
+    for t in range(steps):
+        pi = 0
+        for st in ir["stages"]:
+            for p in st["parts"]:
+                A = _GenArgs()
+                A.nx, A.ny, A.nz = nn
+                for k, acc in enumerate(p["accesses"]):
+                    v, has_step, a = meta[acc["var"]]
+                    arr = slots[acc["var"]][(t + acc["toff"]) % a]
+                    vd = [d for d in v["dims"] if d != ir["step_dim"]]
+                    strides = {d: arr.strides[i] // arr.itemsize for i, d in enumerate(vd)}
+                    off = sum(v["halo"][d][0] * strides[d] for d in vd)
+                    A.ptr[k] = arr.ctypes.data + off * arr.itemsize
+                    A.sx[k] = strides.get(dd[0], 0) if len(dd) > 0 else 0
+                    A.sy[k] = strides.get(dd[1], 0) if len(dd) > 1 else 0
+                    A.sz[k] = strides.get(dd[2], 0) if len(dd) > 2 else 0
+                rc = L.yo_gen_run_part(stencil.encode(), pi, ctypes.byref(A))
+                assert rc == 0, rc
+                for o in p["outputs"]:
+                    last[p["accesses"][o["access"]]["var"]] = t + 1
+                pi += 1
+    out = {}
+    for name, tl in last.items():
+        v, has_step, a = meta[name]
+        out[name] = (tl, slots[name][tl % a])
+    return out
+
+
+# ---------------------------------------------------------------------------------------
 # Prebuilt reference (oracle/_ref): only usable where build_ref.sh has been run.
 # ---------------------------------------------------------------------------------------
 REF_BIN = os.path.join(HERE, "_ref", "yask", "bin")

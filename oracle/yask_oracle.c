@@ -204,3 +204,52 @@ int yo_num_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------ */
+/* Emitter-generated solutions (oracle/gen/<name>.gen.h, written by                         */
+/* yask_b200/emitter/yask_cuda_emit.py from the reference compiler's own output).          */
+/* Each part is a list of single-assignment statements in the reference's evaluation       */
+/* order; this file supplies the loop nest and the statement vocabulary.  All arithmetic   */
+/* is in the element type with no contraction (== reference built with -ffp-contract=off). */
+/* ------------------------------------------------------------------------------------ */
+#define YO_GEN_MAX_ACC 32
+typedef struct {
+    int64_t nx, ny, nz;                 /* rank-domain box [0,n) */
+    void* ptr[YO_GEN_MAX_ACC];          /* element (0,0,0) of each access' step slot */
+    int64_t sx[YO_GEN_MAX_ACC], sy[YO_GEN_MAX_ACC], sz[YO_GEN_MAX_ACC];
+} yo_gen_args;
+typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } yo_gen_part;
+
+#define YO_GEN_LOOP_BEGIN                                                      \
+    _Pragma("omp parallel for collapse(2) schedule(static)")                   \
+    for (int64_t x = 0; x < A->nx; x++)                                        \
+        for (int64_t y = 0; y < A->ny; y++)                                    \
+            for (int64_t z = 0; z < A->nz; z++) {
+#define YO_GEN_LOOP_END }
+#define RD(a, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
+#define WR(a, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
+#define C(v) ((T)(v))
+#define ADD(a, b) ((a) + (b))
+#define SUB(a, b) ((a) - (b))
+#define MUL(a, b) ((a) * (b))
+#define DIV(a, b) ((a) / (b))
+
+#include "gen/awp_elastic.gen.h"
+#include "gen/ssg.gen.h"
+
+static const struct { const char* name; const yo_gen_part* parts; int nparts; } yo_gen_table[] = {
+    {"awp_elastic", yo_awp_elastic_parts, (int)(sizeof(yo_awp_elastic_parts) / sizeof(yo_gen_part))},
+    {"ssg", yo_ssg_parts, (int)(sizeof(yo_ssg_parts) / sizeof(yo_gen_part))},
+};
+
+/* Run part `part` (0-based, in stage order) of generated solution `stencil` over the box in A. */
+int yo_gen_run_part(const char* stencil, int part, const yo_gen_args* A)
+{
+    for (size_t i = 0; i < sizeof(yo_gen_table) / sizeof(yo_gen_table[0]); i++) {
+        if (strcmp(stencil, yo_gen_table[i].name)) continue;
+        if (part < 0 || part >= yo_gen_table[i].nparts) return -2;
+        yo_gen_table[i].parts[part].fn(A);
+        return 0;
+    }
+    return -1;
+}

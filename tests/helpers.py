@@ -21,17 +21,38 @@ def load_golden(path):
     return meta, arrays
 
 
-def regen_inputs(meta, dtype=np.float32):
+def range_of(ranges, name):
+    """Value range of a var: longest matching name prefix (same rule as tests/golden/make_golden.py)."""
+    best = None
+    for k, v in ranges.items():
+        if name.startswith(k) and (best is None or len(k) > len(best[0])):
+            best = (k, v)
+    return best[1]
+
+
+def regen_inputs(meta, dtype=None):
     """Recreate the hash-field inputs a fixture was generated from: {(var, api_step): array over in-box}."""
+    if dtype is None:
+        dtype = np.float64 if "fp64" in meta["ref_tag"] else np.float32
     ins = {}
     for name, g in meta["vars"].items():
-        lo, hi = meta["ranges"][name]
-        has_step = g["dims"][0] == "t"
+        lo, hi = range_of(meta["ranges"], name)
+        has_step = bool(g["dims"]) and g["dims"][0] == "t"
         t0, t1 = meta["vars_before"][name]["steps"] if has_step else (0, 0)
         shape = [l - f + 1 for f, l in zip(g["in_first"], g["in_last"])]
         for t in range(t0, t1 + 1):
-            ins[(name, t)] = hash_field(meta["seed"], var_salt(name, t), g["in_first"], shape, lo, hi, dtype)
+            if shape:
+                ins[(name, t)] = hash_field(meta["seed"], var_salt(name, t), g["in_first"], shape, lo, hi, dtype)
+            else:
+                ins[(name, t)] = np.array(hash_field(meta["seed"], var_salt(name, t), (0,), (1,), lo, hi, dtype)[0], dtype=dtype)
     return ins
+
+
+def field_ulps(got, ref):
+    """max |got - ref| in units of eps * max|ref| ("field ulps"): a well-conditioned error measure for
+    fields whose individual values pass through zero."""
+    eps = np.finfo(ref.dtype).eps
+    return float(np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() / (eps * np.abs(ref).max()))
 
 
 def contract_mode_of(tag: str) -> int:

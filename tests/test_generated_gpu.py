@@ -1,0 +1,149 @@
+"""GPU parity of the emitter-generated solutions (awp_elastic fp32, ssg fp64) through the C ABI:
+  * fp_mode 0 (strict) bit-exact vs the reference built with -ffp-contract=off (golden fixtures),
+  * fp_mode 2 (fused) within 4 field-ulps of the reference's default build,
+  * bit-exact vs the CPU oracle on ragged sizes, and rank grids vs a single rank."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.helpers import field_ulps, golden_cases, load_golden, range_of, regen_inputs
+from tests.golden.make_golden import RANGES
+from yask_b200 import capi, multi
+from yask_b200.synth import hash_field, var_salt
+
+pytestmark = pytest.mark.gpu
+
+
+def load_inputs(s, ins):
+    for v in s.get_vars():
+        vi = v.info
+        name = vi.name.decode()
+        steps = range(vi.step_alloc) if vi.has_step else [0]
+        for t in steps:
+            f, l = v.halo_box(t)
+            v.set_elements_in_slice(ins[(name, t)], f, l)
+
+
+def run_gpu(stencil, n, steps, ins, fp_mode):
+    s = capi.Solution(stencil, elem_bytes=0)
+    s.set_overall_domain_size_vec(n)
+    s.set_option("fp_mode", fp_mode)
+    s.prepare_solution(0)
+    load_inputs(s, ins)
+    s.run_solution(0, steps - 1)
+    out = {}
+    for v in s.get_vars():
+        vi = v.info
+        if vi.is_output:
+            tl = vi.last_valid_step
+            out[vi.name.decode()] = (tl, v.get_elements_in_slice(*v.domain_box(tl)))
+    st = s.get_stats()
+    s.close()
+    return out, st
+
+
+@pytest.mark.parametrize("path", golden_cases("awp_elastic") + golden_cases("ssg"))
+def test_generated_vs_reference_golden(path):
+    meta, arrays = load_golden(path)
+    ins = regen_inputs(meta)
+    strict = "strict" in meta["ref_tag"]
+    out, st = run_gpu(meta["stencil"], meta["n"], meta["steps"], ins, 0 if strict else 2)
+    assert len(out) == 9 and st.kernel_launches == 2 * meta["steps"]
+    for name, (tl, got) in out.items():
+        ref = arrays[f"{name}.t{tl}"]
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        if strict:
+            it = np.uint32 if got.dtype == np.float32 else np.uint64
+            assert np.array_equal(got.view(it), ref.view(it)), name
+        else:
+            assert field_ulps(got, ref) <= 4.0, (name, field_ulps(got, ref))
+
+
+def synth_inputs(stencil, n, seed):
+    ir = O.gen_ir(stencil)
+    dt = np.float32 if ir["elem_bytes"] == 4 else np.float64
+    ins = {}
+    for v in ir["vars"]:
+        lo, hi = range_of(RANGES[stencil], v["name"])
+        vd = [d for d in v["dims"] if d != ir["step_dim"]]
+        first = [-v["halo"][d][0] for d in vd]
+        shape = [n[ir["domain_dims"].index(d)] + sum(v["halo"][d]) for d in vd]
+        has_step = bool(v["dims"]) and v["dims"][0] == ir["step_dim"]
+        for t in range(v["alloc_t"] if has_step else 1):
+            if shape:
+                ins[(v["name"], t)] = hash_field(seed, var_salt(v["name"], t), first, shape, lo, hi, dt)
+            else:
+                ins[(v["name"], t)] = np.array(hash_field(seed, var_salt(v["name"], t), (0,), (1,), lo, hi, dt)[0], dtype=dt)
+    return ins, ir
+
+
+@pytest.mark.parametrize("stencil,n,steps", [("awp_elastic", (37, 21, 150), 3), ("ssg", (19, 33, 131), 2)])
+def test_generated_vs_oracle_ragged(stencil, n, steps):
+    ins, ir = synth_inputs(stencil, n, 31)
+    out, _ = run_gpu(stencil, n, steps, ins, 0)
+    ref = O.gen_run(stencil, n, steps, ins)
+    for name, (tl, got) in out.items():
+        v = [x for x in ir["vars"] if x["name"] == name][0]
+        arr = ref[name][1]
+        r = arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) for i, d in enumerate(ir["domain_dims"]))]
+        it = np.uint32 if got.dtype == np.float32 else np.uint64
+        assert ref[name][0] == tl and np.array_equal(got.view(it), r.view(it)), name
+
+
+@pytest.mark.parametrize("stencil,n,grid,steps", [("awp_elastic", (40, 24, 64), (2, 1, 1), 3), ("awp_elastic", (24, 24, 48), (2, 2, 2), 2),
+                                                   ("ssg", (32, 20, 40), (1, 2, 2), 2), ("ssg", (41, 16, 32), (3, 1, 1), 2)])
+def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
+    """Two-stage solutions exchange halos after each stage; static vars (rho, mu, ...) are exchanged once."""
+    ir = O.gen_ir(stencil)
+
+    def fill(s):
+        for v in s.get_vars():
+            vi = v.info
+            lo, hi = range_of(RANGES[stencil], vi.name.decode())
+            for t in (range(vi.step_alloc) if vi.has_step else [0]):
+                v.fill_hash(t, 5, var_salt(vi.name.decode(), t), lo, hi)
+
+    def collect(solns):
+        out = {}
+        for s in solns:
+            for v in s.get_vars():
+                vi = v.info
+                if not vi.is_output:
+                    continue
+                f, l = v.domain_box(vi.last_valid_step)
+                a = out.setdefault(vi.name.decode(), np.zeros(n, v.dtype))
+                a[f[1]:l[1] + 1, f[2]:l[2] + 1, f[3]:l[3] + 1] = v.get_elements_in_slice(f, l)
+        return out
+
+    s0 = capi.Solution(stencil, elem_bytes=0)
+    s0.set_overall_domain_size_vec(n)
+    s0.set_option("fp_mode", 0)
+    s0.prepare_solution(0)
+    fill(s0)
+    s0.run_solution(0, steps - 1)
+    ref = collect([s0])
+    s0.close()
+    world = grid[0] * grid[1] * grid[2]
+    solns = []
+    for r in range(world):
+        s = capi.Solution(stencil, elem_bytes=0)
+        s.set_overall_domain_size_vec(n)
+        s.set_num_ranks_vec(grid)
+        s.set_rank_index_vec(multi.grid_coords(r, grid))
+        s.set_option("fp_mode", 0)
+        s.prepare_solution(0)
+        solns.append(s)
+    multi.connect_local(solns)
+    for s in solns:
+        fill(s)
+    for s in solns:
+        s.run_solution(0, steps - 1)
+    for s in solns:
+        s.sync()
+    got = collect(solns)
+    for s in solns:
+        s.close()
+    assert set(got) == set(ref) and len(got) == 9
+    for name in ref:
+        it = np.uint32 if ref[name].dtype == np.float32 else np.uint64
+        assert np.array_equal(got[name].view(it), ref[name].view(it)), name

@@ -35,3 +35,32 @@ def test_iso3dfd_oracle_bit_exact_vs_reference(path):
     if meta["steps"] >= 2:
         other = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], 8, meta["steps"], 2 - mode)
         assert not np.array_equal(other[8:-8, 8:-8, 8:-8].view(np.uint32), ref.view(np.uint32))
+
+
+# ---- emitter-generated solutions (awp_elastic fp32, ssg fp64) ---------------------------------------
+from tests.helpers import field_ulps  # noqa: E402
+
+
+def _domain(ir, name, arr):
+    v = [x for x in ir["vars"] if x["name"] == name][0]
+    return arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) for i, d in enumerate(ir["domain_dims"]))]
+
+
+@pytest.mark.parametrize("path", golden_cases("awp_elastic") + golden_cases("ssg"))
+def test_generated_oracle_vs_reference(path):
+    """Strict reference build: bit-exact.  Default (GCC-contracted) build: within 4 field-ulps -- GCC's FMA
+    choices for these expression trees are not restated, see DESIGN.md section 4."""
+    meta, arrays = load_golden(path)
+    ins = regen_inputs(meta)
+    out = O.gen_run(meta["stencil"], meta["n"], meta["steps"], ins)
+    ir = O.gen_ir(meta["stencil"])
+    assert len(out) == 9
+    for name, (tl, arr) in out.items():
+        ref = arrays[f"{name}.t{tl}"]
+        got = _domain(ir, name, arr)
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        if "strict" in meta["ref_tag"]:
+            it = np.uint32 if got.dtype == np.float32 else np.uint64
+            assert np.array_equal(got.view(it), ref.view(it)), name
+        else:
+            assert field_ulps(got, ref) <= 4.0, (name, field_ulps(got, ref))

@@ -254,8 +254,7 @@ int yb_solution_create(yb_solution** out, const char* stencil, int radius, int e
     if (!out || !stencil) return set_error(YB_EINVAL, "null argument");
     *out = nullptr;
     auto s = std::make_unique<Solution>();
-    if (elem_bytes == 0) elem_bytes = 4;
-    if (elem_bytes != 4 && elem_bytes != 8) return set_error(YB_EINVAL, "element bytes must be 4 or 8");
+    if (elem_bytes != 0 && elem_bytes != 4 && elem_bytes != 8) return set_error(YB_EINVAL, "element bytes must be 4 or 8");
     if (int rc = registry_create(stencil, radius, elem_bytes, s->spec, s->engine)) return rc;
     s->ndd = int(s->spec.domain_dims.size());
     for (auto& vs : s->spec.vars) {

@@ -1,0 +1,118 @@
+// Engine for emitter-generated solutions: turns a GenStencil table into a StencilSpec and launches
+// one kernel per part and stage (the reference runs the parts of a stage back to back over each
+// micro-block, /root/reference/src/kernel/lib/context.cpp:1158; parts of a stage are independent).
+#include "yb_core.h"
+#include "yb_gen.cuh"
+// generated solutions
+#include "gen/awp_elastic.gen.cuh"
+#include "gen/ssg.gen.cuh"
+
+namespace yb {
+
+using namespace gen;
+
+namespace {
+
+typedef void (*DescribeFn)(GenStencil&);
+struct GenEntry { const char* name; DescribeFn describe; };
+const GenEntry kGen[] = {
+    {"awp_elastic", awp_elastic_describe},
+    {"ssg", ssg_describe},
+};
+
+struct GenEngine : Engine {
+    GenStencil g;
+    int prepare(Solution& s) override {
+        if (s.spec.elem_bytes != g.elem_bytes)
+            return set_error(YB_EUNSUPPORTED, "solution '%s' was generated for %d-byte elements", g.name.c_str(), g.elem_bytes);
+        for (auto& st : g.stages)
+            for (auto& p : st.parts)
+                if (int(p.acc.size()) > GEN_MAX_ACC) return set_error(YB_EUNSUPPORTED, "part '%s' touches too many vars", p.name);
+        return 0;
+    }
+    int launch(Solution& s, int stage, int64_t t, const Box& box, cudaStream_t st) override {
+        if (box.empty()) return 0;
+        const GenStage& gs = g.stages[stage];
+        int n = 0;
+        for (auto& p : gs.parts) {
+            GenParams P{};
+            P.xb = int(box.b[0]); P.xe = int(box.e[0]);
+            P.yb = int(box.b[1]); P.ye = int(box.e[1]);
+            P.zb = int(box.b[2]); P.ze = int(box.e[2]);
+            for (size_t k = 0; k < p.acc.size(); k++) {
+                const Var& v = s.vars[p.acc[k].var];
+                const int slot = v.slot_of(t + p.acc[k].toff);
+                P.ptr[k] = v.slot_ptr(slot) + size_t(v.origin_offset()) * v.elem_bytes;
+                const Dim* d0 = v.domain_dim(0);
+                const Dim* d1 = v.domain_dim(1);
+                const Dim* d2 = v.domain_dim(2);
+                P.sx[k] = d0 ? d0->stride : 0;
+                P.sy[k] = d1 ? d1->stride : 0;
+                P.sz[k] = d2 ? d2->stride : 0;
+            }
+            GenKernelFn fn = p.fn[g.elem_bytes == 8 ? 1 : 0][s.fp_mode == 0 ? 0 : 1];
+            dim3 grd(unsigned((box.e[2] - box.b[2] + GEN_BLOCK - 1) / GEN_BLOCK), unsigned(box.e[1] - box.b[1]), unsigned(box.e[0] - box.b[0]));
+            if (grd.y > 65535 || grd.z > 65535) return set_error(YB_EUNSUPPORTED, "domain too large in x or y for the generated kernels");
+            fn<<<grd, GEN_BLOCK, 0, st>>>(P);
+            YB_CUDA(cudaGetLastError());
+            n++;
+        }
+        return n;
+    }
+};
+
+}  // namespace
+
+int gen_registry_size() { return int(sizeof(kGen) / sizeof(kGen[0])); }
+const char* gen_registry_name(int i) { return kGen[i].name; }
+
+int gen_registry_create(const std::string& name, int elem_bytes, StencilSpec& spec, std::unique_ptr<Engine>& eng) {
+    for (auto& e : kGen) {
+        if (name != e.name) continue;
+        auto ge = std::unique_ptr<GenEngine>(new GenEngine());
+        e.describe(ge->g);
+        const GenStencil& g = ge->g;
+        if (elem_bytes != 0 && elem_bytes != g.elem_bytes)
+            return set_error(YB_EUNSUPPORTED, "solution '%s' is generated for %d-byte elements (asked for %d)", e.name, g.elem_bytes, elem_bytes);
+        spec = StencilSpec();
+        spec.name = g.name;
+        spec.description = "generated from the reference DSL definition by yask_b200/emitter";
+        spec.step_dim = g.step_dim;
+        spec.domain_dims = g.domain_dims;
+        spec.elem_bytes = g.elem_bytes;
+        for (auto& gv : g.vars) {
+            VarSpec v;
+            v.name = gv.name;
+            v.step_alloc = gv.alloc_t;
+            v.is_output = gv.is_output;
+            v.l1_norm = gv.l1_norm;
+            for (auto* dn : gv.dims) {
+                DimSpec d;
+                d.name = dn;
+                if (g.step_dim == dn) { d.kind = DIM_STEP; }
+                else {
+                    d.kind = DIM_DOMAIN;
+                    for (size_t k = 0; k < g.domain_dims.size(); k++)
+                        if (g.domain_dims[k] == dn) { d.domain_index = int(k); d.halo_l = gv.halo_l[k]; d.halo_r = gv.halo_r[k]; }
+                }
+                v.dims.push_back(d);
+            }
+            spec.vars.push_back(v);
+        }
+        for (auto& gs : g.stages) {
+            StageSpec st;
+            st.name = gs.name;
+            for (auto& p : gs.parts) {
+                st.fp_ops += p.fp_ops; st.reads += p.reads; st.writes += p.writes;
+                for (int o : p.outs) st.outputs.push_back(p.acc[o].var);
+                for (auto& a : p.acc) st.inputs.push_back(a.var);
+            }
+            spec.stages.push_back(st);
+        }
+        eng = std::move(ge);
+        return 0;
+    }
+    return YB_EINVAL;
+}
+
+}  // namespace yb

@@ -4,6 +4,11 @@
 
 namespace yb {
 
+// emitter-generated solutions (yb_gen.cu)
+int gen_registry_size();
+const char* gen_registry_name(int i);
+int gen_registry_create(const std::string& name, int elem_bytes, StencilSpec& spec, std::unique_ptr<Engine>& eng);
+
 namespace {
 struct Entry { const char* name; int default_radius; };
 const Entry kEntries[] = {
@@ -11,17 +16,24 @@ const Entry kEntries[] = {
 };
 }  // namespace
 
-int registry_size() { return int(sizeof(kEntries) / sizeof(kEntries[0])); }
-const char* registry_name(int i) { return (i >= 0 && i < registry_size()) ? kEntries[i].name : ""; }
+const int kNumBuiltin = int(sizeof(kEntries) / sizeof(kEntries[0]));
+int registry_size() { return kNumBuiltin + gen_registry_size(); }
+const char* registry_name(int i) {
+    if (i < 0 || i >= registry_size()) return "";
+    return i < kNumBuiltin ? kEntries[i].name : gen_registry_name(i - kNumBuiltin);
+}
 
 int registry_create(const std::string& name, int radius, int elem_bytes, StencilSpec& spec, std::unique_ptr<Engine>& eng) {
     if (name == "iso3dfd") {
         if (radius <= 0) radius = 8;
+        if (elem_bytes == 0) elem_bytes = 4;
         if (radius > 8) return set_error(YB_EUNSUPPORTED, "iso3dfd: radius %d > 8 is not supported", radius);
         spec = iso3dfd_spec(radius, elem_bytes, false);
         eng = make_iso3dfd_engine();
         return 0;
     }
+    int rc = gen_registry_create(name, elem_bytes, spec, eng);
+    if (rc != YB_EINVAL) return rc;
     return set_error(YB_EINVAL, "unknown stencil solution '%s'", name.c_str());
 }
 

@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""CUDA emitter for YASK stencil solutions (build-time tool).
+
+Pipeline:  DSL (src/stencils/*.cpp, unchanged)  ->  the reference's own compiler FRONT-END
+(`yask_compiler.exe`: parsing, CSE/combination, dependency analysis, part/stage formation, halo and
+step-allocation analysis; /root/reference/src/compiler/lib/Solution.cpp:127-160)  ->  this emitter,
+which replaces the reference's AVX/C++ back-end (`Cpp.cpp`, `CppIntrin.cpp`, `YaskKernel.cpp`).
+
+The front-end is used as a black box through the file it already writes: we ask it for its C++ target
+and read (a) the per-var metadata block (alloc_t, halos, L1 norms -- what the generated context ctor
+encodes, YaskKernel.cpp:730-) and (b) the `calc_scalar()` bodies, which list every part's expression tree
+as a sequence of single-assignment statements in evaluation order with 16-digit constants
+(Cpp.cpp:39-53).  The vector path the reference actually runs evaluates the SAME trees with the constants
+rounded to the element type, every op in the element type -- that is the semantics we emit.
+
+Outputs (committed; nothing at run time needs the reference):
+  yask_b200/csrc/gen/<name>.gen.cuh   CUDA kernels (one per part) + the StencilSpec table
+  oracle/gen/<name>.gen.h             plain-C restatement of the same statements (TEST oracle)
+  yask_b200/csrc/gen/<name>.json      the parsed IR (tests use it for var names / halos)
+
+Unsupported on purpose (reported, not silently dropped): sub-domain / step conditions, scratch vars,
+math functions, misc dims.
+
+usage: python -m yask_b200.emitter.yask_cuda_emit --stencil awp_elastic --elem-bytes 4 [--radius R] [--name NAME]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+COMPILER = os.path.join(ROOT, "oracle", "_ref", "yask", "bin", "yask_compiler.exe")
+COMPILER_LIB = os.path.join(ROOT, "oracle", "_ref", "yask", "lib")
+
+
+class EmitError(RuntimeError):
+    pass
+
+
+# ----------------------------------------------------------------------------------------------------
+# front-end: run the reference compiler and parse its output
+# ----------------------------------------------------------------------------------------------------
+def run_frontend(stencil: str, elem_bytes: int, radius: int | None) -> str:
+    if not os.path.exists(COMPILER):
+        raise EmitError(f"{COMPILER} missing: run oracle/build_ref.sh first (build container only)")
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "gen.hpp")
+        cmd = [COMPILER, "-stencil", stencil, "-target", "avx512", "-elem-bytes", str(elem_bytes), "-p", out]
+        if radius:
+            cmd += ["-radius", str(radius)]
+        env = dict(os.environ, LD_LIBRARY_PATH=COMPILER_LIB + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.exists(out):
+            raise EmitError("reference compiler failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+        return open(out).read()
+
+
+_NUM = r"[-+]?(?:\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|\d+(?:[eE][-+]?\d+)?)"
+
+
+def parse_index(tok: str, dims: list[str]):
+    """'x' | '(x - 1)' | '(t + 1)' | '3' -> (dim or None, offset)"""
+    tok = tok.strip()
+    m = re.fullmatch(r"\(?\s*([A-Za-z_]\w*)\s*(?:([-+])\s*(\d+))?\s*\)?", tok)
+    if m:
+        off = int(m.group(3)) if m.group(3) else 0
+        return m.group(1), (-off if m.group(2) == "-" else off)
+    if re.fullmatch(r"-?\d+", tok):
+        return None, int(tok)
+    raise EmitError(f"unsupported index expression '{tok}'")
+
+
+class Parser:
+    """Tiny recursive-descent parser for the RHS of generated statements: + - * / with C precedence and
+    left associativity, parentheses, unary minus, numeric literals, expr_temp refs and read placeholders."""
+
+    def __init__(self, text: str):
+        self.toks = re.findall(r"@\d+|expr_temp\d+|" + r"\d+\.\d*(?:[eE][-+]?\d+)?|\d+(?:[eE][-+]?\d+)?" + r"|[-+*/()]", text)
+        joined = "".join(self.toks)
+        if joined != re.sub(r"\s+", "", text):
+            raise EmitError(f"unsupported construct in expression: '{text}'")
+        self.i = 0
+
+    def peek(self):
+        return self.toks[self.i] if self.i < len(self.toks) else None
+
+    def next(self):
+        t = self.peek()
+        self.i += 1
+        return t
+
+    def parse(self):
+        e = self.expr()
+        if self.peek() is not None:
+            raise EmitError("trailing tokens in expression")
+        return e
+
+    def expr(self):
+        e = self.term()
+        while self.peek() in ("+", "-"):
+            op = self.next()
+            e = ("add" if op == "+" else "sub", e, self.term())
+        return e
+
+    def term(self):
+        e = self.unary()
+        while self.peek() in ("*", "/"):
+            op = self.next()
+            e = ("mul" if op == "*" else "div", e, self.unary())
+        return e
+
+    def unary(self):
+        if self.peek() == "-":
+            self.next()
+            nxt = self.peek()
+            if nxt and re.fullmatch(r"\d.*", nxt):   # negative literal
+                return ("const", "-" + self.next())
+            return ("neg", self.unary())
+        if self.peek() == "+":
+            self.next()
+        return self.atom()
+
+    def atom(self):
+        t = self.next()
+        if t is None:
+            raise EmitError("unexpected end of expression")
+        if t == "(":
+            e = self.expr()
+            if self.next() != ")":
+                raise EmitError("missing ')'")
+            return e
+        if t.startswith("@"):
+            return ("read", int(t[1:]))
+        if t.startswith("expr_temp"):
+            return ("tmp", int(t[len("expr_temp"):]))
+        return ("const", t)
+
+
+def parse_generated(text: str, name: str) -> dict:
+    ir: dict = {"name": name, "vars": [], "stages": []}
+    # ---- element size, dims --------------------------------------------------------------------------
+    m = re.search(r"#define REAL_BYTES \((\d+)\)", text) or re.search(r"REAL_BYTES\s+\(?(\d+)\)?", text)
+    ir["elem_bytes"] = int(m.group(1)) if m else None
+    # ---- vars -----------------------------------------------------------------------------------------
+    for m in re.finditer(r"// The (?:(\d+)-D var|scalar value) '(\w+)', which is (updated by one or more equations|not updated by any equation)[^\n]*\n"
+                         r"(?:\s*// Dimensions in parameter \(declaration\) order: ([^\n]*)\n)?", text):
+        vname = m.group(2)
+        dims = re.findall(r"'(\w+)'\(#\d+\)", m.group(4) or "")
+        if any(v["name"] == vname for v in ir["vars"]):
+            continue
+        ir["vars"].append({"name": vname, "dims": dims, "is_output": m.group(3).startswith("updated")})
+    if not ir["vars"]:
+        raise EmitError("no vars found in the generated file")
+    step_dim = None
+    dd: list[str] = []
+    for v in ir["vars"]:
+        if v["is_output"] and v["dims"]:
+            step_dim = v["dims"][0]
+            if len(v["dims"]) - 1 > len(dd):
+                dd = v["dims"][1:]
+    ir["step_dim"], ir["domain_dims"] = step_dim, dd
+    for v in ir["vars"]:
+        n = v["name"]
+        m = re.search(rf"const idx_t {n}_alloc_t = (\d+);", text)
+        v["alloc_t"] = int(m.group(1)) if m else 1
+        m = re.search(rf"const int {n}_l1_norm = (\d+);", text)
+        v["l1_norm"] = int(m.group(1)) if m else 0
+        v["halo"] = {}
+        for d in v["dims"]:
+            if d == step_dim:
+                continue
+            if d not in dd:
+                raise EmitError(f"var '{n}' uses misc dim '{d}': not supported by this emitter")
+            ml = re.search(rf"const idx_t {n}_left_halo_{d} = (\d+);", text)
+            mr = re.search(rf"const idx_t {n}_right_halo_{d} = (\d+);", text)
+            v["halo"][d] = [int(ml.group(1)) if ml else 0, int(mr.group(1)) if mr else 0]
+    vindex = {v["name"]: i for i, v in enumerate(ir["vars"])}
+    # ---- stages / parts ---------------------------------------------------------------------------------
+    stage_pos = [(m.start(), m.group(1)) for m in re.finditer(r"//////// Stencil stage '(\w+)' //////", text)]
+    part_iter = list(re.finditer(r"////// Stencil part '(\w+)' ([^\n]*?)//////", text))
+    if not part_iter:
+        raise EmitError("no parts found")
+    for pm in part_iter:
+        pname, cond = pm.group(1), pm.group(2)
+        if "w/o domain condition" not in cond or "w/o step condition" not in cond:
+            raise EmitError(f"part '{pname}' has a sub-domain or step condition: not supported by this emitter")
+        stage = [s for pos, s in stage_pos if pos < pm.start()][-1]
+        body_start = text.index("static void calc_scalar(", pm.end())
+        body_end = text.index("} // calc_scalar.", body_start)
+        body = text[body_start:body_end]
+        head = text[pm.end():body_start]
+        if re.search(r"_is_scratch = true", head):
+            raise EmitError(f"part '{pname}' is a scratch part: not supported by this emitter")
+        part = {"name": pname, "stage": stage,
+                "fp_ops": int(re.search(r"_scalar_fp_ops = (\d+);", head).group(1)),
+                "reads": int(re.search(r"_scalar_points_read = (\d+);", head).group(1)),
+                "writes": int(re.search(r"_scalar_points_written = (\d+);", head).group(1)),
+                "accesses": [], "stmts": [], "outputs": []}
+        ptr = {}   # expr_tempN (pointer) -> var name
+        for m in re.finditer(r"auto\* (expr_temp\d+) = core_data->var_(\w+)_core_p\.get\(\);", body):
+            ptr[m.group(1)] = m.group(2)
+        acc_index: dict = {}
+
+        def access(var: str, idx_text: str):
+            idxs = [s for s in re.split(r",\s*(?![^()]*\))", idx_text.strip()) if s.strip()] if idx_text.strip() else []
+            v = ir["vars"][vindex[var]]
+            if len(idxs) != len(v["dims"]):
+                raise EmitError(f"index count mismatch for var '{var}'")
+            toff = 0
+            offs = {}
+            for d, it in zip(v["dims"], idxs):
+                dim, off = parse_index(it, v["dims"])
+                if dim is None:
+                    raise EmitError("constant (misc) index not supported")
+                if dim != d:
+                    raise EmitError(f"var '{var}': index '{it}' does not follow declared dim '{d}'")
+                if d == step_dim:
+                    toff = off
+                else:
+                    offs[d] = off
+            key = (var, toff)
+            if key not in acc_index:
+                acc_index[key] = len(part["accesses"])
+                part["accesses"].append({"var": var, "toff": toff})
+            return acc_index[key], [offs.get(d, 0) for d in dd]
+
+        for line in body.splitlines():
+            line = line.strip()
+            if not line or line.startswith("//"):
+                continue
+            m = re.fullmatch(r"real_t (expr_temp\d+) = (.*);", line)
+            if m:
+                reads = []
+
+                def repl(mm):
+                    a, offs = access(ptr[mm.group(1)], mm.group(2))
+                    reads.append((a, offs))
+                    return f"@{len(reads) - 1}"
+
+                rhs = re.sub(r"(expr_temp\d+)->read_elem\(\{([^}]*)\}, \w+\)", repl, m.group(2))
+                tree = Parser(rhs).parse()
+                part["stmts"].append({"dst": int(m.group(1)[len("expr_temp"):]), "tree": tree, "reads": reads})
+                continue
+            m = re.fullmatch(r"(expr_temp\d+)->write_elem\((expr_temp\d+), \{([^}]*)\}, \w+\);", line)
+            if m:
+                a, offs = access(ptr[m.group(1)], m.group(3))
+                if any(offs):
+                    raise EmitError("write with a spatial offset is not supported")
+                part["outputs"].append({"access": a, "src": int(m.group(2)[len("expr_temp"):])})
+                continue
+            if re.match(r"(static void calc_scalar|host_assert|auto& thread_core_data|idx_t \w+ = idxs|auto\* expr_temp|const auto step_temp)", line):
+                continue
+            raise EmitError(f"unrecognised statement in calc_scalar of {pname}: {line[:120]}")
+        if not part["outputs"]:
+            raise EmitError(f"part {pname} writes nothing")
+        st = next((s for s in ir["stages"] if s["name"] == stage), None)
+        if st is None:
+            st = {"name": stage, "parts": []}
+            ir["stages"].append(st)
+        st["parts"].append(part)
+    return ir
+
+
+# ----------------------------------------------------------------------------------------------------
+# back-ends
+# ----------------------------------------------------------------------------------------------------
+def _const_text(tok: str) -> str:
+    return tok if re.search(r"[.eE]", tok) else tok + ".0"
+
+
+def gen_expr(tree, rd, ops) -> str:
+    k = tree[0]
+    if k == "const":
+        return f"C({_const_text(tree[1])})"
+    if k == "tmp":
+        return f"e{tree[1]}"
+    if k == "read":
+        return rd(tree[1])
+    if k == "neg":
+        return f"(-{gen_expr(tree[1], rd, ops)})"
+    a, b = gen_expr(tree[1], rd, ops), gen_expr(tree[2], rd, ops)
+    return f"{ops[k]}({a}, {b})"
+
+
+def _stmt_lines(part, ndd, indent="    "):
+    out = []
+    for s in part["stmts"]:
+        def rd(i, s=s):
+            a, offs = s["reads"][i]
+            offs = list(offs) + [0] * (3 - len(offs))
+            return f"RD({a}, {offs[0]}, {offs[1]}, {offs[2]})"
+        out.append(f"{indent}const T e{s['dst']} = {gen_expr(s['tree'], rd, {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'})};")
+    for o in part["outputs"]:
+        out.append(f"{indent}WR({o['access']}, e{o['src']});")
+    return out
+
+
+def emit_cuda(ir: dict) -> str:
+    n = ir["name"]
+    ident = re.sub(r"\W", "_", n)
+    L = []
+    L.append(f"// GENERATED by yask_b200/emitter/yask_cuda_emit.py from the reference compiler's analysis of solution '{n}'.")
+    L.append("// Do not edit: re-run the emitter.  One kernel per solution part; statements are the part's expression")
+    L.append("// tree in the reference's evaluation order (generated calc_scalar(), emitted by")
+    L.append("// /root/reference/src/compiler/lib/YaskKernel.cpp:429- / Cpp.cpp), every op in the element type.")
+    L.append("#pragma once")
+    L.append('#include "../yb_gen.cuh"')
+    L.append("namespace yb { namespace gen {")
+    for st in ir["stages"]:
+        for p in st["parts"]:
+            L.append(f"// part '{p['name']}' of stage '{st['name']}': {p['fp_ops']} FP ops, {p['reads']} reads, {p['writes']} writes per point")
+            L.append("template <typename T, int MODE>")
+            L.append(f"__global__ void __launch_bounds__(GEN_BLOCK) {ident}_{p['name']}_kernel(const __grid_constant__ GenParams P) {{")
+            L.append("    GEN_KERNEL_PROLOGUE")
+            L.extend(_stmt_lines(p, len(ir["domain_dims"])))
+            L.append("}")
+    # spec table
+    L.append(f"inline void {ident}_describe(GenStencil& g) {{")
+    L.append(f'    g.name = "{n}"; g.elem_bytes = {ir["elem_bytes"]}; g.step_dim = "{ir["step_dim"]}";')
+    L.append("    g.domain_dims = {" + ", ".join(f'"{d}"' for d in ir["domain_dims"]) + "};")
+    for v in ir["vars"]:
+        dims = ", ".join(f'"{d}"' for d in v["dims"])
+        hl = ", ".join(str(v["halo"].get(d, [0, 0])[0]) for d in ir["domain_dims"])
+        hr = ", ".join(str(v["halo"].get(d, [0, 0])[1]) for d in ir["domain_dims"])
+        L.append(f'    g.vars.push_back(GenVar{{"{v["name"]}", {{{dims}}}, {v["alloc_t"]}, {str(v["is_output"]).lower()}, {v["l1_norm"]}, {{{hl}}}, {{{hr}}}}});')
+    vidx = {v["name"]: i for i, v in enumerate(ir["vars"])}
+    for st in ir["stages"]:
+        L.append(f'    g.stages.push_back(GenStage{{"{st["name"]}", {{}}}});')
+        for p in st["parts"]:
+            acc = ", ".join(f"{{{vidx[a['var']]}, {a['toff']}}}" for a in p["accesses"])
+            outs = ", ".join(str(o["access"]) for o in p["outputs"])
+            k = f"{ident}_{p['name']}_kernel"
+            fns = f"{{{{GEN_FN({k}, float, 0), GEN_FN({k}, float, 1)}}, {{GEN_FN({k}, double, 0), GEN_FN({k}, double, 1)}}}}"
+            L.append(f'    g.stages.back().parts.push_back(GenPart{{"{p["name"]}", {p["fp_ops"]}, {p["reads"]}, {p["writes"]}, {{{acc}}}, {{{outs}}}, {fns}}});')
+    L.append("}")
+    L.append("} }  // namespace yb::gen")
+    return "\n".join(L) + "\n"
+
+
+def emit_oracle(ir: dict) -> str:
+    n = ir["name"]
+    ident = re.sub(r"\W", "_", n)
+    T = "float" if ir["elem_bytes"] == 4 else "double"
+    L = []
+    L.append(f"/* GENERATED by yask_b200/emitter/yask_cuda_emit.py -- TEST INFRASTRUCTURE ONLY (CPU oracle for '{n}').")
+    L.append(" * Plain-C restatement of the statements the reference compiler emits for each part (generated")
+    L.append(" * calc_scalar()), evaluated as the reference's VECTOR path does: constants rounded to the element")
+    L.append(" * type, every operation in the element type, no contraction (compile with -ffp-contract=off).")
+    L.append(" * Pinned against the reference built with -ffp-contract=off (tests/golden). */")
+    for st in ir["stages"]:
+        for p in st["parts"]:
+            L.append(f"static void yo_{ident}_{p['name']}(const yo_gen_args* A) {{")
+            L.append(f"    typedef {T} T;")
+            L.append("    YO_GEN_LOOP_BEGIN")
+            L.extend(_stmt_lines(p, len(ir["domain_dims"]), indent="        "))
+            L.append("    YO_GEN_LOOP_END")
+            L.append("}")
+    L.append(f"static const yo_gen_part yo_{ident}_parts[] = {{")
+    for st in ir["stages"]:
+        for p in st["parts"]:
+            L.append(f'    {{"{p["name"]}", yo_{ident}_{p["name"]}, {len(p["accesses"])}}},')
+    L.append("};")
+    return "\n".join(L) + "\n"
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stencil", required=True)
+    ap.add_argument("--elem-bytes", type=int, default=4)
+    ap.add_argument("--radius", type=int, default=0)
+    ap.add_argument("--name", default=None, help="registry name of the generated solution (default: stencil)")
+    ap.add_argument("--from-file", default=None, help="parse this already generated file instead of running the compiler")
+    a = ap.parse_args(argv)
+    name = a.name or a.stencil
+    text = open(a.from_file).read() if a.from_file else run_frontend(a.stencil, a.elem_bytes, a.radius or None)
+    ir = parse_generated(text, name)
+    if ir["elem_bytes"] is None:
+        ir["elem_bytes"] = a.elem_bytes
+    ir["stencil"], ir["radius"] = a.stencil, a.radius
+    gdir = os.path.join(ROOT, "yask_b200", "csrc", "gen")
+    odir = os.path.join(ROOT, "oracle", "gen")
+    os.makedirs(gdir, exist_ok=True)
+    os.makedirs(odir, exist_ok=True)
+    ident = re.sub(r"\W", "_", name)
+    open(os.path.join(gdir, f"{ident}.gen.cuh"), "w").write(emit_cuda(ir))
+    open(os.path.join(odir, f"{ident}.gen.h"), "w").write(emit_oracle(ir))
+    slim = {k: v for k, v in ir.items() if k != "stages"}
+    slim["stages"] = [{"name": s["name"], "parts": [{"name": p["name"], "fp_ops": p["fp_ops"], "reads": p["reads"], "writes": p["writes"],
+                                                       "accesses": p["accesses"], "outputs": p["outputs"]} for p in s["parts"]]} for s in ir["stages"]]
+    json.dump(slim, open(os.path.join(gdir, f"{ident}.json"), "w"), indent=1)
+    nst = sum(len(p["stmts"]) for s in ir["stages"] for p in s["parts"])
+    print(f"emitted {name}: {len(ir['vars'])} vars, {len(ir['stages'])} stage(s), {nst} statements, elem_bytes {ir['elem_bytes']}")
+
+
+if __name__ == "__main__":
+    main()
