@@ -144,6 +144,12 @@ int yb_solution_is_prepared(const yb_solution* s);
 int yb_num_vars(const yb_solution* s);
 int yb_var_index(const yb_solution* s, const char* name);     /* <0 if unknown */
 int yb_var_info_get(const yb_solution* s, int var, yb_var_info* out);
+/* User-created vars (yk_solution::new_var / new_fixed_size_var, aux/yk_solution_api.hpp:994-1089): not read
+ * or written by the stencil kernels.  dim names matching the step dim / a domain dim take that role, any
+ * other name is a misc dim.  sizes == NULL: sized like the solution (new_var); otherwise fixed sizes (one per
+ * dim: steps / domain points / misc extent).  Returns the new var's index (>= 0) or a negative error. */
+int yb_var_create(yb_solution* s, const char* name, int ndims, const char* const* dim_names, const int64_t* sizes);
+
 /* Set per-var geometry before prepare (set_halo_size / set_min_pad_size, yk_var_api.hpp:1180-1290). */
 int yb_var_set_min_pad(yb_solution* s, int var, int dim, int64_t left, int64_t right);
 
@@ -168,6 +174,9 @@ int yb_var_fill_hash(yb_solution* s, int var, int64_t step, uint32_t seed, uint3
 int yb_var_checksum(yb_solution* s, int var, int64_t step, uint64_t* out);
 /* Raw device pointer of a step slot (get_raw_storage_buffer, yk_var_api.hpp:1399-1437). */
 int yb_var_device_ptr(yb_solution* s, int var, int64_t step, void** out);
+
+/* Plain device->host copy of `bytes` bytes (for host snapshots of raw storage). */
+int yb_copy_to_host(void* host_dst, const void* dev_src, size_t bytes);
 
 /* ---- run (yk_solution::run_solution, context.cpp:220-624) ----------------------------------- */
 int yb_solution_run(yb_solution* s, int64_t first_step, int64_t last_step);

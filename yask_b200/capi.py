@@ -57,9 +57,9 @@ ABI_SYMBOLS = [
     "yb_set_rank_domain_size", "yb_set_overall_domain_size", "yb_set_num_ranks", "yb_set_rank_index", "yb_set_min_pad_size",
     "yb_get_rank_domain_size", "yb_get_overall_domain_size", "yb_get_num_ranks", "yb_get_rank_index",
     "yb_get_first_rank_domain_index", "yb_get_last_rank_domain_index", "yb_set_option", "yb_get_option", "yb_set_stream",
-    "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_set_min_pad",
+    "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_create", "yb_var_set_min_pad",
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
-    "yb_var_set_slice_same", "yb_var_fill_hash", "yb_var_checksum", "yb_var_device_ptr", "yb_solution_run", "yb_solution_sync",
+    "yb_var_set_slice_same", "yb_var_fill_hash", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
     "yb_exchange_halos",
 ]
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         L.yb_num_vars.argtypes = [p]
         L.yb_var_index.argtypes = [p, C.c_char_p]
         L.yb_var_info_get.argtypes = [p, i32, C.POINTER(VarInfo)]
+        L.yb_var_create.argtypes = [p, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(i64)]
         L.yb_var_set_min_pad.argtypes = [p, i32, i32, i64, i64]
         for nm in ("yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device"):
             getattr(L, nm).argtypes = [p, i32, p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
@@ -320,6 +321,14 @@ class Solution:
 
     def get_var(self, name: str) -> Var:
         return Var(self, _chk(lib().yb_var_index(self._h, name.encode())))
+
+    def new_fixed_size_var(self, name: str, dims, sizes) -> Var:
+        names = (C.c_char_p * len(dims))(*[d.encode() for d in dims])
+        return Var(self, _chk(lib().yb_var_create(self._h, name.encode(), len(dims), names, _arr(sizes))))
+
+    def new_var(self, name: str, dims) -> Var:
+        names = (C.c_char_p * len(dims))(*[d.encode() for d in dims])
+        return Var(self, _chk(lib().yb_var_create(self._h, name.encode(), len(dims), names, None)))
 
     def get_vars(self):
         return [Var(self, i) for i in range(self.get_num_vars())]

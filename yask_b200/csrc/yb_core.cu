@@ -86,11 +86,15 @@ static void compute_var_geometry(Solution& s, Var& v) {
         if (v.dims[i].spec.kind == DIM_DOMAIN) last_domain = i;
     for (int i = 0; i < nd; i++) {
         Dim& d = v.dims[i];
-        if (d.spec.kind == DIM_STEP) { d.domain = v.spec.step_alloc; d.alloc = d.domain; d.stride = 0; continue; }
+        if (d.spec.kind == DIM_STEP) {
+            if (v.spec.fixed_size) v.spec.step_alloc = int(v.spec.fixed_sizes[i]);
+            d.domain = v.spec.step_alloc; d.alloc = d.domain; d.stride = 0; continue;
+        }
         if (d.spec.kind == DIM_MISC) { d.domain = d.spec.misc_size; d.alloc = d.domain; d.pad_l = d.pad_r = 0; continue; }
         int dd = d.spec.domain_index;
         d.domain = s.rank_size[dd];
         d.rank_offset = s.rank_offset[dd];
+        if (v.spec.fixed_size) { d.domain = v.spec.fixed_sizes[i]; d.rank_offset = 0; }
         int64_t pl = std::max({d.spec.halo_l, d.min_pad_l, s.min_pad[dd]});
         int64_t pr = std::max({d.spec.halo_r, d.min_pad_r, s.min_pad[dd]});
         if (i == nd - 1 && i == last_domain) {
@@ -294,16 +298,18 @@ int yb_set_rank_domain_size(yb_solution* s_, int dim, int64_t n) {
     Solution* s = SOL(s_);
     if (int rc = check_dim(s, dim)) return rc;
     if (int rc = not_prepared(s, "set_rank_domain_size")) return rc;
-    if (n < 1) return set_error(YB_EINVAL, "domain size must be positive");
-    s->req_rank_size[dim] = n; s->req_overall_size[dim] = 0;
+    if (n < 0) return set_error(YB_EINVAL, "domain size must not be negative");
+    s->req_rank_size[dim] = n;            // 0 = derive from the overall size (settings.cpp:196-200)
+    if (n > 0) s->req_overall_size[dim] = 0;
     return 0;
 }
 int yb_set_overall_domain_size(yb_solution* s_, int dim, int64_t n) {
     Solution* s = SOL(s_);
     if (int rc = check_dim(s, dim)) return rc;
     if (int rc = not_prepared(s, "set_overall_domain_size")) return rc;
-    if (n < 1) return set_error(YB_EINVAL, "domain size must be positive");
-    s->req_overall_size[dim] = n; s->req_rank_size[dim] = 0;
+    if (n < 0) return set_error(YB_EINVAL, "domain size must not be negative");
+    s->req_overall_size[dim] = n;         // 0 = derive from the rank size
+    if (n > 0) s->req_rank_size[dim] = 0;
     return 0;
 }
 int yb_set_num_ranks(yb_solution* s_, int dim, int64_t n) {
@@ -462,6 +468,50 @@ int yb_var_info_get(const yb_solution* s_, int var, yb_var_info* out) {
     return 0;
 }
 
+int yb_var_create(yb_solution* s_, const char* name, int ndims, const char* const* dim_names, const int64_t* sizes) {
+    Solution* s = SOL(s_);
+    if (!s || !name || (ndims > 0 && !dim_names)) return set_error(YB_EINVAL, "null argument");
+    if (ndims < 0 || ndims > YB_MAX_DIMS) return set_error(YB_EINVAL, "a var may have at most %d dims", YB_MAX_DIMS);
+    for (auto& v : s->vars)
+        if (v.spec.name == name) return set_error(YB_EINVAL, "var '%s' already exists", name);
+    Var v;
+    v.spec.name = name;
+    v.spec.user_var = true;
+    v.spec.fixed_size = sizes != nullptr;
+    v.elem_bytes = s->spec.elem_bytes;
+    for (int i = 0; i < ndims; i++) {
+        DimSpec d;
+        d.name = dim_names[i];
+        for (int j = 0; j < i; j++)
+            if (d.name == dim_names[j]) return set_error(YB_EINVAL, "dim '%s' repeated in var '%s'", dim_names[i], name);
+        if (d.name == s->spec.step_dim) {
+            if (i != 0) return set_error(YB_EINVAL, "step dim '%s' must be the first dim of var '%s'", dim_names[i], name);
+            d.kind = DIM_STEP;
+        } else {
+            d.kind = DIM_MISC;
+            for (int k = 0; k < s->ndd; k++)
+                if (d.name == s->spec.domain_dims[k]) { d.kind = DIM_DOMAIN; d.domain_index = k; }
+            if (d.kind == DIM_MISC) d.misc_size = sizes ? sizes[i] : 1;
+        }
+        if (sizes) {
+            if (sizes[i] < 1) return set_error(YB_EINVAL, "size of dim '%s' must be positive", dim_names[i]);
+            v.spec.fixed_sizes.push_back(sizes[i]);
+        }
+        v.spec.dims.push_back(d);
+    }
+    v.spec.step_alloc = 1;
+    for (auto& ds : v.spec.dims) { Dim d; d.spec = ds; v.dims.push_back(d); }
+    if (s->prepared) {
+        YB_CUDA(cudaSetDevice(s->device));
+        compute_var_geometry(*s, v);
+        YB_CUDA(cudaMalloc(&v.dev, v.bytes()));
+        YB_CUDA(cudaMemsetAsync(v.dev, 0, v.bytes(), s->stream()));
+        if (s->halo) return set_error(YB_EUNSUPPORTED, "vars cannot be added to a prepared multi-rank solution");
+    }
+    s->vars.push_back(std::move(v));
+    return int(s->vars.size()) - 1;
+}
+
 int yb_var_set_min_pad(yb_solution* s_, int var, int dim, int64_t left, int64_t right) {
     Solution* s = SOL(s_);
     if (int rc = check_var(s, var)) return rc;
@@ -571,6 +621,12 @@ int yb_var_device_ptr(yb_solution* s_, int var, int64_t step, void** out) {
     if (!out) return set_error(YB_EINVAL, "null output");
     Var& v = s->vars[var];
     *out = v.slot_ptr(v.slot_of(step));
+    return 0;
+}
+
+int yb_copy_to_host(void* host_dst, const void* dev_src, size_t bytes) {
+    if (!host_dst || !dev_src) return set_error(YB_EINVAL, "null argument");
+    YB_CUDA(cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -34,6 +34,9 @@ struct VarSpec {
     std::vector<DimSpec> dims;  // declared order; step dim (if any) first
     int step_alloc = 1;         // alloc_t
     bool is_output = false;
+    bool user_var = false;      // created through yb_var_create (not touched by kernels)
+    bool fixed_size = false;    // user var with explicit sizes (not tied to the rank domain)
+    std::vector<int64_t> fixed_sizes;
     int l1_norm = 0;            // max L1 distance of any read -> which neighbours need halos
 };
 
