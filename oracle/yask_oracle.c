@@ -226,8 +226,8 @@ typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } y
         for (int64_t y = 0; y < A->ny; y++)                                    \
             for (int64_t z = 0; z < A->nz; z++) {
 #define YO_GEN_LOOP_END }
-#define RD(a, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
-#define WR(a, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
+#define RD(a, m, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
+#define WR(a, m, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
 #define C(v) ((T)(v))
 #define ADD(a, b) ((a) + (b))
 #define SUB(a, b) ((a) - (b))

@@ -32,10 +32,9 @@ if __name__ == "__main__":
     res = []
     base = None
     variants = []
-    for tile in (2, 3):
-        for (pc, ph) in ((0, 0), (2, 0), (2, 1), (0, 1), (2, 2)):
-            variants.append(dict(kernel="tma", tile=tile, lx=512, pol_c=pc, pol_h=ph))
-    variants += [dict(kernel="tma", tile=3, lx=512, pol_c=2, pol_h=0, mem_probe=1), dict(kernel="tma", tile=3, lx=512, pol_c=2, pol_h=1, mem_probe=1)]
+    for rep in range(2):
+        for tile in (2, 4, 5):
+            variants.append(dict(kernel="tma", tile=tile))
     for opts in variants:
         steps = 3 if opts.get("kernel") == "direct" else 20
         g, ms, cs = run(n, steps, 3, **opts)

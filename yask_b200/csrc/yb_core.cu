@@ -95,8 +95,8 @@ static void compute_var_geometry(Solution& s, Var& v) {
         d.domain = s.rank_size[dd];
         d.rank_offset = s.rank_offset[dd];
         if (v.spec.fixed_size) { d.domain = v.spec.fixed_sizes[i]; d.rank_offset = 0; }
-        int64_t pl = std::max({d.spec.halo_l, d.min_pad_l, s.min_pad[dd]});
-        int64_t pr = std::max({d.spec.halo_r, d.min_pad_r, s.min_pad[dd]});
+        int64_t pl = std::max({d.spec.halo_l, d.min_pad_l, s.min_pad[dd], s.spec.uniform_pad[dd]});
+        int64_t pr = std::max({d.spec.halo_r, d.min_pad_r, s.min_pad[dd], s.spec.uniform_pad[dd]});
         if (i == nd - 1 && i == last_domain) {
             // unit-stride dim: domain origin on a 128-B boundary, pitch a multiple of 128 B
             pl = (pl + align_elems - 1) / align_elems * align_elems;
@@ -501,6 +501,7 @@ int yb_var_create(yb_solution* s_, const char* name, int ndims, const char* cons
     }
     v.spec.step_alloc = 1;
     for (auto& ds : v.spec.dims) { Dim d; d.spec = ds; v.dims.push_back(d); }
+    if (v.spec.fixed_size) compute_var_geometry(*s, v);   // geometry of a fixed-size var is known at creation
     if (s->prepared) {
         YB_CUDA(cudaSetDevice(s->device));
         compute_var_geometry(*s, v);

@@ -55,6 +55,7 @@ struct StencilSpec {
     std::vector<StageSpec> stages;
     int radius = 0;
     int elem_bytes = 4;
+    int64_t uniform_pad[YB_MAX_DOMAIN_DIMS] = {0, 0, 0};  // pad every var at least this much (shared geometry)
 };
 
 // ---- run-time geometry -------------------------------------------------------------------------

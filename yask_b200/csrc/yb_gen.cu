@@ -1,6 +1,8 @@
 // Engine for emitter-generated solutions: turns a GenStencil table into a StencilSpec and launches
 // one kernel per part and stage (the reference runs the parts of a stage back to back over each
 // micro-block, /root/reference/src/kernel/lib/context.cpp:1158; parts of a stage are independent).
+#include <algorithm>
+
 #include "yb_core.h"
 #include "yb_gen.cuh"
 // generated solutions
@@ -39,6 +41,7 @@ struct GenEngine : Engine {
             P.xb = int(box.b[0]); P.xe = int(box.e[0]);
             P.yb = int(box.b[1]); P.ye = int(box.e[1]);
             P.zb = int(box.b[2]); P.ze = int(box.e[2]);
+            P.SX = P.SY = 0;
             for (size_t k = 0; k < p.acc.size(); k++) {
                 const Var& v = s.vars[p.acc[k].var];
                 const int slot = v.slot_of(t + p.acc[k].toff);
@@ -49,9 +52,15 @@ struct GenEngine : Engine {
                 P.sx[k] = d0 ? d0->stride : 0;
                 P.sy[k] = d1 ? d1->stride : 0;
                 P.sz[k] = d2 ? d2->stride : 0;
+                if (d0 && d1 && d2) {   // full-rank var: must share the solution-wide geometry
+                    if (P.SX == 0) { P.SX = int(d0->stride); P.SY = int(d1->stride); }
+                    if (d0->stride != P.SX || d1->stride != P.SY || d2->stride != 1 || v.slot_elems >= (int64_t(1) << 31))
+                        return set_error(YB_EUNSUPPORTED, "var '%s' does not share the solution's padded geometry", v.spec.name.c_str());
+                }
             }
             GenKernelFn fn = p.fn[g.elem_bytes == 8 ? 1 : 0][s.fp_mode == 0 ? 0 : 1];
-            dim3 grd(unsigned((box.e[2] - box.b[2] + GEN_BLOCK - 1) / GEN_BLOCK), unsigned(box.e[1] - box.b[1]), unsigned(box.e[0] - box.b[0]));
+            dim3 grd(unsigned((box.e[2] - box.b[2] + GEN_BZ - 1) / GEN_BZ), unsigned((box.e[1] - box.b[1] + GEN_BY - 1) / GEN_BY),
+                     unsigned((box.e[0] - box.b[0] + GEN_BX - 1) / GEN_BX));
             if (grd.y > 65535 || grd.z > 65535) return set_error(YB_EUNSUPPORTED, "domain too large in x or y for the generated kernels");
             fn<<<grd, GEN_BLOCK, 0, st>>>(P);
             YB_CUDA(cudaGetLastError());
@@ -99,6 +108,10 @@ int gen_registry_create(const std::string& name, int elem_bytes, StencilSpec& sp
             }
             spec.vars.push_back(v);
         }
+        // one padded geometry for all vars: pad every dim to the largest halo any var has there
+        for (auto& gv : g.vars)
+            for (size_t k = 0; k < g.domain_dims.size() && k < 3; k++)
+                spec.uniform_pad[k] = std::max<int64_t>(spec.uniform_pad[k], std::max(gv.halo_l[k], gv.halo_r[k]));
         for (auto& gs : g.stages) {
             StageSpec st;
             st.name = gs.name;

@@ -11,12 +11,18 @@
 namespace yb { namespace gen {
 
 constexpr int GEN_MAX_ACC = 32;   // distinct (var, step-offset) pairs one part may touch
-constexpr int GEN_BLOCK = 128;    // threads per CTA along the unit-stride dim
+// CTA = GEN_BZ x GEN_BY x GEN_BX points (z fastest): neighbouring rows/planes of a point are computed by
+// the same CTA, so their reads of shared neighbours hit L1 instead of going back to L2.
+constexpr int GEN_BZ = 64, GEN_BY = 2, GEN_BX = 2;
+constexpr int GEN_BLOCK = GEN_BZ * GEN_BY * GEN_BX;
 
 struct GenParams {
     int xb, xe, yb, ye, zb, ze;              // box to compute, rank-local domain coordinates
     void* ptr[GEN_MAX_ACC];                  // element (0,0,0) of the var's step slot for each access
     long long sx[GEN_MAX_ACC], sy[GEN_MAX_ACC], sz[GEN_MAX_ACC];   // element strides (0 where the var lacks the dim)
+    // All vars that span every domain dim share ONE padded geometry (the engine pads them to the solution's
+    // largest halo), so their neighbour offsets dx*SX + dy*SY + dz are computed once and shared by all vars.
+    int SX, SY;
 };
 
 typedef void (*GenKernelFn)(const GenParams);
@@ -72,13 +78,21 @@ template <typename T> struct GenOp<T, 1> {
     static __device__ __forceinline__ T div(T a, T b) { return a / b; }
 };
 
-#define GEN_KERNEL_PROLOGUE                                            \
-    const int z = P.zb + blockIdx.x * GEN_BLOCK + threadIdx.x;         \
-    const int y = P.yb + blockIdx.y;                                   \
-    const int x = P.xb + blockIdx.z;                                   \
-    if (z >= P.ze) return;
-#define RD(a, dx, dy, dz) (static_cast<const T*>(P.ptr[a])[(x + (dx)) * P.sx[a] + (y + (dy)) * P.sy[a] + (z + (dz)) * P.sz[a]])
-#define WR(a, v) static_cast<T*>(P.ptr[a])[x * P.sx[a] + y * P.sy[a] + z * P.sz[a]] = (v)
+#define GEN_KERNEL_PROLOGUE                                                          \
+    const int z = P.zb + blockIdx.x * GEN_BZ + (threadIdx.x % GEN_BZ);               \
+    const int y = P.yb + blockIdx.y * GEN_BY + (threadIdx.x / GEN_BZ) % GEN_BY;      \
+    const int x = P.xb + blockIdx.z * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);      \
+    if (z >= P.ze || y >= P.ye || x >= P.xe) return;
+// m = dim mask of the var (x=1, y=2, z=4).  Full-rank vars (m==7) use the shared geometry: one 64-bit position
+// per thread, 32-bit neighbour offsets that the compiler shares across vars; lower-rank vars (1-D sponge
+// arrays, scalars) take the general strided path.
+#define GEN_POS (x * P.SX + y * P.SY + z)   /* 32-bit: the engine refuses slots of 2^31 elements or more */
+#define RD(a, m, dx, dy, dz)                                                                                             \
+    ((m) == 7 ? static_cast<const T*>(P.ptr[a])[GEN_POS + ((dx) * P.SX + (dy) * P.SY + (dz))]                              \
+              : static_cast<const T*>(P.ptr[a])[(x + (dx)) * P.sx[a] + (y + (dy)) * P.sy[a] + (z + (dz)) * P.sz[a]])
+#define WR(a, m, v)                                                                                                      \
+    do { if ((m) == 7) static_cast<T*>(P.ptr[a])[GEN_POS] = (v);                                                         \
+         else static_cast<T*>(P.ptr[a])[x * P.sx[a] + y * P.sy[a] + z * P.sz[a]] = (v); } while (0)
 #define C(v) static_cast<T>(v)
 #define ADD(a, b) GenOp<T, MODE>::add(a, b)
 #define SUB(a, b) GenOp<T, MODE>::sub(a, b)

@@ -165,13 +165,21 @@ TileCfg cfg_gen2(const char* name) {
                    {iso3dfd_tma2_kernel<T, 0>, iso3dfd_tma2_kernel<T, 1>, iso3dfd_tma2_kernel<T, 2>, iso3dfd_tma2_kernel<T, 3>}};
 }
 
-constexpr int NTILES = 4;
+template <class T>
+TileCfg cfg_gen3(const char* name) {
+    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
+                   {iso3dfd_tma3_kernel<T, 0>, iso3dfd_tma3_kernel<T, 1>, iso3dfd_tma3_kernel<T, 2>, nullptr}};
+}
+
+constexpr int NTILES = 6;
 const TileCfg& tile_cfg(int i) {
     static const TileCfg cfgs[NTILES] = {
         cfg_gen1<IsoTile<8, 32, 16, 5>>("gen1 32x64, 512 thr x 4 pts"),
         cfg_gen1<IsoTile<8, 16, 32, 5>>("gen1 16x128, 512 thr x 4 pts"),
         cfg_gen2<IsoTile2<8, 16, 16, 5>>("gen2 32x64, 256 thr x 8 pts (row pairs)"),
         cfg_gen2<IsoTile2<8, 8, 32, 5>>("gen2 16x128, 256 thr x 8 pts (row pairs)"),
+        cfg_gen3<IsoTile3<8, 16, 16, 11, 3>>("gen3 32x64, row pairs, 11 resident haloed planes"),
+        cfg_gen3<IsoTile3<8, 16, 16, 12, 2>>("gen3 32x64, row pairs, 12 resident haloed planes"),
     };
     return cfgs[i];
 }

@@ -506,4 +506,224 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tiled TMA kernel, generation 3 ("resident planes").
+//
+// Generation 2 fetches every plane twice from L2 (halo-less, R planes early, to feed the x queue, and
+// again with its halo when it becomes the current plane); ncu showed 21.5 GB of TMA reads and 19.7 GB
+// of DRAM traffic per 1024^3 launch against 17.2 GB algorithmic, and a memory-only probe of that traffic
+// pattern capped at ~293-315 GPts/s.  Generation 3 loads each plane ONCE, with its halo, into a ring of
+// NS > R shared-memory slots where it stays resident from the step it feeds the queue (x+R) until it has
+// been the current plane (x): one haloed box per plane instead of two boxes, no R-plane reuse distance in
+// L2.  p(t-1) and v travel through their own small ring.  Threads, arithmetic and stores are those of
+// generation 2.
+//
+//   iteration I (per CTA, global over its work units):
+//     feed    : own quads of plane I           <- H slot  I      mod NS   (wait full_h)
+//     compute : plane I - R (if inside the unit's sweep) from H slot (I-R) mod NS, P/V slot c mod NPV
+//     release : every warp arrives on done[I mod 4]; the producer thread, at the top of iteration I+1,
+//               waits for it, then refills the H slot of plane I-R (with plane I-R+NS) and the next P/V slot.
+// ---------------------------------------------------------------------------------------------
+template <int R_, int TYP_, int TZQ_, int NS_, int NPV_>
+struct IsoTile3 {
+    static constexpr int R = R_, TYP = TYP_, TZQ = TZQ_, NS = NS_, NPV = NPV_;
+    static constexpr int TY = 2 * TYP;
+    static constexpr int TZ = 4 * TZQ;
+    static constexpr int HZ = (R + 3) / 4 * 4;
+    static constexpr int ZQ = HZ / 4;
+    static constexpr int HP = TZ + 2 * HZ;
+    static constexpr int HROWS = TY + 2 * R;
+    static constexpr int THREADS = TYP * TZQ;
+    static constexpr int NWARPS = THREADS / 32;
+    static constexpr int QN = 2 * R + 1;
+    static constexpr int NDONE = 4;
+    static constexpr uint32_t H_BYTES = HROWS * HP * 4;
+    static constexpr uint32_t H_STRIDE = (H_BYTES + 127) / 128 * 128;
+    static constexpr uint32_t C_BYTES = TY * TZ * 4;
+    static constexpr uint32_t PV_STRIDE = 2 * C_BYTES;            // P tile then V tile
+    static constexpr uint32_t PV_OFF = NS * H_STRIDE;
+    static constexpr uint32_t BAR_OFF = PV_OFF + NPV * PV_STRIDE;
+    static constexpr uint32_t SMEM_BYTES = BAR_OFF + (NS + NPV + NDONE) * 8 + 128;
+    static_assert(NS > R + 1, "ring must hold planes x .. x+R plus at least one in flight");
+    static_assert(THREADS % 32 == 0, "whole warps");
+    static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can use");
+};
+
+template <class T, int MODE>
+__global__ void __launch_bounds__(T::THREADS, 1)
+iso3dfd_tma3_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ IsoParams P) {
+    constexpr int R = T::R, QN = T::QN, ZQ = T::ZQ, NS = T::NS, NPV = T::NPV, NDONE = T::NDONE;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
+    uint64_t* full_h = reinterpret_cast<uint64_t*>(sbase + T::BAR_OFF);
+    uint64_t* full_pv = full_h + NS;
+    uint64_t* done_bar = full_pv + NPV;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int nunits = P.nty * P.ntz * P.nchunks;
+
+    if (tid == 0) {
+        tma_prefetch_desc(&M.h); tma_prefetch_desc(&M.p); tma_prefetch_desc(&M.v);
+        for (int s = 0; s < NS; s++) mbar_init(&full_h[s], 1);
+        for (int s = 0; s < NPV; s++) mbar_init(&full_pv[s], 1);
+        for (int s = 0; s < NDONE; s++) mbar_init(&done_bar[s], T::NWARPS);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    // ---- producer state (thread 0) ---------------------------------------------------------------------
+    const uint64_t pol_pv = l2_policy(P.pol_pv), pol_h = l2_policy(P.pol_h);
+    IsoCursor ph;   // next haloed plane to request: it = plane index within unit, 0 .. lx_u + 2R - 1
+    IsoCursor pp;   // next P/V tile to request:     it = compute index within unit, 0 .. lx_u - 1
+    ph.unit = pp.unit = blockIdx.x;
+    ph.stage = pp.stage = 0; ph.phase = pp.phase = 0;
+    ph.it = pp.it = 0; ph.n_it = pp.n_it = 0; ph.x0 = ph.y0 = ph.z0 = pp.x0 = pp.y0 = pp.z0 = 0;
+    int pg = 0;          // global index of the next plane to request
+    int pc = 0;          // global index of the next compute step whose P/V to request
+    bool ph_live = (tid == 0) && (blockIdx.x < nunits), pp_live = ph_live;
+    if (ph_live) { iso_unit_setup<T>(ph, P); iso_unit_setup<T>(pp, P); pp.n_it -= 2 * R; }
+
+    auto request_plane = [&]() {
+        uint64_t* fb = &full_h[ph.stage];
+        mbar_arrive_expect_tx(fb, T::H_BYTES);
+        tma_load_3d_hint(sbase + ph.stage * T::H_STRIDE, &M.h, fb, P.pad_z + ph.z0 - T::HZ, P.pad_y + ph.y0 - R, P.pad_x + ph.x0 - R + ph.it, pol_h);
+        if (++ph.stage == NS) ph.stage = 0;
+        pg++;
+        if (++ph.it == ph.n_it) {
+            ph.unit += gridDim.x;
+            if (ph.unit < nunits) iso_unit_setup<T>(ph, P); else ph_live = false;
+        }
+    };
+    auto request_pv = [&]() {
+        uint64_t* fb = &full_pv[pp.stage];
+        uint8_t* dst = sbase + T::PV_OFF + pp.stage * T::PV_STRIDE;
+        mbar_arrive_expect_tx(fb, 2 * T::C_BYTES);
+        tma_load_3d_hint(dst, &M.p, fb, P.pad_z + pp.z0, P.pad_y + pp.y0, P.pad_x + pp.x0 + pp.it, pol_pv);
+        tma_load_3d_hint(dst + T::C_BYTES, &M.v, fb, P.vpad_z + pp.z0, P.vpad_y + pp.y0, P.vpad_x + pp.x0 + pp.it, pol_pv);
+        if (++pp.stage == NPV) pp.stage = 0;
+        pc++;
+        if (++pp.it == pp.n_it) {
+            pp.unit += gridDim.x;
+            if (pp.unit < nunits) { iso_unit_setup<T>(pp, P); pp.n_it -= 2 * R; } else pp_live = false;
+        }
+    };
+
+    // ---- consumer state --------------------------------------------------------------------------------
+    const int rp = tid / T::TZQ;
+    const int quad = tid % T::TZQ;
+    const uint32_t h_own = ((2 * rp + R) * T::HP + T::HZ + 4 * quad) * 4;   // row a centre inside an H slot
+    const uint32_t c_own = (2 * rp * T::TZ + 4 * quad) * 4;                 // row a inside a P or V tile
+
+    int I = 0;                         // global iteration
+    int cdone = 0;                     // compute steps finished before iteration I (all warps)
+    int feed_slot = 0, cur_slot = NS - R % NS;      // I mod NS and (I - R) mod NS
+    if (cur_slot >= NS) cur_slot -= NS;
+    uint32_t feed_par = 0;             // parity of the fill of feed_slot that holds plane I
+    int pv_slot = 0; uint32_t pv_par = 0;
+    int done_slot = 0; uint32_t done_par = 0;       // barrier of iteration I
+    float4 qa[QN], qb[QN];
+#pragma unroll
+    for (int k = 0; k < QN; k++) { qa[k] = make_float4(0.f, 0.f, 0.f, 0.f); qb[k] = qa[k]; }
+
+    IsoCursor cu;
+    for (cu.unit = blockIdx.x; cu.unit < nunits; cu.unit += gridDim.x) {
+        iso_unit_setup<T>(cu, P);
+        const int ya = cu.y0 + 2 * rp;
+        const int zq = cu.z0 + 4 * quad;
+        const int nz_ok = max(0, min(4, P.z_end - zq));
+        const int nva = (ya < P.y_end) ? nz_ok : 0;
+        const int nvb = (ya + 1 < P.y_end) ? nz_ok : 0;
+        float* out_a = P.out + (long long)ya * P.out_sy + zq + (long long)(cu.x0 - 2 * R) * P.out_sx;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_a) & 15) == 0);
+
+#pragma unroll 1
+        for (int it = 0; it < cu.n_it; it++, I++) {
+            const bool compute = it >= 2 * R;
+            if (tid == 0) {
+                // all warps have finished iteration I-1: its current plane's slot and its P/V slot are free
+                if (I > 0) {
+                    const int ds = done_slot == 0 ? NDONE - 1 : done_slot - 1;
+                    const uint32_t dp = done_slot == 0 ? done_par ^ 1u : done_par;
+                    mbar_wait(&done_bar[ds], dp);
+                }
+                while (ph_live && pg <= I + NS - R - 1) request_plane();
+                while (pp_live && pc < cdone + NPV) request_pv();
+            }
+
+            // feed the x queues with plane I
+            mbar_wait(&full_h[feed_slot], feed_par);
+            {
+                const uint8_t* hs = sbase + feed_slot * T::H_STRIDE + h_own;
+#pragma unroll
+                for (int k = 0; k < QN - 1; k++) { qa[k] = qa[k + 1]; qb[k] = qb[k + 1]; }
+                qa[QN - 1] = *reinterpret_cast<const float4*>(hs);
+                qb[QN - 1] = *reinterpret_cast<const float4*>(hs + T::HP * 4);
+            }
+
+            if (compute) {
+                mbar_wait(&full_pv[pv_slot], pv_par);
+                const float* hp = reinterpret_cast<const float*>(sbase + cur_slot * T::H_STRIDE + h_own);
+                const uint8_t* pvs = sbase + T::PV_OFF + pv_slot * T::PV_STRIDE + c_own;
+                float pa[4], pb[4];
+                f4_to_arr(qa[R], pa);
+                f4_to_arr(qb[R], pb);
+                float za[4 * (2 * ZQ + 1)], zb[4 * (2 * ZQ + 1)];
+#pragma unroll
+                for (int k = -ZQ; k <= ZQ; k++) {
+                    if (k == 0) { f4_to_arr(qa[R], &za[4 * ZQ]); f4_to_arr(qb[R], &zb[4 * ZQ]); continue; }
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp + 4 * k), &za[4 * (k + ZQ)]);
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp + T::HP + 4 * k), &zb[4 * (k + ZQ)]);
+                }
+                float acca[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
+                float wlo_prev[4], whi_prev[4];
+                f4_to_arr(qa[R], wlo_prev);
+                f4_to_arr(qb[R], whi_prev);
+#pragma unroll
+                for (int r = 1; r <= R; r++) {
+                    float wlo[4], whi[4], xm[4], xp[4];
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp - r * T::HP), wlo);
+                    f4_to_arr(*reinterpret_cast<const float4*>(hp + (r + 1) * T::HP), whi);
+                    f4_to_arr(qa[R - r], xm); f4_to_arr(qa[R + r], xp);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        acca[i] = iso_group<MODE>(acca[i], pa[i], P.c[0], P.c[r], xm[i], xp[i], wlo[i], whi_prev[i],
+                                                  za[4 * ZQ + i - r], za[4 * ZQ + i + r], r == 1);
+                    f4_to_arr(qb[R - r], xm); f4_to_arr(qb[R + r], xp);
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        accb[i] = iso_group<MODE>(accb[i], pb[i], P.c[0], P.c[r], xm[i], xp[i], wlo_prev[i], whi[i],
+                                                  zb[4 * ZQ + i - r], zb[4 * ZQ + i + r], r == 1);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { wlo_prev[i] = wlo[i]; whi_prev[i] = whi[i]; }
+                }
+                const float4 pva = *reinterpret_cast<const float4*>(pvs);
+                const float4 vva = *reinterpret_cast<const float4*>(pvs + T::C_BYTES);
+                const float4 pvb = *reinterpret_cast<const float4*>(pvs + T::TZ * 4);
+                const float4 vvb = *reinterpret_cast<const float4*>(pvs + T::C_BYTES + T::TZ * 4);
+                float4 ra, rb;
+                ra.x = iso_final<MODE>(acca[0], pa[0], pva.x, vva.x); ra.y = iso_final<MODE>(acca[1], pa[1], pva.y, vva.y);
+                ra.z = iso_final<MODE>(acca[2], pa[2], pva.z, vva.z); ra.w = iso_final<MODE>(acca[3], pa[3], pva.w, vva.w);
+                rb.x = iso_final<MODE>(accb[0], pb[0], pvb.x, vvb.x); rb.y = iso_final<MODE>(accb[1], pb[1], pvb.y, vvb.y);
+                rb.z = iso_final<MODE>(accb[2], pb[2], pvb.z, vvb.z); rb.w = iso_final<MODE>(accb[3], pb[3], pvb.w, vvb.w);
+                float* oa = out_a + (long long)it * P.out_sx;
+                float* ob = oa + P.out_sy;
+                if (vec_ok && nva == 4) stg128(oa, ra);
+                else if (nva > 0) { oa[0] = ra.x; if (nva > 1) oa[1] = ra.y; if (nva > 2) oa[2] = ra.z; if (nva > 3) oa[3] = ra.w; }
+                if (vec_ok && nvb == 4) stg128(ob, rb);
+                else if (nvb > 0) { ob[0] = rb.x; if (nvb > 1) ob[1] = rb.y; if (nvb > 2) ob[2] = rb.z; if (nvb > 3) ob[3] = rb.w; }
+                if (++pv_slot == NPV) { pv_slot = 0; pv_par ^= 1u; }
+                cdone++;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&done_bar[done_slot]);
+            if (++done_slot == NDONE) { done_slot = 0; done_par ^= 1u; }
+            if (++feed_slot == NS) { feed_slot = 0; feed_par ^= 1u; }
+            if (++cur_slot == NS) cur_slot = 0;
+        }
+    }
+}
+
 }  // namespace yb

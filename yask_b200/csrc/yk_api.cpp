@@ -624,7 +624,10 @@ struct B200Solution : yk_solution {
     void clear_stats() override { chk(yb_clear_stats(h->s)); }
     void reset_auto_tuner(bool, bool) override {}    // no CPU block sizes to tune
     bool is_auto_tuner_enabled() const override { return false; }
-    void run_auto_tuner_now(bool) override {}
+    void run_auto_tuner_now(bool) override {
+        // auto_tuner.cpp raises when called before prepare_solution(); there are no CPU block sizes to tune on the GPU
+        if (!yb_solution_is_prepared(h->s)) fail("run_auto_tuner_now() called without calling prepare_solution() first");
+    }
     void set_min_pad_size(const std::string& dim, idx_t size) override { chk(yb_set_min_pad_size(h->s, dpos(dim, "set_min_pad_size"), size)); min_pad[dim] = size; }
     std::map<std::string, idx_t> min_pad;
     idx_t get_min_pad_size(const std::string& dim) const override { dpos(dim, "get_min_pad_size"); auto it = min_pad.find(dim); return it == min_pad.end() ? 0 : it->second; }

@@ -287,16 +287,30 @@ def gen_expr(tree, rd, ops) -> str:
     return f"{ops[k]}({a}, {b})"
 
 
-def _stmt_lines(part, ndd, indent="    "):
+def _stmt_lines(part, ndd, indent="    ", masks=None):
     out = []
     for s in part["stmts"]:
         def rd(i, s=s):
             a, offs = s["reads"][i]
             offs = list(offs) + [0] * (3 - len(offs))
-            return f"RD({a}, {offs[0]}, {offs[1]}, {offs[2]})"
+            return f"RD({a}, {masks[a]}, {offs[0]}, {offs[1]}, {offs[2]})"
         out.append(f"{indent}const T e{s['dst']} = {gen_expr(s['tree'], rd, {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'})};")
     for o in part["outputs"]:
-        out.append(f"{indent}WR({o['access']}, e{o['src']});")
+        out.append(f"{indent}WR({o['access']}, {masks[o['access']]}, e{o['src']});")
+    return out
+
+
+def _masks(ir, part):
+    """Per access: bit d set if the var spans solution domain dim d (x=1, y=2, z=4)."""
+    dd = ir["domain_dims"]
+    vmap = {v["name"]: v for v in ir["vars"]}
+    out = []
+    for a in part["accesses"]:
+        m = 0
+        for i, d in enumerate(dd):
+            if d in vmap[a["var"]]["dims"]:
+                m |= 1 << i
+        out.append(m)
     return out
 
 
@@ -317,7 +331,7 @@ def emit_cuda(ir: dict) -> str:
             L.append("template <typename T, int MODE>")
             L.append(f"__global__ void __launch_bounds__(GEN_BLOCK) {ident}_{p['name']}_kernel(const __grid_constant__ GenParams P) {{")
             L.append("    GEN_KERNEL_PROLOGUE")
-            L.extend(_stmt_lines(p, len(ir["domain_dims"])))
+            L.extend(_stmt_lines(p, len(ir["domain_dims"]), masks=_masks(ir, p)))
             L.append("}")
     # spec table
     L.append(f"inline void {ident}_describe(GenStencil& g) {{")
@@ -357,7 +371,7 @@ def emit_oracle(ir: dict) -> str:
             L.append(f"static void yo_{ident}_{p['name']}(const yo_gen_args* A) {{")
             L.append(f"    typedef {T} T;")
             L.append("    YO_GEN_LOOP_BEGIN")
-            L.extend(_stmt_lines(p, len(ir["domain_dims"]), indent="        "))
+            L.extend(_stmt_lines(p, len(ir["domain_dims"]), indent="        ", masks=_masks(ir, p)))
             L.append("    YO_GEN_LOOP_END")
             L.append("}")
     L.append(f"static const yo_gen_part yo_{ident}_parts[] = {{")
