@@ -59,7 +59,7 @@ def test_bit_exact_vs_reference_golden(path, kernel):
 
 
 @pytest.mark.parametrize("fp_mode", [0, 1, 2])
-@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 @pytest.mark.parametrize("n,steps,lx", [((40, 70, 150), 2, 16), ((17, 33, 65), 3, 7), ((64, 64, 128), 1, 128), ((9, 8, 16), 2, 4)])
 def test_tma_kernel_vs_oracle(n, steps, lx, tile, fp_mode):
     ins = synth_inputs(n, 99)

@@ -33,9 +33,9 @@ if __name__ == "__main__":
     base = None
     variants = []
     for rep in range(2):
-        for tile in (2, 4, 5):
+        for tile in (2, 7, 8, 10, 11):
             variants.append(dict(kernel="tma", tile=tile))
     for opts in variants:
-        steps = 3 if opts.get("kernel") == "direct" else 20
+        steps = 3 if opts.get("kernel") == "direct" else 40
         g, ms, cs = run(n, steps, 3, **opts)
         print(json.dumps(dict(opts=opts, gpts=round(g, 2), ms_per_step=round(ms, 4), gbps=round(g*16, 1), checksum=cs)), flush=True)

@@ -171,7 +171,14 @@ TileCfg cfg_gen3(const char* name) {
                    {iso3dfd_tma3_kernel<T, 0>, iso3dfd_tma3_kernel<T, 1>, iso3dfd_tma3_kernel<T, 2>, nullptr}};
 }
 
-constexpr int NTILES = 6;
+template <class T, int PW, int U>
+TileCfg cfg_gen2x(const char* name) {
+    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS + 128 * PW, T::SMEM_BYTES,
+                   {iso3dfd_tma2_kernel<T, 0, PW, U>, iso3dfd_tma2_kernel<T, 1, PW, U>, iso3dfd_tma2_kernel<T, 2, PW, U>,
+                    iso3dfd_tma2_kernel<T, 3, PW, U>}};
+}
+
+constexpr int NTILES = 12;
 const TileCfg& tile_cfg(int i) {
     static const TileCfg cfgs[NTILES] = {
         cfg_gen1<IsoTile<8, 32, 16, 5>>("gen1 32x64, 512 thr x 4 pts"),
@@ -180,6 +187,12 @@ const TileCfg& tile_cfg(int i) {
         cfg_gen2<IsoTile2<8, 8, 32, 5>>("gen2 16x128, 256 thr x 8 pts (row pairs)"),
         cfg_gen3<IsoTile3<8, 16, 16, 11, 3>>("gen3 32x64, row pairs, 11 resident haloed planes"),
         cfg_gen3<IsoTile3<8, 16, 16, 12, 2>>("gen3 32x64, row pairs, 12 resident haloed planes"),
+        cfg_gen2x<IsoTile2<8, 16, 16, 5>, 1, 1>("gen2 32x64 + producer warp"),
+        cfg_gen2x<IsoTile2<8, 16, 16, 5>, 0, 2>("gen2 32x64, 2 planes per trip"),
+        cfg_gen2x<IsoTile2<8, 8, 32, 5>, 1, 1>("gen2 16x128 + producer warp"),
+        cfg_gen2x<IsoTile2<8, 8, 32, 5>, 0, 2>("gen2 16x128, 2 planes per trip"),
+        cfg_gen2x<IsoTile2<8, 16, 16, 5>, 1, 2>("gen2 32x64 + producer warp, 2 planes per trip"),
+        cfg_gen2x<IsoTile2<8, 8, 32, 5>, 1, 2>("gen2 16x128 + producer warp, 2 planes per trip"),
     };
     return cfgs[i];
 }
@@ -188,7 +201,7 @@ struct IsoEngine : Engine {
     int radius = 8;
     double coef[ISO_MAX_R + 1] = {0};
     std::string kernel = "auto";   // auto | tma | direct
-    int tile = 2;                  // index into tile_cfg()
+    int tile = 11;                 // index into tile_cfg(): gen2 16x128, producer warpgroup, 2 planes per trip
     int lx = 0;                    // planes per sweep chunk (0 = choose per launch)
     int grid_override = 0;
     int num_sms = 148;

@@ -12,6 +12,8 @@
 // FP modes (see oracle/yask_oracle.c): 0 strict IEEE mul/add, 1 canonical FMA,
 // 2 = FMA pattern GCC 13 emits for the reference's default build (bit-exact vs it).
 #pragma once
+#include <type_traits>
+
 #include "yb_ptx.cuh"
 
 namespace yb {
@@ -346,10 +348,15 @@ struct IsoTile2 {
 
 __device__ __forceinline__ void f4_to_arr(const float4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
-template <class T, int MODE>
-__global__ void __launch_bounds__(T::THREADS, 1)
+// PW = 1: a dedicated producer warp (warp NWARPS) issues the TMA loads, so no compute warp carries the
+//         issue code (with 2 warps per scheduler a straggling warp 0 delays every stage hand-over).
+// U  = 2: the sweep loop handles two planes per trip and rotates the x queues by two entries every second
+//         plane (half the register moves of U = 1) at the price of one extra queue entry per row.
+template <class T, int MODE, int PW = 0, int U = 1>
+__global__ void __launch_bounds__(T::THREADS + 128 * PW, 1)
 iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ IsoParams P) {
     constexpr int R = T::R, QN = T::QN, ZQ = T::ZQ;
+    constexpr int QL = QN + (U - 1);          // queue entries kept per row
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* sbase = smem_raw + (base - smem_u32(smem_raw));
@@ -359,6 +366,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int nunits = P.nty * P.ntz * P.nchunks;
+    const int prod_tid = PW ? T::THREADS : 0;
 
     if (tid == 0) {
         tma_prefetch_desc(&M.h); tma_prefetch_desc(&M.c); tma_prefetch_desc(&M.p); tma_prefetch_desc(&M.v);
@@ -367,11 +375,11 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
     }
     __syncthreads();
 
-    // ---- producer (thread 0) -------------------------------------------------------------
+    // ---- producer -----------------------------------------------------------------------------------
     IsoCursor pr;
     pr.unit = blockIdx.x; pr.stage = 0; pr.phase = 0; pr.it = 0; pr.n_it = 0; pr.x0 = pr.y0 = pr.z0 = 0;
     const uint64_t pol_pv = l2_policy(P.pol_pv), pol_c = l2_policy(P.pol_c), pol_h = l2_policy(P.pol_h);
-    bool pr_live = (tid == 0) && (pr.unit < nunits);
+    bool pr_live = (tid == prod_tid) && (pr.unit < nunits);
     if (pr_live) iso_unit_setup<T>(pr, P);
 
     auto produce_one = [&]() {
@@ -394,11 +402,20 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
             if (pr.unit < nunits) iso_unit_setup<T>(pr, P); else pr_live = false;
         }
     };
-    if (tid == 0) {
+    if (PW) {
+        // Warp-specialised register budget (setmaxnreg works on whole warpgroups): the producer warpgroup
+        // hands its registers back, the two consumer warpgroups take them.
+        if (tid >= T::THREADS) {          // producer warpgroup: one lane streams every load of this CTA, then exits
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+            while (pr_live) produce_one();
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    } else if (tid == 0) {
         for (int k = 0; k < T::STAGES - 1 && pr_live; k++) produce_one();
     }
 
-    // ---- consumer ------------------------------------------------------------------------
+    // ---- consumer ------------------------------------------------------------------------------------
     const int rp = tid / T::TZQ;           // row pair 0..TYP-1  (rows 2rp, 2rp+1)
     const int quad = tid % T::TZQ;
     const uint32_t h_own = ((2 * rp + R) * T::HP + T::HZ + 4 * quad) * 4;  // row a centre in H
@@ -406,9 +423,9 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
 
     IsoCursor cu;
     cu.stage = 0; cu.phase = 0;
-    float4 qa[QN], qb[QN];
+    float4 qa[QL], qb[QL];
 #pragma unroll
-    for (int k = 0; k < QN; k++) { qa[k] = make_float4(0.f, 0.f, 0.f, 0.f); qb[k] = qa[k]; }
+    for (int k = 0; k < QL; k++) { qa[k] = make_float4(0.f, 0.f, 0.f, 0.f); qb[k] = qa[k]; }
 
     for (cu.unit = blockIdx.x; cu.unit < nunits; cu.unit += gridDim.x) {
         iso_unit_setup<T>(cu, P);
@@ -420,29 +437,32 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
         float* out_a = P.out + (long long)ya * P.out_sy + zq + (long long)(cu.x0 - 2 * R) * P.out_sx;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_a) & 15) == 0);
 
-#pragma unroll 1
-        for (int it = 0; it < cu.n_it; it++) {
-            if (tid == 0 && pr_live) produce_one();
+        // One sweep step.  B = index of the oldest live queue entry after the push (window = q[B .. B+2R]).
+        auto step = [&](auto Bc, const int it) {
+            constexpr int B = decltype(Bc)::value;
+            if (!PW && tid == 0 && pr_live) produce_one();
 
             const uint8_t* st = sbase + cu.stage * T::STAGE_BYTES;
             mbar_wait(&full_bar[cu.stage], cu.phase);
 
-            // rotate the x queue (register moves) and push plane x0 - R + it
+            // push plane x0 - R + it into the x queues
+            if (B == 0) {
 #pragma unroll
-            for (int k = 0; k < QN - 1; k++) { qa[k] = qa[k + 1]; qb[k] = qb[k + 1]; }
-            qa[QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own);
-            qb[QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own + T::TZ * 4);
+                for (int k = 0; k + U < QL; k++) { qa[k] = qa[k + U]; qb[k] = qb[k + U]; }
+            }
+            qa[B + QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own);
+            qb[B + QN - 1] = *reinterpret_cast<const float4*>(st + T::C_OFF + c_own + T::TZ * 4);
 
             if (MODE == 3) {
-                // DEBUG (fp_mode=3): memory-system ceiling probe -- same TMA traffic and stores, no stencil math.
+                // DEBUG (mem_probe=1): memory-system ceiling probe -- same TMA traffic and stores, no stencil math.
                 if (it >= 2 * R) {
                     const float4 pva = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own);
                     const float4 vva = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own);
                     const float4 pvb = *reinterpret_cast<const float4*>(st + T::P_OFF + c_own + T::TZ * 4);
                     const float4 vvb = *reinterpret_cast<const float4*>(st + T::V_OFF + c_own + T::TZ * 4);
                     const float4 ha = *reinterpret_cast<const float4*>(st + T::H_OFF + h_own);
-                    float4 ra = make_float4(pva.x + vva.x * qa[R].x, pva.y + vva.y * ha.y, pva.z + vva.z, pva.w + vva.w);
-                    float4 rb = make_float4(pvb.x + vvb.x * qb[R].x, pvb.y + vvb.y, pvb.z + vvb.z, pvb.w + vvb.w);
+                    float4 ra = make_float4(pva.x + vva.x * qa[B + R].x, pva.y + vva.y * ha.y, pva.z + vva.z, pva.w + vva.w);
+                    float4 rb = make_float4(pvb.x + vvb.x * qb[B + R].x, pvb.y + vvb.y, pvb.z + vvb.z, pvb.w + vvb.w);
                     float* oa = out_a + (long long)it * P.out_sx;
                     if (vec_ok && nva == 4) stg128(oa, ra);
                     if (vec_ok && nvb == 4) stg128(oa + P.out_sy, rb);
@@ -450,32 +470,32 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
             } else if (it >= 2 * R) {
                 const float* hp = reinterpret_cast<const float*>(st + T::H_OFF + h_own);
                 float pa[4], pb[4];
-                f4_to_arr(qa[R], pa);
-                f4_to_arr(qb[R], pb);
+                f4_to_arr(qa[B + R], pa);
+                f4_to_arr(qb[B + R], pb);
                 // z windows of both rows (centre quads come from the queue)
                 float za[4 * (2 * ZQ + 1)], zb[4 * (2 * ZQ + 1)];
 #pragma unroll
                 for (int k = -ZQ; k <= ZQ; k++) {
-                    if (k == 0) { f4_to_arr(qa[R], &za[4 * ZQ]); f4_to_arr(qb[R], &zb[4 * ZQ]); continue; }
+                    if (k == 0) { f4_to_arr(qa[B + R], &za[4 * ZQ]); f4_to_arr(qb[B + R], &zb[4 * ZQ]); continue; }
                     f4_to_arr(*reinterpret_cast<const float4*>(hp + 4 * k), &za[4 * (k + ZQ)]);
                     f4_to_arr(*reinterpret_cast<const float4*>(hp + T::HP + 4 * k), &zb[4 * (k + ZQ)]);
                 }
                 float acca[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
-                // y window: row index k <-> H row (2rp + k - R) ... w(k) = hp + (k - R) * HP ; row a centre = w(R), row b = w(R+1)
+                // y window: w(k) = hp + (k - R) * HP ; row a centre = w(R), row b centre = w(R+1)
                 float wlo_prev[4], whi_prev[4];   // w(R - (r-1)) and w(R+1 + (r-1)) from the previous radius
-                f4_to_arr(qa[R], wlo_prev);       // r=1: row b's y-1 neighbour is row a's centre
-                f4_to_arr(qb[R], whi_prev);       //      row a's y+1 neighbour is row b's centre
+                f4_to_arr(qa[B + R], wlo_prev);   // r=1: row b's y-1 neighbour is row a's centre
+                f4_to_arr(qb[B + R], whi_prev);   //      row a's y+1 neighbour is row b's centre
 #pragma unroll
                 for (int r = 1; r <= R; r++) {
                     float wlo[4], whi[4], xm[4], xp[4];
                     f4_to_arr(*reinterpret_cast<const float4*>(hp - r * T::HP), wlo);        // row a - r
                     f4_to_arr(*reinterpret_cast<const float4*>(hp + (r + 1) * T::HP), whi);  // row b + r
-                    f4_to_arr(qa[R - r], xm); f4_to_arr(qa[R + r], xp);
+                    f4_to_arr(qa[B + R - r], xm); f4_to_arr(qa[B + R + r], xp);
 #pragma unroll
                     for (int i = 0; i < 4; i++)   // row a: y-r = wlo, y+r = w(R+r) = previous whi
                         acca[i] = iso_group<MODE>(acca[i], pa[i], P.c[0], P.c[r], xm[i], xp[i], wlo[i], whi_prev[i],
                                                   za[4 * ZQ + i - r], za[4 * ZQ + i + r], r == 1);
-                    f4_to_arr(qb[R - r], xm); f4_to_arr(qb[R + r], xp);
+                    f4_to_arr(qb[B + R - r], xm); f4_to_arr(qb[B + R + r], xp);
 #pragma unroll
                     for (int i = 0; i < 4; i++)   // row b: y-r = w(R+1-r) = previous wlo, y+r = whi
                         accb[i] = iso_group<MODE>(accb[i], pb[i], P.c[0], P.c[r], xm[i], xp[i], wlo_prev[i], whi[i],
@@ -502,10 +522,21 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[cu.stage]);
             if (++cu.stage == T::STAGES) { cu.stage = 0; cu.phase ^= 1u; }
+        };
+
+        if (U == 1) {
+#pragma unroll 1
+            for (int it = 0; it < cu.n_it; it++) step(std::integral_constant<int, 0>{}, it);
+        } else {
+            // trip = [rotate by 2, push] then [push]: the second plane lands one entry further along
+#pragma unroll 1
+            for (int it = 0; it < cu.n_it; it += 2) {
+                step(std::integral_constant<int, 0>{}, it);
+                if (it + 1 < cu.n_it) step(std::integral_constant<int, U - 1>{}, it + 1);
+            }
         }
     }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Tiled TMA kernel, generation 3 ("resident planes").
