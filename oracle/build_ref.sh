@@ -57,6 +57,11 @@ if [ "${REF_ALL:-1}" = "1" ]; then
     build_kernel awp_elastic "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     build_kernel ssg "-fp64"        8
     build_kernel ssg "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+    # further solutions the CUDA emitter covers; "3axis" is the heat3d-style shape
+    for st in awp iso3dfd_sponge 3axis 3axis_with_diags 3plane cube tti; do
+        build_kernel $st ""        4
+        build_kernel $st "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+    done
 fi
 # Strip debug info (the reference builds with -g) and drop the (large) intermediate build tree.
 strip --strip-debug "$OUT"/lib/*.so "$OUT"/bin/*.exe "$OUT"/bin/ref_driver.* 2>/dev/null || true

@@ -66,8 +66,8 @@ def iso3dfd_run(p0: np.ndarray, p1: np.ndarray, v: np.ndarray, radius: int, step
 # Emitter-generated solutions (oracle/gen/*.gen.h): generic runner
 # ---------------------------------------------------------------------------------------
 class _GenArgs(ctypes.Structure):
-    _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 32),
-                ("sx", ctypes.c_int64 * 32), ("sy", ctypes.c_int64 * 32), ("sz", ctypes.c_int64 * 32)]
+    _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 48),
+                ("sx", ctypes.c_int64 * 48), ("sy", ctypes.c_int64 * 48), ("sz", ctypes.c_int64 * 48)]
 
 
 def gen_ir(stencil: str) -> dict:

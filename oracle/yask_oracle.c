@@ -212,7 +212,7 @@ int yo_num_threads(void)
 /* order; this file supplies the loop nest and the statement vocabulary.  All arithmetic   */
 /* is in the element type with no contraction (== reference built with -ffp-contract=off). */
 /* ------------------------------------------------------------------------------------ */
-#define YO_GEN_MAX_ACC 32
+#define YO_GEN_MAX_ACC 48
 typedef struct {
     int64_t nx, ny, nz;                 /* rank-domain box [0,n) */
     void* ptr[YO_GEN_MAX_ACC];          /* element (0,0,0) of each access' step slot */
@@ -234,13 +234,9 @@ typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } y
 #define MUL(a, b) ((a) * (b))
 #define DIV(a, b) ((a) / (b))
 
-#include "gen/awp_elastic.gen.h"
-#include "gen/ssg.gen.h"
+#include "gen/gen_all.inc"
 
-static const struct { const char* name; const yo_gen_part* parts; int nparts; } yo_gen_table[] = {
-    {"awp_elastic", yo_awp_elastic_parts, (int)(sizeof(yo_awp_elastic_parts) / sizeof(yo_gen_part))},
-    {"ssg", yo_ssg_parts, (int)(sizeof(yo_ssg_parts) / sizeof(yo_gen_part))},
-};
+static const struct { const char* name; const yo_gen_part* parts; int nparts; } yo_gen_table[] = {YO_GEN_TABLE};
 
 /* Run part `part` (0-based, in stage order) of generated solution `stencil` over the box in A. */
 int yo_gen_run_part(const char* stencil, int part, const yo_gen_args* A)

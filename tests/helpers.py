@@ -14,6 +14,17 @@ def golden_cases(prefix):
     return sorted(glob.glob(os.path.join(GOLDEN, prefix + "*.npz")))
 
 
+def generated_golden_cases():
+    """Fixtures of every emitter-generated solution (yask_b200/csrc/gen/manifest.json)."""
+    man = json.load(open(os.path.join(os.path.dirname(GOLDEN), "..", "yask_b200", "csrc", "gen", "manifest.json")))
+    out = []
+    for p in golden_cases(""):
+        st = json.loads(str(np.load(p)["meta"]))["stencil"]
+        if st in man:
+            out.append(p)
+    return out
+
+
 def load_golden(path):
     z = np.load(path)
     meta = json.loads(str(z["meta"]))

@@ -52,7 +52,7 @@ def _drive(stencil, n, steps, ins, opts=()):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", [p for p in golden_cases("") if "strict" not in p or "iso3dfd" not in p])
+@pytest.mark.parametrize("path", [p for p in golden_cases("iso3dfd_avx512") + golden_cases("awp_elastic") + golden_cases("ssg")])
 def test_same_driver_source_reproduces_reference_outputs(path):
     meta, arrays = load_golden(path)
     ins = regen_inputs(meta)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle as O
-from tests.helpers import field_ulps, golden_cases, load_golden, range_of, regen_inputs
+from tests.helpers import field_ulps, generated_golden_cases, load_golden, range_of, regen_inputs
 from tests.golden.make_golden import RANGES
 from yask_b200 import capi, multi
 from yask_b200.synth import hash_field, var_salt
@@ -42,13 +42,15 @@ def run_gpu(stencil, n, steps, ins, fp_mode):
     return out, st
 
 
-@pytest.mark.parametrize("path", golden_cases("awp_elastic") + golden_cases("ssg"))
+@pytest.mark.parametrize("path", generated_golden_cases())
 def test_generated_vs_reference_golden(path):
     meta, arrays = load_golden(path)
     ins = regen_inputs(meta)
     strict = "strict" in meta["ref_tag"]
     out, st = run_gpu(meta["stencil"], meta["n"], meta["steps"], ins, 0 if strict else 2)
-    assert len(out) == 9 and st.kernel_launches == 2 * meta["steps"]
+    ir = O.gen_ir(meta["stencil"])
+    assert len(out) == sum(1 for v in ir["vars"] if v["is_output"])
+    assert st.kernel_launches == sum(len(s["parts"]) for s in ir["stages"]) * meta["steps"]
     for name, (tl, got) in out.items():
         ref = arrays[f"{name}.t{tl}"]
         assert got.shape == ref.shape and got.dtype == ref.dtype
@@ -77,7 +79,8 @@ def synth_inputs(stencil, n, seed):
     return ins, ir
 
 
-@pytest.mark.parametrize("stencil,n,steps", [("awp_elastic", (37, 21, 150), 3), ("ssg", (19, 33, 131), 2)])
+@pytest.mark.parametrize("stencil,n,steps", [("awp_elastic", (37, 21, 150), 3), ("ssg", (19, 33, 131), 2), ("awp", (21, 19, 70), 2),
+                                             ("tti", (18, 20, 66), 2), ("3axis", (30, 20, 100), 3), ("iso3dfd_sponge", (20, 24, 80), 2)])
 def test_generated_vs_oracle_ragged(stencil, n, steps):
     ins, ir = synth_inputs(stencil, n, 31)
     out, _ = run_gpu(stencil, n, steps, ins, 0)
@@ -91,7 +94,9 @@ def test_generated_vs_oracle_ragged(stencil, n, steps):
 
 
 @pytest.mark.parametrize("stencil,n,grid,steps", [("awp_elastic", (40, 24, 64), (2, 1, 1), 3), ("awp_elastic", (24, 24, 48), (2, 2, 2), 2),
-                                                   ("ssg", (32, 20, 40), (1, 2, 2), 2), ("ssg", (41, 16, 32), (3, 1, 1), 2)])
+                                                   ("ssg", (32, 20, 40), (1, 2, 2), 2), ("ssg", (41, 16, 32), (3, 1, 1), 2),
+                                                   ("awp", (32, 24, 48), (2, 2, 1), 2), ("tti", (36, 36, 48), (2, 2, 2), 2),
+                                                   ("cube", (32, 32, 64), (2, 2, 2), 2)])
 def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     """Two-stage solutions exchange halos after each stage; static vars (rho, mu, ...) are exchanged once."""
     ir = O.gen_ir(stencil)
@@ -143,7 +148,7 @@ def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     got = collect(solns)
     for s in solns:
         s.close()
-    assert set(got) == set(ref) and len(got) == 9
+    assert set(got) == set(ref) and len(got) == sum(1 for v in ir["vars"] if v["is_output"])
     for name in ref:
         it = np.uint32 if ref[name].dtype == np.float32 else np.uint64
         assert np.array_equal(got[name].view(it), ref[name].view(it)), name

@@ -46,7 +46,10 @@ def _domain(ir, name, arr):
     return arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) for i, d in enumerate(ir["domain_dims"]))]
 
 
-@pytest.mark.parametrize("path", golden_cases("awp_elastic") + golden_cases("ssg"))
+from tests.helpers import generated_golden_cases  # noqa: E402
+
+
+@pytest.mark.parametrize("path", generated_golden_cases())
 def test_generated_oracle_vs_reference(path):
     """Strict reference build: bit-exact.  Default (GCC-contracted) build: within 4 field-ulps -- GCC's FMA
     choices for these expression trees are not restated, see DESIGN.md section 4."""
@@ -54,7 +57,7 @@ def test_generated_oracle_vs_reference(path):
     ins = regen_inputs(meta)
     out = O.gen_run(meta["stencil"], meta["n"], meta["steps"], ins)
     ir = O.gen_ir(meta["stencil"])
-    assert len(out) == 9
+    assert len(out) == sum(1 for v in ir["vars"] if v["is_output"])
     for name, (tl, arr) in out.items():
         ref = arrays[f"{name}.t{tl}"]
         got = _domain(ir, name, arr)

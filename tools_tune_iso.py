@@ -33,8 +33,8 @@ if __name__ == "__main__":
     base = None
     variants = []
     for rep in range(2):
-        for tile in (2, 7, 8, 10, 11):
-            variants.append(dict(kernel="tma", tile=tile))
+        for (cs, pc, ph) in ((0, 0, 0), (1, 0, 0), (1, 2, 0), (1, 2, 2), (0, 2, 2), (1, 0, 2)):
+            variants.append(dict(kernel="tma", tile=11, st_cs=cs, pol_c=pc, pol_h=ph))
     for opts in variants:
         steps = 3 if opts.get("kernel") == "direct" else 40
         g, ms, cs = run(n, steps, 3, **opts)

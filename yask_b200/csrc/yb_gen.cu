@@ -6,8 +6,7 @@
 #include "yb_core.h"
 #include "yb_gen.cuh"
 // generated solutions
-#include "gen/awp_elastic.gen.cuh"
-#include "gen/ssg.gen.cuh"
+#include "gen/gen_all.inc"
 
 namespace yb {
 
@@ -17,10 +16,7 @@ namespace {
 
 typedef void (*DescribeFn)(GenStencil&);
 struct GenEntry { const char* name; DescribeFn describe; };
-const GenEntry kGen[] = {
-    {"awp_elastic", awp_elastic_describe},
-    {"ssg", ssg_describe},
-};
+const GenEntry kGen[] = {YB_GEN_TABLE};
 
 struct GenEngine : Engine {
     GenStencil g;

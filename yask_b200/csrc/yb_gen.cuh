@@ -10,7 +10,7 @@
 
 namespace yb { namespace gen {
 
-constexpr int GEN_MAX_ACC = 32;   // distinct (var, step-offset) pairs one part may touch
+constexpr int GEN_MAX_ACC = 48;   // distinct (var, step-offset) pairs one part may touch
 // CTA = GEN_BZ x GEN_BY x GEN_BX points (z fastest): neighbouring rows/planes of a point are computed by
 // the same CTA, so their reads of shared neighbours hit L1 instead of going back to L2.
 constexpr int GEN_BZ = 64, GEN_BY = 2, GEN_BX = 2;

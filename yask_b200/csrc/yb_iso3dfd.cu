@@ -206,7 +206,7 @@ struct IsoEngine : Engine {
     int grid_override = 0;
     int num_sms = 148;
     bool attr_set[NTILES][4] = {};
-    int pol_c = 0, pol_h = 0, pol_pv = 1;
+    int pol_c = 0, pol_h = 0, pol_pv = 1, st_cs = 0;
     bool mem_probe = false;      // debug: fp_mode=3 style memory-only kernel
     IsoMaps maps[NTILES][2];       // [tile][cur slot]
     bool maps_ok = false;
@@ -226,6 +226,7 @@ struct IsoEngine : Engine {
         else if (k == "pol_c") { pol_c = atoi(v.c_str()); }
         else if (k == "pol_h") { pol_h = atoi(v.c_str()); }
         else if (k == "pol_pv") { pol_pv = atoi(v.c_str()); }
+        else if (k == "st_cs") { st_cs = atoi(v.c_str()) != 0; }
         else return YB_EINVAL;
         return 0;
     }
@@ -281,7 +282,7 @@ struct IsoEngine : Engine {
         P.z_begin = int(box.b[2]); P.z_end = int(box.e[2]);
         P.pad_x = int(px->pad_l); P.pad_y = int(py->pad_l); P.pad_z = int(pz->pad_l);
         P.vpad_x = int(vx->pad_l); P.vpad_y = int(vy->pad_l); P.vpad_z = int(vz->pad_l);
-        P.pol_c = pol_c; P.pol_h = pol_h; P.pol_pv = pol_pv;
+        P.pol_c = pol_c; P.pol_h = pol_h; P.pol_pv = pol_pv; P.st_cs = st_cs;
         for (int r = 0; r <= ISO_MAX_R; r++) P.c[r] = r <= radius ? float(coef[r]) : 0.f;
     }
 

@@ -34,6 +34,7 @@ struct IsoParams {
     int vpad_x, vpad_y, vpad_z; // v array: same
     int nty, ntz, nchunks, lx;  // tiling of [begin,end): tiles in y,z; chunks of lx planes in x
     int pol_c, pol_h, pol_pv;   // L2 eviction policy of the TMA streams: 0 normal, 1 evict_first, 2 evict_last
+    int st_cs;                  // 1: results leave with streaming (evict-first) stores
     float c[ISO_MAX_R + 1];
 };
 
@@ -514,9 +515,9 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
                 rb.z = iso_final<MODE>(accb[2], pb[2], pvb.z, vvb.z); rb.w = iso_final<MODE>(accb[3], pb[3], pvb.w, vvb.w);
                 float* oa = out_a + (long long)it * P.out_sx;
                 float* ob = oa + P.out_sy;
-                if (vec_ok && nva == 4) stg128(oa, ra);
+                if (vec_ok && nva == 4) { if (P.st_cs) stg128_cs(oa, ra); else stg128(oa, ra); }
                 else if (nva > 0) { oa[0] = ra.x; if (nva > 1) oa[1] = ra.y; if (nva > 2) oa[2] = ra.z; if (nva > 3) oa[3] = ra.w; }
-                if (vec_ok && nvb == 4) stg128(ob, rb);
+                if (vec_ok && nvb == 4) { if (P.st_cs) stg128_cs(ob, rb); else stg128(ob, rb); }
                 else if (nvb > 0) { ob[0] = rb.x; if (nvb > 1) ob[1] = rb.y; if (nvb > 2) ob[2] = rb.z; if (nvb > 3) ob[3] = rb.w; }
             }
             __syncwarp();

@@ -101,4 +101,9 @@ __device__ __forceinline__ void stg128(float* p, float4 v) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// streaming store: evict-first in L1/L2 (the written plane is not read again during this step)
+__device__ __forceinline__ void stg128_cs(float* p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 }  // namespace yb

@@ -42,6 +42,12 @@ class EmitError(RuntimeError):
     pass
 
 
+def c_ident(name: str) -> str:
+    """C identifier for a solution name ("3axis" -> "s3axis")."""
+    i = re.sub(r"\W", "_", name)
+    return ("s" + i) if i[0].isdigit() else i
+
+
 # ----------------------------------------------------------------------------------------------------
 # front-end: run the reference compiler and parse its output
 # ----------------------------------------------------------------------------------------------------
@@ -316,7 +322,7 @@ def _masks(ir, part):
 
 def emit_cuda(ir: dict) -> str:
     n = ir["name"]
-    ident = re.sub(r"\W", "_", n)
+    ident = c_ident(n)
     L = []
     L.append(f"// GENERATED by yask_b200/emitter/yask_cuda_emit.py from the reference compiler's analysis of solution '{n}'.")
     L.append("// Do not edit: re-run the emitter.  One kernel per solution part; statements are the part's expression")
@@ -358,7 +364,7 @@ def emit_cuda(ir: dict) -> str:
 
 def emit_oracle(ir: dict) -> str:
     n = ir["name"]
-    ident = re.sub(r"\W", "_", n)
+    ident = c_ident(n)
     T = "float" if ir["elem_bytes"] == 4 else "double"
     L = []
     L.append(f"/* GENERATED by yask_b200/emitter/yask_cuda_emit.py -- TEST INFRASTRUCTURE ONLY (CPU oracle for '{n}').")
@@ -382,6 +388,26 @@ def emit_oracle(ir: dict) -> str:
     return "\n".join(L) + "\n"
 
 
+def write_registry():
+    """Regenerate the include lists / tables of every emitted solution from gen/manifest.json."""
+    gdir = os.path.join(ROOT, "yask_b200", "csrc", "gen")
+    odir = os.path.join(ROOT, "oracle", "gen")
+    man = json.load(open(os.path.join(gdir, "manifest.json")))
+    names = sorted(man)
+    cu = ["// GENERATED by yask_b200/emitter/yask_cuda_emit.py: every emitted solution (see manifest.json)."]
+    cu += [f'#include "{c_ident(n)}.gen.cuh"' for n in names]
+    cu.append("#define YB_GEN_TABLE \\")
+    cu += [f'    {{"{n}", yb::gen::{c_ident(n)}_describe}}, \\' for n in names]
+    cu.append("")
+    open(os.path.join(gdir, "gen_all.inc"), "w").write("\n".join(cu) + "\n")
+    oc = ["/* GENERATED by yask_b200/emitter/yask_cuda_emit.py -- TEST INFRASTRUCTURE ONLY. */"]
+    oc += [f'#include "{c_ident(n)}.gen.h"' for n in names]
+    oc.append("#define YO_GEN_TABLE \\")
+    oc += [f'    {{"{n}", yo_{c_ident(n)}_parts, (int)(sizeof(yo_{c_ident(n)}_parts) / sizeof(yo_gen_part))}}, \\' for n in names]
+    oc.append("")
+    open(os.path.join(odir, "gen_all.inc"), "w").write("\n".join(oc) + "\n")
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--stencil", required=True)
@@ -400,13 +426,18 @@ def main(argv=None):
     odir = os.path.join(ROOT, "oracle", "gen")
     os.makedirs(gdir, exist_ok=True)
     os.makedirs(odir, exist_ok=True)
-    ident = re.sub(r"\W", "_", name)
+    ident = c_ident(name)
     open(os.path.join(gdir, f"{ident}.gen.cuh"), "w").write(emit_cuda(ir))
     open(os.path.join(odir, f"{ident}.gen.h"), "w").write(emit_oracle(ir))
     slim = {k: v for k, v in ir.items() if k != "stages"}
     slim["stages"] = [{"name": s["name"], "parts": [{"name": p["name"], "fp_ops": p["fp_ops"], "reads": p["reads"], "writes": p["writes"],
                                                        "accesses": p["accesses"], "outputs": p["outputs"]} for p in s["parts"]]} for s in ir["stages"]]
-    json.dump(slim, open(os.path.join(gdir, f"{ident}.json"), "w"), indent=1)
+    json.dump(slim, open(os.path.join(gdir, f"{name}.json"), "w"), indent=1)
+    mpath = os.path.join(gdir, "manifest.json")
+    man = json.load(open(mpath)) if os.path.exists(mpath) else {}
+    man[name] = {"stencil": a.stencil, "radius": a.radius, "elem_bytes": ir["elem_bytes"]}
+    json.dump(man, open(mpath, "w"), indent=1, sort_keys=True)
+    write_registry()
     nst = sum(len(p["stmts"]) for s in ir["stages"] for p in s["parts"])
     print(f"emitted {name}: {len(ir['vars'])} vars, {len(ir['stages'])} stage(s), {nst} statements, elem_bytes {ir['elem_bytes']}")
 
