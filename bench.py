@@ -270,52 +270,55 @@ def main_b200(args):
     # ---- e2e through the C ABI with host buffers ------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        f0, l0 = p.halo_box(0)
-        shape = [b - a + 1 for a, b in zip(f0[1:], l0[1:])]
-        tl = p.get_last_valid_step_index()
-        # host copies of the inputs in pinned memory (set-up, untimed): read back the synthetic fields
-        hp = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
-        hv = torch.empty([N, N, N], dtype=torch.float32, pin_memory=True)
-        hout = torch.empty([N, N, N], dtype=torch.float32, pin_memory=True)
-        import ctypes as C
-        L = capi.lib()
+      try:
+            f0, l0 = p.halo_box(0)
+            shape = [b - a + 1 for a, b in zip(f0[1:], l0[1:])]
+            tl = p.get_last_valid_step_index()
+            # host copies of the inputs in pinned memory (set-up, untimed): read back the synthetic fields
+            hp = [torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            hv = torch.empty([N, N, N], dtype=torch.float32, pin_memory=True)
+            hout = torch.empty([N, N, N], dtype=torch.float32, pin_memory=True)
+            import ctypes as C
+            L = capi.lib()
 
-        def get_into(var, tens, first, last):
-            n = C.c_int64(0)
-            capi._chk(L.yb_var_get_slice(s._h, var.index, C.c_void_p(tens.data_ptr()), capi._arr(first), capi._arr(last), C.byref(n)))
+            def get_into(var, tens, first, last):
+                n = C.c_int64(0)
+                capi._chk(L.yb_var_get_slice(s._h, var.index, C.c_void_p(tens.data_ptr()), capi._arr(first), capi._arr(last), C.byref(n)))
 
-        def set_from(var, tens, first, last):
-            n = C.c_int64(0)
-            capi._chk(L.yb_var_set_slice(s._h, var.index, C.c_void_p(tens.data_ptr()), capi._arr(first), capi._arr(last), C.byref(n)))
+            def set_from(var, tens, first, last):
+                n = C.c_int64(0)
+                capi._chk(L.yb_var_set_slice(s._h, var.index, C.c_void_p(tens.data_ptr()), capi._arr(first), capi._arr(last), C.byref(n)))
 
-        for i, t in enumerate((tl - 1, tl)):
-            f, l = p.halo_box(t)
-            get_into(p, hp[i], f, l)
-        fv, lv = v.halo_box(0)
-        get_into(v, hv, fv, lv)
-        barrier()
-        te0 = time.time()
-        for i, t in enumerate((tl - 1, tl)):           # H2D: both step slots of p, and v
-            f, l = p.halo_box(t)
-            set_from(p, hp[i], f, l)
-        set_from(v, hv, fv, lv)
-        s.run_solution(tl, tl + K - 1)                   # K steps
-        tl2 = p.get_last_valid_step_index()
-        get_into(p, hout, *p.domain_box(tl2))            # D2H of the result (syncs)
-        s.sync()
-        barrier()
-        te1 = time.time()
-        e2e_s = te1 - te0
-        if dist:
-            tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e2e_s = tt.item()
-        h2d = (2 * hp[0].numel() + hv.numel()) * 4
-        d2h = hout.numel() * 4
-        e2e = {"value": round(pts_per_gpu * world * K / e2e_s / 1e9, 2), "unit": "GPoints/s", "h2d_bytes_per_step": h2d // K,
-               "d2h_bytes_per_step": d2h // K, "seconds": round(e2e_s, 4), "h2d_bytes_total_per_gpu": h2d, "d2h_bytes_total_per_gpu": d2h,
-               "note": "set_elements_in_slice(p t-1,t; v) from pinned host + run_solution(K) + get_elements_in_slice(p)"}
-        launches_e2e = s.get_stats().kernel_launches - launches
+            for i, t in enumerate((tl - 1, tl)):
+                f, l = p.halo_box(t)
+                get_into(p, hp[i], f, l)
+            fv, lv = v.halo_box(0)
+            get_into(v, hv, fv, lv)
+            barrier()
+            te0 = time.time()
+            for i, t in enumerate((tl - 1, tl)):           # H2D: both step slots of p, and v
+                f, l = p.halo_box(t)
+                set_from(p, hp[i], f, l)
+            set_from(v, hv, fv, lv)
+            s.run_solution(tl, tl + K - 1)                   # K steps
+            tl2 = p.get_last_valid_step_index()
+            get_into(p, hout, *p.domain_box(tl2))            # D2H of the result (syncs)
+            s.sync()
+            barrier()
+            te1 = time.time()
+            e2e_s = te1 - te0
+            if dist:
+                tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                e2e_s = tt.item()
+            h2d = (2 * hp[0].numel() + hv.numel()) * 4
+            d2h = hout.numel() * 4
+            e2e = {"value": round(pts_per_gpu * world * K / e2e_s / 1e9, 2), "unit": "GPoints/s", "h2d_bytes_per_step": h2d // K,
+                   "d2h_bytes_per_step": d2h // K, "seconds": round(e2e_s, 4), "h2d_bytes_total_per_gpu": h2d, "d2h_bytes_total_per_gpu": d2h,
+                   "note": "set_elements_in_slice(p t-1,t; v) from pinned host + run_solution(K) + get_elements_in_slice(p)"}
+            launches_e2e = s.get_stats().kernel_launches - launches
+      except Exception as ex:   # keep the bench line alive (e.g. pinned-memory limits on a shared host)
+        e2e = {"value": None, "unit": "GPoints/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "error": repr(ex)[:200]}
     s.close()
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------

@@ -48,7 +48,7 @@ def synth_inputs(n, seed, radius=8):
 
 
 @pytest.mark.parametrize("kernel", ["tma", "direct"])
-@pytest.mark.parametrize("path", golden_cases("iso3dfd"))
+@pytest.mark.parametrize("path", golden_cases("iso3dfd_avx512") + golden_cases("iso3dfd-strict"))
 def test_bit_exact_vs_reference_golden(path, kernel):
     meta, arrays = load_golden(path)
     ins = regen_inputs(meta)

@@ -20,7 +20,7 @@ def test_fd_coefficients_match_generated_literals():
     assert abs(c2[0] - (-3.0e-3)) < 1e-9 and abs(c2[1] - 0.000533333) < 1e-9 and abs(c2[2] - (-3.333333e-05)) < 1e-11
 
 
-@pytest.mark.parametrize("path", golden_cases("iso3dfd"))
+@pytest.mark.parametrize("path", golden_cases("iso3dfd_avx512") + golden_cases("iso3dfd-strict"))
 def test_iso3dfd_oracle_bit_exact_vs_reference(path):
     meta, arrays = load_golden(path)
     ins = regen_inputs(meta)
