@@ -13,7 +13,7 @@ from typing import Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libyask_b200.so")
+LIB_PATH = os.environ.get("YASK_B200_LIB", os.path.join(_HERE, "lib", "libyask_b200.so"))   # env override: tuning experiments only
 
 YB_MAX_DIMS = 5
 YB_NAME_LEN = 64

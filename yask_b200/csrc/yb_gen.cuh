@@ -13,7 +13,18 @@ namespace yb { namespace gen {
 constexpr int GEN_MAX_ACC = 48;   // distinct (var, step-offset) pairs one part may touch
 // CTA = GEN_BZ x GEN_BY x GEN_BX points (z fastest): neighbouring rows/planes of a point are computed by
 // the same CTA, so their reads of shared neighbours hit L1 instead of going back to L2.
-constexpr int GEN_BZ = 64, GEN_BY = 2, GEN_BX = 2;
+#ifndef YB_GEN_BZ
+#define YB_GEN_BZ 64
+#define YB_GEN_BY 2
+#define YB_GEN_BX 2
+#endif
+#ifndef YB_GEN_NP
+#define YB_GEN_NP 2
+#endif
+constexpr int GEN_BZ = YB_GEN_BZ, GEN_BY = YB_GEN_BY, GEN_BX = YB_GEN_BX;
+// Each thread computes GEN_NP points (rows y, y + GEN_BY, ...): the unrolled bodies are independent, so the
+// compiler overlaps their loads -- the kernels are load-latency bound (ncu: long_scoreboard dominates).
+constexpr int GEN_NP = YB_GEN_NP;
 constexpr int GEN_BLOCK = GEN_BZ * GEN_BY * GEN_BX;
 
 struct GenParams {
@@ -78,11 +89,15 @@ template <typename T> struct GenOp<T, 1> {
     static __device__ __forceinline__ T div(T a, T b) { return a / b; }
 };
 
-#define GEN_KERNEL_PROLOGUE                                                          \
-    const int z = P.zb + blockIdx.x * GEN_BZ + (threadIdx.x % GEN_BZ);               \
-    const int y = P.yb + blockIdx.y * GEN_BY + (threadIdx.x / GEN_BZ) % GEN_BY;      \
-    const int x = P.xb + blockIdx.z * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);      \
-    if (z >= P.ze || y >= P.ye || x >= P.xe) return;
+#define GEN_KERNEL_BEGIN                                                                         \
+    const int z = P.zb + blockIdx.x * GEN_BZ + (threadIdx.x % GEN_BZ);                           \
+    const int y0_ = P.yb + blockIdx.y * (GEN_BY * GEN_NP) + (threadIdx.x / GEN_BZ) % GEN_BY;     \
+    const int x = P.xb + blockIdx.z * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);                  \
+    if (z >= P.ze || x >= P.xe) return;                                                          \
+    _Pragma("unroll") for (int gp_ = 0; gp_ < GEN_NP; gp_++) {                                   \
+        const int y = y0_ + gp_ * GEN_BY;                                                        \
+        if (y < P.ye) {
+#define GEN_KERNEL_END } }
 // m = dim mask of the var (x=1, y=2, z=4).  Full-rank vars (m==7) use the shared geometry: one 64-bit position
 // per thread, 32-bit neighbour offsets that the compiler shares across vars; lower-rank vars (1-D sponge
 // arrays, scalars) take the general strided path.

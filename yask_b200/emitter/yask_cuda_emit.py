@@ -336,8 +336,9 @@ def emit_cuda(ir: dict) -> str:
             L.append(f"// part '{p['name']}' of stage '{st['name']}': {p['fp_ops']} FP ops, {p['reads']} reads, {p['writes']} writes per point")
             L.append("template <typename T, int MODE>")
             L.append(f"__global__ void __launch_bounds__(GEN_BLOCK) {ident}_{p['name']}_kernel(const __grid_constant__ GenParams P) {{")
-            L.append("    GEN_KERNEL_PROLOGUE")
+            L.append("    GEN_KERNEL_BEGIN")
             L.extend(_stmt_lines(p, len(ir["domain_dims"]), masks=_masks(ir, p)))
+            L.append("    GEN_KERNEL_END")
             L.append("}")
     # spec table
     L.append(f"inline void {ident}_describe(GenStencil& g) {{")
