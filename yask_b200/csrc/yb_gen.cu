@@ -55,7 +55,7 @@ struct GenEngine : Engine {
                 }
             }
             GenKernelFn fn = p.fn[g.elem_bytes == 8 ? 1 : 0][s.fp_mode == 0 ? 0 : 1];
-            dim3 grd(unsigned((box.e[2] - box.b[2] + GEN_BZ - 1) / GEN_BZ), unsigned((box.e[1] - box.b[1] + GEN_BY * GEN_NP - 1) / (GEN_BY * GEN_NP)),
+            dim3 grd(unsigned((box.e[2] - box.b[2] + GEN_BZ - 1) / GEN_BZ), unsigned((box.e[1] - box.b[1] + GEN_BY * gen_np(g.elem_bytes) - 1) / (GEN_BY * gen_np(g.elem_bytes))),
                      unsigned((box.e[0] - box.b[0] + GEN_BX - 1) / GEN_BX));
             if (grd.y > 65535 || grd.z > 65535) return set_error(YB_EUNSUPPORTED, "domain too large in x or y for the generated kernels");
             fn<<<grd, GEN_BLOCK, 0, st>>>(P);

@@ -14,17 +14,16 @@ constexpr int GEN_MAX_ACC = 48;   // distinct (var, step-offset) pairs one part 
 // CTA = GEN_BZ x GEN_BY x GEN_BX points (z fastest): neighbouring rows/planes of a point are computed by
 // the same CTA, so their reads of shared neighbours hit L1 instead of going back to L2.
 #ifndef YB_GEN_BZ
-#define YB_GEN_BZ 64
-#define YB_GEN_BY 2
-#define YB_GEN_BX 2
-#endif
-#ifndef YB_GEN_NP
-#define YB_GEN_NP 2
+#define YB_GEN_BZ 128
+#define YB_GEN_BY 1
+#define YB_GEN_BX 1
 #endif
 constexpr int GEN_BZ = YB_GEN_BZ, GEN_BY = YB_GEN_BY, GEN_BX = YB_GEN_BX;
-// Each thread computes GEN_NP points (rows y, y + GEN_BY, ...): the unrolled bodies are independent, so the
+// Each thread computes several points (rows y, y + GEN_BY, ...): the unrolled bodies are independent, so the
 // compiler overlaps their loads -- the kernels are load-latency bound (ncu: long_scoreboard dominates).
-constexpr int GEN_NP = YB_GEN_NP;
+// Measured on B200 at 512^3 (profiles/r1_iso3dfd.md): 4 rows per thread is best for fp32 (awp_elastic 19.3 ->
+// 22.1 GPts/s), 2 for fp64 (ssg 11.1 -> 11.6; 4 rows spill into lower occupancy).
+__host__ __device__ constexpr int gen_np(int elem_bytes) { return elem_bytes == 4 ? 4 : 2; }
 constexpr int GEN_BLOCK = GEN_BZ * GEN_BY * GEN_BX;
 
 struct GenParams {
@@ -91,6 +90,7 @@ template <typename T> struct GenOp<T, 1> {
 
 #define GEN_KERNEL_BEGIN                                                                         \
     const int z = P.zb + blockIdx.x * GEN_BZ + (threadIdx.x % GEN_BZ);                           \
+    constexpr int GEN_NP = gen_np(int(sizeof(T)));                                               \
     const int y0_ = P.yb + blockIdx.y * (GEN_BY * GEN_NP) + (threadIdx.x / GEN_BZ) % GEN_BY;     \
     const int x = P.xb + blockIdx.z * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);                  \
     if (z >= P.ze || x >= P.xe) return;                                                          \
