@@ -187,6 +187,7 @@ def main_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("YB_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         import torch.distributed as dist_
         dist = dist_
         torch.cuda.set_device(local)

@@ -358,7 +358,7 @@ int yb_set_option(yb_solution* s_, const char* key, const char* value) {
         int m = atoi(value);
         if (m < 0 || m > 2) return set_error(YB_EINVAL, "fp_mode must be 0, 1 or 2");
         s->fp_mode = m;
-    } else if (k == "overlap_comms" || k == "min_exterior") {
+    } else if (k == "overlap_comms" || k == "min_exterior" || k == "fused_halo") {
         // consumed by the halo engine at run time
     } else if (s->engine->set_option(*s, k, v) != 0) {
         return set_error(YB_EINVAL, "unknown option '%s'", key);

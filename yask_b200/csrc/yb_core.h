@@ -163,6 +163,10 @@ struct Solution {
     size_t stage_host_bytes = 0;
     // multi-GPU
     HaloState* halo = nullptr;   // owned; freed by halo_free()
+    // Fused halo stores (set by the halo layer before a stage launch, consumed by an engine that can store its
+    // boundary planes straight into the x neighbours' halo cells): element (0,0,0)-relative base pointers of the
+    // OUTPUT var's step slot in the lower / upper x neighbour, or null.  The engine sets `used` if it honoured them.
+    struct FusedX { void* lo = nullptr; void* hi = nullptr; int var = -1; bool used = false; } fused_x;
     int multi_rank() const { return int(num_ranks[0] * num_ranks[1] * num_ranks[2]) > 1; }
     ~Solution();
 };

@@ -240,7 +240,8 @@ static int push_var_slot(Solution& s, const Neighbor& nb, int vi, int slot, cuda
 }
 
 // Push every dirty (var, slot) to every neighbour, signal, then wait for the neighbours' signals.
-int halo_exchange_all(Solution& s, cudaStream_t st) {
+// skip_var/skip_x: the stage kernel already stored this var's x-face halos into the peers (fused path).
+static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var) {
     HaloState* h = s.halo;
     if (!h) return 0;
     if (!h->finalized) return set_error(YB_ESTATE, "multi-rank solution: halo peers were not connected (yb_halo_import/finalize)");
@@ -252,6 +253,7 @@ int halo_exchange_all(Solution& s, cudaStream_t st) {
     for (auto& nb : h->nbrs) {
         for (size_t vi = 0; vi < s.vars.size(); vi++) {
             if (!var_talks_to(s.vars[vi], nb.dir)) continue;
+            if (int(vi) == skip_var && nb.dir[0] != 0 && nb.dir[1] == 0 && nb.dir[2] == 0) continue;   // done by the kernel
             for (int slot = 0; slot < s.vars[vi].step_alloc(); slot++) {
                 if (!h->dirty[vi][slot]) continue;
                 int rc = push_var_slot(s, nb, int(vi), slot, st);
@@ -272,21 +274,51 @@ int halo_exchange_all(Solution& s, cudaStream_t st) {
     return 0;
 }
 
+int halo_exchange_all(Solution& s, cudaStream_t st) { return halo_exchange_impl(s, st, -1); }
+
 // One stage of one step on a multi-rank solution.  Round 1: whole-domain compute, then push + wait
 // (the face transfer is ~1-2 % of a step at 1024^3 per GPU; the boundary-first overlap of
 // context.cpp:378-475 is replaced in a later step by a kernel that stores to the peers directly).
 int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
     Box whole;
     for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = d < s.ndd ? s.rank_size[d] : 1; }
+    HaloState* h = s.halo;
+    if (!h->finalized) return set_error(YB_ESTATE, "multi-rank solution: halo peers were not connected (yb_halo_import/finalize)");
+    // Fused path: if the stage writes exactly one var, hand the engine the x neighbours' halo cells of that
+    // var's output slot; an engine that can (the iso3dfd sweep kernel) stores its first/last planes there while it
+    // computes them, so that transfer rides on the sweep instead of following it.
+    s.fused_x = Solution::FusedX();
+    const auto& outs = s.spec.stages[stage].outputs;
+    auto fo = s.options.find("fused_halo");
+    const bool want_fused = fo == s.options.end() || fo->second != "0";
+    if (outs.size() == 1 && want_fused) {
+        const int vi = outs[0];
+        const Var& v = s.vars[vi];
+        const int slot = v.slot_of(t + 1);
+        const Dim* dx = v.domain_dim(0);
+        for (auto& nb : h->nbrs) {
+            if (nb.dir[1] != 0 || nb.dir[2] != 0 || nb.dir[0] == 0 || !dx) continue;
+            const BlobVar& pg = nb.var_geom[vi];
+            // same y/z geometry on both sides (always true for pure x neighbours) and a 3-D var
+            bool same = pg.nd == 3 && pg.stride[0] == v.dims[1].stride && pg.stride[1] == v.dims[2].stride && pg.stride[2] == 1;
+            if (!same) continue;
+            char* base = nb.var_base[vi] + size_t(slot) * pg.slot_elems * v.elem_bytes;
+            long long origin = pg.pad_l[0] * pg.stride[0] + pg.pad_l[1] * pg.stride[1] + pg.pad_l[2] * pg.stride[2];
+            if (nb.dir[0] < 0) s.fused_x.lo = base + (origin + pg.domain[0] * pg.stride[0]) * v.elem_bytes;      // its right halo starts at its n_x
+            else s.fused_x.hi = base + (origin - dx->domain * pg.stride[0]) * v.elem_bytes;                          // my plane n_x-R.. -> its planes -R..
+            s.fused_x.var = vi;
+        }
+    }
     int rc = s.engine->launch(s, stage, t, whole, st);
     if (rc < 0) return rc;
     s.stats.kernel_launches += rc;
-    HaloState* h = s.halo;
     for (int vi : s.spec.stages[stage].outputs) {
         const Var& v = s.vars[vi];
         h->dirty[vi][v.slot_of(t + 1)] = 1;
     }
-    return halo_exchange_all(s, st);
+    const int skip = s.fused_x.used ? s.fused_x.var : -1;
+    s.fused_x = Solution::FusedX();
+    return halo_exchange_impl(s, st, skip);
 }
 
 }  // namespace yb

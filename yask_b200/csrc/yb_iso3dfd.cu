@@ -148,6 +148,7 @@ int make_map(CUtensorMap* map, const Var& v, int slot, int bz, int by) {
 // Tile configurations of the TMA kernels that are compiled in.
 typedef void (*IsoKernelFn)(const IsoMaps, const IsoParams);
 struct TileCfg {
+    bool fused_ok;      // kernel can store boundary planes into the x neighbours (gen2 PW/U variants)
     const char* name;
     int ty, tz, hp, hrows, threads;
     uint32_t smem;
@@ -156,24 +157,24 @@ struct TileCfg {
 
 template <class T>
 TileCfg cfg_gen1(const char* name) {
-    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
+    return TileCfg{false, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
                    {iso3dfd_tma_kernel<T, 0>, iso3dfd_tma_kernel<T, 1>, iso3dfd_tma_kernel<T, 2>, nullptr}};
 }
 template <class T>
 TileCfg cfg_gen2(const char* name) {
-    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
+    return TileCfg{true, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
                    {iso3dfd_tma2_kernel<T, 0>, iso3dfd_tma2_kernel<T, 1>, iso3dfd_tma2_kernel<T, 2>, iso3dfd_tma2_kernel<T, 3>}};
 }
 
 template <class T>
 TileCfg cfg_gen3(const char* name) {
-    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
+    return TileCfg{false, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
                    {iso3dfd_tma3_kernel<T, 0>, iso3dfd_tma3_kernel<T, 1>, iso3dfd_tma3_kernel<T, 2>, nullptr}};
 }
 
 template <class T, int PW, int U>
 TileCfg cfg_gen2x(const char* name) {
-    return TileCfg{name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS + 128 * PW, T::SMEM_BYTES,
+    return TileCfg{true, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS + 128 * PW, T::SMEM_BYTES,
                    {iso3dfd_tma2_kernel<T, 0, PW, U>, iso3dfd_tma2_kernel<T, 1, PW, U>, iso3dfd_tma2_kernel<T, 2, PW, U>,
                     iso3dfd_tma2_kernel<T, 3, PW, U>}};
 }
@@ -302,6 +303,13 @@ struct IsoEngine : Engine {
         if (use_tma) {
             const TileCfg& c = tile_cfg(tile);
             if (mem_probe && c.fn[3]) mode = 3;
+            // fused halo exchange: only for whole-domain launches of a kernel that implements the peer stores
+            P.peer_lo = P.peer_hi = nullptr;
+            if (s.fused_x.var == 0 && c.fused_ok && mode != 3 && box.b[0] == 0 && box.e[0] == P.nx && P.nx >= 2 * radius) {
+                P.peer_lo = static_cast<float*>(s.fused_x.lo);
+                P.peer_hi = static_cast<float*>(s.fused_x.hi);
+                s.fused_x.used = true;
+            }
             P.nty = int((box.e[1] - box.b[1] + c.ty - 1) / c.ty);
             P.ntz = int((box.e[2] - box.b[2] + c.tz - 1) / c.tz);
             const int64_t nxb = box.e[0] - box.b[0];

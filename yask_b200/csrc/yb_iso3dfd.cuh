@@ -35,6 +35,10 @@ struct IsoParams {
     int nty, ntz, nchunks, lx;  // tiling of [begin,end): tiles in y,z; chunks of lx planes in x
     int pol_c, pol_h, pol_pv;   // L2 eviction policy of the TMA streams: 0 normal, 1 evict_first, 2 evict_last
     int st_cs;                  // 1: results leave with streaming (evict-first) stores
+    // Fused halo exchange: when non-null, the first / last R computed x planes are ALSO stored into the lower /
+    // upper x neighbour's halo cells (peer HBM over NVLink), indexed exactly like `out`.
+    float* peer_lo;
+    float* peer_hi;
     float c[ISO_MAX_R + 1];
 };
 
@@ -519,6 +523,17 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
                 else if (nva > 0) { oa[0] = ra.x; if (nva > 1) oa[1] = ra.y; if (nva > 2) oa[2] = ra.z; if (nva > 3) oa[3] = ra.w; }
                 if (vec_ok && nvb == 4) { if (P.st_cs) stg128_cs(ob, rb); else stg128(ob, rb); }
                 else if (nvb > 0) { ob[0] = rb.x; if (nvb > 1) ob[1] = rb.y; if (nvb > 2) ob[2] = rb.z; if (nvb > 3) ob[3] = rb.w; }
+                // fused halo exchange: boundary planes also go straight into the x neighbours' halo cells
+                const int xo = cu.x0 + it - 2 * R;
+                float* peer = (P.peer_lo != nullptr && xo < R) ? P.peer_lo : ((P.peer_hi != nullptr && xo >= P.nx - R) ? P.peer_hi : nullptr);
+                if (peer != nullptr) {
+                    float* qa_ = peer + (oa - P.out);
+                    float* qb_ = qa_ + P.out_sy;
+                    if (vec_ok && nva == 4) stg128(qa_, ra);
+                    else if (nva > 0) { qa_[0] = ra.x; if (nva > 1) qa_[1] = ra.y; if (nva > 2) qa_[2] = ra.z; if (nva > 3) qa_[3] = ra.w; }
+                    if (vec_ok && nvb == 4) stg128(qb_, rb);
+                    else if (nvb > 0) { qb_[0] = rb.x; if (nvb > 1) qb_[1] = rb.y; if (nvb > 2) qb_[2] = rb.z; if (nvb > 3) qb_[3] = rb.w; }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[cu.stage]);
