@@ -1,6 +1,6 @@
 """Scratch: short iso3dfd run for ncu (not part of the product)."""
 import sys
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, '..')
 from yask_b200 import capi
 from yask_b200.synth import var_salt
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 1024

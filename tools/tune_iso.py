@@ -1,7 +1,7 @@
 """Scratch tuner: time iso3dfd variants on one GPU (not part of the product; used through gpurun)."""
 import json, sys, time
 import ctypes as C
-sys.path.insert(0, '.')
+sys.path.insert(0, '.'); sys.path.insert(0, '..')
 from yask_b200 import capi
 from yask_b200.synth import var_salt
 import torch
