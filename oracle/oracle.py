@@ -67,7 +67,8 @@ def iso3dfd_run(p0: np.ndarray, p1: np.ndarray, v: np.ndarray, radius: int, step
 # ---------------------------------------------------------------------------------------
 class _GenArgs(ctypes.Structure):
     _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 48),
-                ("sx", ctypes.c_int64 * 48), ("sy", ctypes.c_int64 * 48), ("sz", ctypes.c_int64 * 48)]
+                ("sx", ctypes.c_int64 * 48), ("sy", ctypes.c_int64 * 48), ("sz", ctypes.c_int64 * 48),
+                ("off", ctypes.c_int64 * 3), ("gfirst", ctypes.c_int64 * 3), ("glast", ctypes.c_int64 * 3)]
 
 
 def gen_ir(stencil: str) -> dict:
@@ -109,6 +110,8 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
             for p in st["parts"]:
                 A = _GenArgs()
                 A.nx, A.ny, A.nz = nn
+                for d in range(3):
+                    A.off[d], A.gfirst[d], A.glast[d] = 0, 0, nn[d] - 1
                 for k, acc in enumerate(p["accesses"]):
                     v, has_step, a = meta[acc["var"]]
                     arr = slots[acc["var"]][(t + acc["toff"]) % a]

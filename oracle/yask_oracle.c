@@ -217,6 +217,7 @@ typedef struct {
     int64_t nx, ny, nz;                 /* rank-domain box [0,n) */
     void* ptr[YO_GEN_MAX_ACC];          /* element (0,0,0) of each access' step slot */
     int64_t sx[YO_GEN_MAX_ACC], sy[YO_GEN_MAX_ACC], sz[YO_GEN_MAX_ACC];
+    int64_t off[3], gfirst[3], glast[3];   /* for sub-domain conditions (global indices) */
 } yo_gen_args;
 typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } yo_gen_part;
 
@@ -229,6 +230,9 @@ typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } y
 #define RD(a, m, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
 #define WR(a, m, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
 #define C(v) ((T)(v))
+#define G(i) ((i) == 0 ? x + A->off[0] : ((i) == 1 ? y + A->off[1] : z + A->off[2]))
+#define GF(i) A->gfirst[i]
+#define GL(i) A->glast[i]
 #define ADD(a, b) ((a) + (b))
 #define SUB(a, b) ((a) - (b))
 #define MUL(a, b) ((a) * (b))

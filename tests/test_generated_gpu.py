@@ -80,7 +80,8 @@ def synth_inputs(stencil, n, seed):
 
 
 @pytest.mark.parametrize("stencil,n,steps", [("awp_elastic", (37, 21, 150), 3), ("ssg", (19, 33, 131), 2), ("awp", (21, 19, 70), 2),
-                                             ("tti", (18, 20, 66), 2), ("3axis", (30, 20, 100), 3), ("iso3dfd_sponge", (20, 24, 80), 2)])
+                                             ("tti", (18, 20, 66), 2), ("3axis", (30, 20, 100), 3), ("iso3dfd_sponge", (20, 24, 80), 2),
+                                             ("awp_elastic_abc", (19, 23, 40), 3), ("awp_abc", (16, 18, 37), 2)])
 def test_generated_vs_oracle_ragged(stencil, n, steps):
     ins, ir = synth_inputs(stencil, n, 31)
     out, _ = run_gpu(stencil, n, steps, ins, 0)
@@ -96,7 +97,8 @@ def test_generated_vs_oracle_ragged(stencil, n, steps):
 @pytest.mark.parametrize("stencil,n,grid,steps", [("awp_elastic", (40, 24, 64), (2, 1, 1), 3), ("awp_elastic", (24, 24, 48), (2, 2, 2), 2),
                                                    ("ssg", (32, 20, 40), (1, 2, 2), 2), ("ssg", (41, 16, 32), (3, 1, 1), 2),
                                                    ("awp", (32, 24, 48), (2, 2, 1), 2), ("tti", (36, 36, 48), (2, 2, 2), 2),
-                                                   ("cube", (32, 32, 64), (2, 2, 2), 2)])
+                                                   ("cube", (32, 32, 64), (2, 2, 2), 2),
+                                                   ("awp_elastic_abc", (24, 24, 40), (2, 1, 2), 3), ("awp_abc", (24, 20, 36), (1, 2, 3), 2)])
 def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     """Two-stage solutions exchange halos after each stage; static vars (rho, mu, ...) are exchanged once."""
     ir = O.gen_ir(stencil)

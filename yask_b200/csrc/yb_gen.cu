@@ -34,9 +34,22 @@ struct GenEngine : Engine {
         int n = 0;
         for (auto& p : gs.parts) {
             GenParams P{};
-            P.xb = int(box.b[0]); P.xe = int(box.e[0]);
-            P.yb = int(box.b[1]); P.ye = int(box.e[1]);
-            P.zb = int(box.b[2]); P.ze = int(box.e[2]);
+            // shrink the launch box to the part's sub-domain (IF_DOMAIN), expressed over global indices
+            // (the reference intersects with per-part bounding boxes, setup.cpp:1235-1498)
+            Box pb = box;
+            for (int d = 0; d < 3; d++) {
+                P.off[d] = d < s.ndd ? s.rank_offset[d] : 0;
+                P.gfirst[d] = 0;
+                P.glast[d] = d < s.ndd ? s.overall_size[d] - 1 : 0;
+                const auto& bd = p.bound[d];
+                auto resolve = [&](int kind, int off) { return (kind == 2 ? P.glast[d] : (kind == 1 ? P.gfirst[d] : 0)) + off; };
+                if (bd.lo_kind >= 0) pb.b[d] = std::max<int64_t>(pb.b[d], resolve(bd.lo_kind, bd.lo_off) - P.off[d]);
+                if (bd.hi_kind >= 0) pb.e[d] = std::min<int64_t>(pb.e[d], resolve(bd.hi_kind, bd.hi_off) - P.off[d] + 1);
+            }
+            if (pb.empty()) continue;
+            P.xb = int(pb.b[0]); P.xe = int(pb.e[0]);
+            P.yb = int(pb.b[1]); P.ye = int(pb.e[1]);
+            P.zb = int(pb.b[2]); P.ze = int(pb.e[2]);
             P.SX = P.SY = 0;
             for (size_t k = 0; k < p.acc.size(); k++) {
                 const Var& v = s.vars[p.acc[k].var];
@@ -55,8 +68,8 @@ struct GenEngine : Engine {
                 }
             }
             GenKernelFn fn = p.fn[g.elem_bytes == 8 ? 1 : 0][s.fp_mode == 0 ? 0 : 1];
-            dim3 grd(unsigned((box.e[2] - box.b[2] + GEN_BZ - 1) / GEN_BZ), unsigned((box.e[1] - box.b[1] + GEN_BY * gen_np(g.elem_bytes) - 1) / (GEN_BY * gen_np(g.elem_bytes))),
-                     unsigned((box.e[0] - box.b[0] + GEN_BX - 1) / GEN_BX));
+            dim3 grd(unsigned((pb.e[2] - pb.b[2] + GEN_BZ - 1) / GEN_BZ), unsigned((pb.e[1] - pb.b[1] + GEN_BY * gen_np(g.elem_bytes) - 1) / (GEN_BY * gen_np(g.elem_bytes))),
+                     unsigned((pb.e[0] - pb.b[0] + GEN_BX - 1) / GEN_BX));
             if (grd.y > 65535 || grd.z > 65535) return set_error(YB_EUNSUPPORTED, "domain too large in x or y for the generated kernels");
             fn<<<grd, GEN_BLOCK, 0, st>>>(P);
             YB_CUDA(cudaGetLastError());

@@ -33,6 +33,8 @@ struct GenParams {
     // All vars that span every domain dim share ONE padded geometry (the engine pads them to the solution's
     // largest halo), so their neighbour offsets dx*SX + dy*SY + dz are computed once and shared by all vars.
     int SX, SY;
+    // sub-domain conditions are written over GLOBAL indices: rank offset and overall first/last index per dim
+    long long off[3], gfirst[3], glast[3];
 };
 
 typedef void (*GenKernelFn)(const GenParams);
@@ -52,6 +54,9 @@ struct GenPart {
     std::vector<GenAccess> acc;
     std::vector<int> outs;           // indices into acc of the written accesses
     GenKernelFn fn[2][2];            // [fp64?][mode: 0 strict, 1 fused]
+    // Launch-box bounds derived from the part's sub-domain condition, per domain dim: global index range
+    // [lo, hi] with each end = offset relative to 0 / first / last overall index (kind 0/1/2), kind -1 = open.
+    struct Bound { int lo_kind, lo_off, hi_kind, hi_off; } bound[3];
 };
 struct GenStage { const char* name; std::vector<GenPart> parts; };
 struct GenStencil {
@@ -109,6 +114,9 @@ template <typename T> struct GenOp<T, 1> {
     do { if ((m) == 7) static_cast<T*>(P.ptr[a])[GEN_POS] = (v);                                                         \
          else static_cast<T*>(P.ptr[a])[x * P.sx[a] + y * P.sy[a] + z * P.sz[a]] = (v); } while (0)
 #define C(v) static_cast<T>(v)
+#define G(i) ((i) == 0 ? x + P.off[0] : ((i) == 1 ? y + P.off[1] : z + P.off[2]))
+#define GF(i) P.gfirst[i]
+#define GL(i) P.glast[i]
 #define ADD(a, b) GenOp<T, MODE>::add(a, b)
 #define SUB(a, b) GenOp<T, MODE>::sub(a, b)
 #define MUL(a, b) GenOp<T, MODE>::mul(a, b)

@@ -81,6 +81,97 @@ def parse_index(tok: str, dims: list[str]):
     raise EmitError(f"unsupported index expression '{tok}'")
 
 
+def parse_domain_cond(text: str, dd: list[str]) -> dict:
+    """Sub-domain condition of a part (IF_DOMAIN in the DSL; printed by the reference as a C expression over the
+    GLOBAL domain indices with FIRST_INDEX(d)/LAST_INDEX(d) for the overall problem bounds).
+    Returns {"expr": neutral C text using G(i), GF(i), GL(i); "bounds": per-dim [lo, hi] affine bounds when the
+    expression is a conjunction of simple comparisons (used to shrink the launch box), else None}."""
+    t = text.strip()
+    for i, d in enumerate(dd):
+        t = re.sub(rf"FIRST_INDEX\(\s*{d}\s*\)", f"GF({i})", t)
+        t = re.sub(rf"LAST_INDEX\(\s*{d}\s*\)", f"GL({i})", t)
+    for i, d in enumerate(dd):
+        t = re.sub(rf"(?<!\w){d}(?!\w)", f"G({i})", t)
+    left = re.sub(r"G[FL]?\(\d\)|\d+|[-+*/%()<>=!&| ]", "", t)
+    if left:
+        raise EmitError(f"unsupported token(s) '{left}' in sub-domain condition '{text}'")
+    # bounds: conjunction of  G(i) OP (affine in GF/GL(i) and integers)
+    bounds = {}
+    ok = True
+
+    def strip_parens(x):
+        x = x.strip()
+        while x.startswith("(") and x.endswith(")"):
+            depth, good = 0, True
+            for k, ch in enumerate(x):
+                depth += ch == "("
+                depth -= ch == ")"
+                if depth == 0 and k < len(x) - 1:
+                    good = False
+                    break
+            if not good:
+                break
+            x = x[1:-1].strip()
+        return x
+
+    def split_top(x, sep):
+        parts, depth, cur, k = [], 0, "", 0
+        while k < len(x):
+            ch = x[k]
+            depth += ch == "("
+            depth -= ch == ")"
+            if depth == 0 and x.startswith(sep, k):
+                parts.append(cur)
+                cur = ""
+                k += len(sep)
+                continue
+            cur += ch
+            k += 1
+        parts.append(cur)
+        return parts
+
+    for term in split_top(strip_parens(t), "&&"):
+        term = strip_parens(term)
+        m = re.fullmatch(r"G\((\d)\)\s*(==|<=|>=|<|>)\s*(.+)", term)
+        if not m or "||" in term:
+            ok = False
+            break
+        i, op, rhs = int(m.group(1)), m.group(2), m.group(3)
+        # evaluate rhs symbolically as base + off with base in {GF(i), GL(i), none}
+        probe = {}
+        for base in ("GF", "GL"):
+            if re.search(rf"{base}\((?!{i}\))", rhs):
+                ok = False
+        if not ok:
+            break
+        try:
+            v0 = eval(rhs.replace(f"GF({i})", "0").replace(f"GL({i})", "0"), {"__builtins__": {}})
+            vf = eval(rhs.replace(f"GF({i})", "1").replace(f"GL({i})", "0"), {"__builtins__": {}})
+            vl = eval(rhs.replace(f"GF({i})", "0").replace(f"GL({i})", "1"), {"__builtins__": {}})
+        except Exception:
+            ok = False
+            break
+        cf, cl = vf - v0, vl - v0
+        if (cf, cl) not in ((0, 0), (1, 0), (0, 1)):
+            ok = False
+            break
+        base = "GF" if cf else ("GL" if cl else "0")
+        lo, hi = bounds.get(i, [None, None])
+        b = [base, int(v0)]
+        if op == "==":
+            lo, hi = b, b
+        elif op == "<=":
+            hi = b
+        elif op == "<":
+            hi = [base, int(v0) - 1]
+        elif op == ">=":
+            lo = b
+        elif op == ">":
+            lo = [base, int(v0) + 1]
+        bounds[i] = [lo, hi]
+    return {"expr": t, "bounds": {str(k): v for k, v in bounds.items()} if ok else None, "text": text.strip()}
+
+
 class Parser:
     """Tiny recursive-descent parser for the RHS of generated statements: + - * / with C precedence and
     left associativity, parentheses, unary minus, numeric literals, expr_temp refs and read placeholders."""
@@ -193,8 +284,9 @@ def parse_generated(text: str, name: str) -> dict:
         raise EmitError("no parts found")
     for pm in part_iter:
         pname, cond = pm.group(1), pm.group(2)
-        if "w/o domain condition" not in cond or "w/o step condition" not in cond:
-            raise EmitError(f"part '{pname}' has a sub-domain or step condition: not supported by this emitter")
+        if "w/o step condition" not in cond:
+            raise EmitError(f"part '{pname}' has a step condition: not supported by this emitter")
+        has_dom_cond = "w/o domain condition" not in cond
         stage = [s for pos, s in stage_pos if pos < pm.start()][-1]
         body_start = text.index("static void calc_scalar(", pm.end())
         body_end = text.index("} // calc_scalar.", body_start)
@@ -202,7 +294,13 @@ def parse_generated(text: str, name: str) -> dict:
         head = text[pm.end():body_start]
         if re.search(r"_is_scratch = true", head):
             raise EmitError(f"part '{pname}' is a scratch part: not supported by this emitter")
-        part = {"name": pname, "stage": stage,
+        dom_cond = None
+        if has_dom_cond:
+            mm = re.search(r"is_in_valid_domain\(.*?\n(?:.*?\n)*?\s*return (.*);", head)
+            if not mm:
+                raise EmitError(f"part '{pname}': cannot find its sub-domain expression")
+            dom_cond = parse_domain_cond(mm.group(1), dd)
+        part = {"name": pname, "stage": stage, "cond": dom_cond,
                 "fp_ops": int(re.search(r"_scalar_fp_ops = (\d+);", head).group(1)),
                 "reads": int(re.search(r"_scalar_points_read = (\d+);", head).group(1)),
                 "writes": int(re.search(r"_scalar_points_written = (\d+);", head).group(1)),
@@ -337,7 +435,11 @@ def emit_cuda(ir: dict) -> str:
             L.append("template <typename T, int MODE>")
             L.append(f"__global__ void __launch_bounds__(GEN_BLOCK) {ident}_{p['name']}_kernel(const __grid_constant__ GenParams P) {{")
             L.append("    GEN_KERNEL_BEGIN")
+            if p.get("cond"):
+                L.append(f"    if ({p['cond']['expr']}) {{   // sub-domain: {p['cond']['text']}")
             L.extend(_stmt_lines(p, len(ir["domain_dims"]), masks=_masks(ir, p)))
+            if p.get("cond"):
+                L.append("    }")
             L.append("    GEN_KERNEL_END")
             L.append("}")
     # spec table
@@ -357,7 +459,13 @@ def emit_cuda(ir: dict) -> str:
             outs = ", ".join(str(o["access"]) for o in p["outputs"])
             k = f"{ident}_{p['name']}_kernel"
             fns = f"{{{{GEN_FN({k}, float, 0), GEN_FN({k}, float, 1)}}, {{GEN_FN({k}, double, 0), GEN_FN({k}, double, 1)}}}}"
-            L.append(f'    g.stages.back().parts.push_back(GenPart{{"{p["name"]}", {p["fp_ops"]}, {p["reads"]}, {p["writes"]}, {{{acc}}}, {{{outs}}}, {fns}}});')
+            bl = []
+            bnds = (p.get("cond") or {}).get("bounds") or {}
+            kind = {"0": 0, "GF": 1, "GL": 2}
+            for d in range(3):
+                lo, hi = bnds.get(str(d), [None, None])
+                bl.append(f"{{{kind[lo[0]] if lo else -1}, {lo[1] if lo else 0}, {kind[hi[0]] if hi else -1}, {hi[1] if hi else 0}}}")
+            L.append(f'    g.stages.back().parts.push_back(GenPart{{"{p["name"]}", {p["fp_ops"]}, {p["reads"]}, {p["writes"]}, {{{acc}}}, {{{outs}}}, {fns}, {{{", ".join(bl)}}}}});')
     L.append("}")
     L.append("} }  // namespace yb::gen")
     return "\n".join(L) + "\n"
@@ -378,7 +486,11 @@ def emit_oracle(ir: dict) -> str:
             L.append(f"static void yo_{ident}_{p['name']}(const yo_gen_args* A) {{")
             L.append(f"    typedef {T} T;")
             L.append("    YO_GEN_LOOP_BEGIN")
+            if p.get("cond"):
+                L.append(f"        if ({p['cond']['expr']}) {{   /* sub-domain: {p['cond']['text']} */")
             L.extend(_stmt_lines(p, len(ir["domain_dims"]), indent="        ", masks=_masks(ir, p)))
+            if p.get("cond"):
+                L.append("        }")
             L.append("    YO_GEN_LOOP_END")
             L.append("}")
     L.append(f"static const yo_gen_part yo_{ident}_parts[] = {{")
@@ -432,7 +544,8 @@ def main(argv=None):
     open(os.path.join(odir, f"{ident}.gen.h"), "w").write(emit_oracle(ir))
     slim = {k: v for k, v in ir.items() if k != "stages"}
     slim["stages"] = [{"name": s["name"], "parts": [{"name": p["name"], "fp_ops": p["fp_ops"], "reads": p["reads"], "writes": p["writes"],
-                                                       "accesses": p["accesses"], "outputs": p["outputs"]} for p in s["parts"]]} for s in ir["stages"]]
+                                                       "accesses": p["accesses"], "outputs": p["outputs"], "cond": p.get("cond")} for p in s["parts"]]}
+                      for s in ir["stages"]]
     json.dump(slim, open(os.path.join(gdir, f"{name}.json"), "w"), indent=1)
     mpath = os.path.join(gdir, "manifest.json")
     man = json.load(open(mpath)) if os.path.exists(mpath) else {}
