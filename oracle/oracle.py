@@ -103,7 +103,8 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
                 slots[v["name"]][t % a] = arrs[t]
         meta[v["name"]] = (v, has_step, a)
     last = {}
-    nn = list(n) + [1] * (3 - len(n))
+    nn = [1] * (3 - len(n)) + list(n)      # domain dims right-aligned into the (x,y,z) slots, like the CUDA engine
+    sh = 3 - len(dd)
     for t in range(steps):
         pi = 0
         for st in ir["stages"]:
@@ -119,9 +120,9 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
                     strides = {d: arr.strides[i] // arr.itemsize for i, d in enumerate(vd)}
                     off = sum(v["halo"][d][0] * strides[d] for d in vd)
                     A.ptr[k] = arr.ctypes.data + off * arr.itemsize
-                    A.sx[k] = strides.get(dd[0], 0) if len(dd) > 0 else 0
-                    A.sy[k] = strides.get(dd[1], 0) if len(dd) > 1 else 0
-                    A.sz[k] = strides.get(dd[2], 0) if len(dd) > 2 else 0
+                    A.sx[k] = strides.get(dd[0 - sh], 0) if sh <= 0 else 0
+                    A.sy[k] = strides.get(dd[1 - sh], 0) if sh <= 1 else 0
+                    A.sz[k] = strides.get(dd[2 - sh], 0)
                 rc = L.yo_gen_run_part(stencil.encode(), pi, ctypes.byref(A))
                 assert rc == 0, rc
                 for o in p["outputs"]:
@@ -173,6 +174,7 @@ def _parse_manifest(text: str) -> dict:
 
 
 def ref_info(tag: str, n) -> dict:
+    n = list(n) + [1] * (3 - len(n))     # the driver takes three sizes and uses the first ndd
     r = subprocess.run([os.path.join(REF_BIN, f"ref_driver.{tag}"), "info"] + [str(int(i)) for i in n],
                        check=True, capture_output=True, text=True)
     return _parse_manifest(r.stdout)
@@ -181,6 +183,7 @@ def ref_info(tag: str, n) -> dict:
 def ref_run(tag: str, n, steps: int, inputs: dict, threads: int | None = None) -> tuple[dict, dict]:
     """inputs: {(var, step): ndarray over the var's in-box}.  Returns ({(var, step): ndarray over
     the out-box}, manifest-after-run)."""
+    n = list(n) + [1] * (3 - len(n))
     info = ref_info(tag, n)
     dt = np.float32 if info["elem_bytes"] == 4 else np.float64
     env = dict(os.environ)

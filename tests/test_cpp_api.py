@@ -42,7 +42,8 @@ def _drive(stencil, n, steps, ins, opts=()):
     with tempfile.TemporaryDirectory() as d:
         for (name, t), a in ins.items():
             np.ascontiguousarray(a).tofile(os.path.join(d, f"{name}.t{t}.in"))
-        r = subprocess.run([exe, "run"] + [str(i) for i in n] + [str(steps), d], capture_output=True, text=True)
+        n3 = list(n) + [1] * (3 - len(n))
+        r = subprocess.run([exe, "run"] + [str(i) for i in n3] + [str(steps), d], capture_output=True, text=True)
         assert r.returncode == 0, r.stdout + r.stderr
         outs = {}
         for fn in os.listdir(d):
@@ -68,7 +69,7 @@ def test_same_driver_source_reproduces_reference_outputs(path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("stencil", ["iso3dfd", "awp_elastic", "ssg"])
+@pytest.mark.parametrize("stencil", ["test_3d", "iso3dfd", "awp_elastic", "ssg"])   # the reference runs it on test_3d
 def test_reference_kernel_api_test_passes_unmodified(stencil):
     r = subprocess.run([_bin(f"ref_kernel_api_test.{stencil}")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])

@@ -81,7 +81,8 @@ def synth_inputs(stencil, n, seed):
 
 @pytest.mark.parametrize("stencil,n,steps", [("awp_elastic", (37, 21, 150), 3), ("ssg", (19, 33, 131), 2), ("awp", (21, 19, 70), 2),
                                              ("tti", (18, 20, 66), 2), ("3axis", (30, 20, 100), 3), ("iso3dfd_sponge", (20, 24, 80), 2),
-                                             ("awp_elastic_abc", (19, 23, 40), 3), ("awp_abc", (16, 18, 37), 2)])
+                                             ("awp_elastic_abc", (19, 23, 40), 3), ("awp_abc", (16, 18, 37), 2),
+                                             ("test_2d", (37, 150), 3), ("test_1d", (300,), 4), ("test_boundary_3d", (20, 20, 70), 3)])
 def test_generated_vs_oracle_ragged(stencil, n, steps):
     ins, ir = synth_inputs(stencil, n, 31)
     out, _ = run_gpu(stencil, n, steps, ins, 0)

@@ -34,17 +34,23 @@ struct GenEngine : Engine {
         int n = 0;
         for (auto& p : gs.parts) {
             GenParams P{};
+            // The solution's domain dims are right-aligned into the kernel's (x,y,z) slots: slot k holds domain dim
+            // k - sh, so the unit-stride dim always lands in slot z (1-D/2-D solutions leave the outer slots empty).
+            const int sh = 3 - s.ndd;
             // shrink the launch box to the part's sub-domain (IF_DOMAIN), expressed over global indices
             // (the reference intersects with per-part bounding boxes, setup.cpp:1235-1498)
-            Box pb = box;
-            for (int d = 0; d < 3; d++) {
-                P.off[d] = d < s.ndd ? s.rank_offset[d] : 0;
-                P.gfirst[d] = 0;
-                P.glast[d] = d < s.ndd ? s.overall_size[d] - 1 : 0;
-                const auto& bd = p.bound[d];
-                auto resolve = [&](int kind, int off) { return (kind == 2 ? P.glast[d] : (kind == 1 ? P.gfirst[d] : 0)) + off; };
-                if (bd.lo_kind >= 0) pb.b[d] = std::max<int64_t>(pb.b[d], resolve(bd.lo_kind, bd.lo_off) - P.off[d]);
-                if (bd.hi_kind >= 0) pb.e[d] = std::min<int64_t>(pb.e[d], resolve(bd.hi_kind, bd.hi_off) - P.off[d] + 1);
+            Box pb;
+            for (int k = 0; k < 3; k++) {
+                const int d = k - sh;
+                pb.b[k] = d >= 0 ? box.b[d] : 0;
+                pb.e[k] = d >= 0 ? box.e[d] : 1;
+                P.off[k] = d >= 0 ? s.rank_offset[d] : 0;
+                P.gfirst[k] = 0;
+                P.glast[k] = d >= 0 ? s.overall_size[d] - 1 : 0;
+                const auto& bd = p.bound[k];
+                auto resolve = [&](int kind, int off) { return (kind == 2 ? P.glast[k] : (kind == 1 ? P.gfirst[k] : 0)) + off; };
+                if (bd.lo_kind >= 0) pb.b[k] = std::max<int64_t>(pb.b[k], resolve(bd.lo_kind, bd.lo_off) - P.off[k]);
+                if (bd.hi_kind >= 0) pb.e[k] = std::min<int64_t>(pb.e[k], resolve(bd.hi_kind, bd.hi_off) - P.off[k] + 1);
             }
             if (pb.empty()) continue;
             P.xb = int(pb.b[0]); P.xe = int(pb.e[0]);
@@ -55,9 +61,9 @@ struct GenEngine : Engine {
                 const Var& v = s.vars[p.acc[k].var];
                 const int slot = v.slot_of(t + p.acc[k].toff);
                 P.ptr[k] = v.slot_ptr(slot) + size_t(v.origin_offset()) * v.elem_bytes;
-                const Dim* d0 = v.domain_dim(0);
-                const Dim* d1 = v.domain_dim(1);
-                const Dim* d2 = v.domain_dim(2);
+                const Dim* d0 = sh <= 0 ? v.domain_dim(0 - sh) : nullptr;
+                const Dim* d1 = sh <= 1 ? v.domain_dim(1 - sh) : nullptr;
+                const Dim* d2 = v.domain_dim(2 - sh);
                 P.sx[k] = d0 ? d0->stride : 0;
                 P.sy[k] = d1 ? d1->stride : 0;
                 P.sz[k] = d2 ? d2->stride : 0;

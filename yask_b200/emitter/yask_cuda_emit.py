@@ -87,11 +87,14 @@ def parse_domain_cond(text: str, dd: list[str]) -> dict:
     Returns {"expr": neutral C text using G(i), GF(i), GL(i); "bounds": per-dim [lo, hi] affine bounds when the
     expression is a conjunction of simple comparisons (used to shrink the launch box), else None}."""
     t = text.strip()
+    if len(dd) > 3:
+        raise EmitError("more than 3 domain dims are not supported")
+    sh = 3 - len(dd)          # kernel slot of domain dim i is i + sh
     for i, d in enumerate(dd):
-        t = re.sub(rf"FIRST_INDEX\(\s*{d}\s*\)", f"GF({i})", t)
-        t = re.sub(rf"LAST_INDEX\(\s*{d}\s*\)", f"GL({i})", t)
+        t = re.sub(rf"FIRST_INDEX\(\s*{d}\s*\)", f"GF({i + sh})", t)
+        t = re.sub(rf"LAST_INDEX\(\s*{d}\s*\)", f"GL({i + sh})", t)
     for i, d in enumerate(dd):
-        t = re.sub(rf"(?<!\w){d}(?!\w)", f"G({i})", t)
+        t = re.sub(rf"(?<!\w){d}(?!\w)", f"G({i + sh})", t)
     left = re.sub(r"G[FL]?\(\d\)|\d+|[-+*/%()<>=!&| ]", "", t)
     if left:
         raise EmitError(f"unsupported token(s) '{left}' in sub-domain condition '{text}'")
@@ -261,6 +264,10 @@ def parse_generated(text: str, name: str) -> dict:
             if len(v["dims"]) - 1 > len(dd):
                 dd = v["dims"][1:]
     ir["step_dim"], ir["domain_dims"] = step_dim, dd
+    if len(dd) > 3:
+        raise EmitError(f"{len(dd)} domain dims: more than 3 are not supported")
+    if "thread_core_data.var_" in text:
+        raise EmitError("scratch vars are not supported by this emitter")
     for v in ir["vars"]:
         n = v["name"]
         m = re.search(rf"const idx_t {n}_alloc_t = (\d+);", text)
@@ -396,7 +403,7 @@ def _stmt_lines(part, ndd, indent="    ", masks=None):
     for s in part["stmts"]:
         def rd(i, s=s):
             a, offs = s["reads"][i]
-            offs = list(offs) + [0] * (3 - len(offs))
+            offs = [0] * (3 - len(offs)) + list(offs)     # domain dims are right-aligned into the kernel's (x,y,z) slots
             return f"RD({a}, {masks[a]}, {offs[0]}, {offs[1]}, {offs[2]})"
         out.append(f"{indent}const T e{s['dst']} = {gen_expr(s['tree'], rd, {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'})};")
     for o in part["outputs"]:
@@ -405,15 +412,17 @@ def _stmt_lines(part, ndd, indent="    ", masks=None):
 
 
 def _masks(ir, part):
-    """Per access: bit d set if the var spans solution domain dim d (x=1, y=2, z=4)."""
+    """Per access: bit k set if the var spans the domain dim held by kernel slot k (slots x=1, y=2, z=4; the
+    solution's domain dims are right-aligned into the slots, so the unit-stride dim is always slot z)."""
     dd = ir["domain_dims"]
+    sh = 3 - len(dd)
     vmap = {v["name"]: v for v in ir["vars"]}
     out = []
     for a in part["accesses"]:
         m = 0
         for i, d in enumerate(dd):
             if d in vmap[a["var"]]["dims"]:
-                m |= 1 << i
+                m |= 1 << (i + sh)
         out.append(m)
     return out
 
