@@ -66,8 +66,8 @@ def iso3dfd_run(p0: np.ndarray, p1: np.ndarray, v: np.ndarray, radius: int, step
 # Emitter-generated solutions (oracle/gen/*.gen.h): generic runner
 # ---------------------------------------------------------------------------------------
 class _GenArgs(ctypes.Structure):
-    _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 48),
-                ("sx", ctypes.c_int64 * 48), ("sy", ctypes.c_int64 * 48), ("sz", ctypes.c_int64 * 48),
+    _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 96),
+                ("sx", ctypes.c_int64 * 96), ("sy", ctypes.c_int64 * 96), ("sz", ctypes.c_int64 * 96),
                 ("off", ctypes.c_int64 * 3), ("gfirst", ctypes.c_int64 * 3), ("glast", ctypes.c_int64 * 3)]
 
 
@@ -118,7 +118,10 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
                     arr = slots[acc["var"]][(t + acc["toff"]) % a]
                     vd = [d for d in v["dims"] if d != ir["step_dim"]]
                     strides = {d: arr.strides[i] // arr.itemsize for i, d in enumerate(vd)}
-                    off = sum(v["halo"][d][0] * strides[d] for d in vd)
+                    off = sum(v["halo"][d][0] * strides[d] for d in vd if d in v["halo"])
+                    mdims = [d for d in vd if d not in v["halo"]]          # misc dims: constant index selects a sub-array
+                    for d, mi in zip(mdims, acc.get("misc", [])):
+                        off += (mi - v["misc_range"][d][0]) * strides[d]
                     A.ptr[k] = arr.ctypes.data + off * arr.itemsize
                     A.sx[k] = strides.get(dd[0 - sh], 0) if sh <= 0 else 0
                     A.sy[k] = strides.get(dd[1 - sh], 0) if sh <= 1 else 0

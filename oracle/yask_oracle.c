@@ -212,7 +212,7 @@ int yo_num_threads(void)
 /* order; this file supplies the loop nest and the statement vocabulary.  All arithmetic   */
 /* is in the element type with no contraction (== reference built with -ffp-contract=off). */
 /* ------------------------------------------------------------------------------------ */
-#define YO_GEN_MAX_ACC 48
+#define YO_GEN_MAX_ACC 96
 typedef struct {
     int64_t nx, ny, nz;                 /* rank-domain box [0,n) */
     void* ptr[YO_GEN_MAX_ACC];          /* element (0,0,0) of each access' step slot */

@@ -68,8 +68,9 @@ def synth_inputs(stencil, n, seed):
     for v in ir["vars"]:
         lo, hi = range_of(RANGES[stencil], v["name"])
         vd = [d for d in v["dims"] if d != ir["step_dim"]]
-        first = [-v["halo"][d][0] for d in vd]
-        shape = [n[ir["domain_dims"].index(d)] + sum(v["halo"][d]) for d in vd]
+        mr = v.get("misc_range", {})
+        first = [(-v["halo"][d][0] if d in v["halo"] else mr[d][0]) for d in vd]
+        shape = [(n[ir["domain_dims"].index(d)] + sum(v["halo"][d]) if d in v["halo"] else mr[d][1] - mr[d][0] + 1) for d in vd]
         has_step = bool(v["dims"]) and v["dims"][0] == ir["step_dim"]
         for t in range(v["alloc_t"] if has_step else 1):
             if shape:
@@ -82,7 +83,8 @@ def synth_inputs(stencil, n, seed):
 @pytest.mark.parametrize("stencil,n,steps", [("awp_elastic", (37, 21, 150), 3), ("ssg", (19, 33, 131), 2), ("awp", (21, 19, 70), 2),
                                              ("tti", (18, 20, 66), 2), ("3axis", (30, 20, 100), 3), ("iso3dfd_sponge", (20, 24, 80), 2),
                                              ("awp_elastic_abc", (19, 23, 40), 3), ("awp_abc", (16, 18, 37), 2),
-                                             ("test_2d", (37, 150), 3), ("test_1d", (300,), 4), ("test_boundary_3d", (20, 20, 70), 3)])
+                                             ("test_2d", (37, 150), 3), ("test_1d", (300,), 4), ("test_boundary_3d", (20, 20, 70), 3),
+                                             ("ssg2", (20, 18, 50), 2), ("fsg2", (14, 12, 40), 2)])
 def test_generated_vs_oracle_ragged(stencil, n, steps):
     ins, ir = synth_inputs(stencil, n, 31)
     out, _ = run_gpu(stencil, n, steps, ins, 0)
@@ -90,7 +92,8 @@ def test_generated_vs_oracle_ragged(stencil, n, steps):
     for name, (tl, got) in out.items():
         v = [x for x in ir["vars"] if x["name"] == name][0]
         arr = ref[name][1]
-        r = arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) for i, d in enumerate(ir["domain_dims"]))]
+        vd = [d for d in v["dims"] if d != ir["step_dim"]]
+        r = arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) if d in v["halo"] else slice(None) for i, d in enumerate(vd))]
         it = np.uint32 if got.dtype == np.float32 else np.uint64
         assert ref[name][0] == tl and np.array_equal(got.view(it), r.view(it)), name
 
@@ -99,7 +102,8 @@ def test_generated_vs_oracle_ragged(stencil, n, steps):
                                                    ("ssg", (32, 20, 40), (1, 2, 2), 2), ("ssg", (41, 16, 32), (3, 1, 1), 2),
                                                    ("awp", (32, 24, 48), (2, 2, 1), 2), ("tti", (36, 36, 48), (2, 2, 2), 2),
                                                    ("cube", (32, 32, 64), (2, 2, 2), 2),
-                                                   ("awp_elastic_abc", (24, 24, 40), (2, 1, 2), 3), ("awp_abc", (24, 20, 36), (1, 2, 3), 2)])
+                                                   ("awp_elastic_abc", (24, 24, 40), (2, 1, 2), 3), ("awp_abc", (24, 20, 36), (1, 2, 3), 2),
+                                                   ("ssg2", (32, 24, 40), (2, 2, 1), 2), ("test_2d", (64, 96), (2, 2), 3)])
 def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     """Two-stage solutions exchange halos after each stage; static vars (rho, mu, ...) are exchanged once."""
     ir = O.gen_ir(stencil)
@@ -112,6 +116,7 @@ def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
                 v.fill_hash(t, 5, var_salt(vi.name.decode(), t), lo, hi)
 
     def collect(solns):
+        """Assemble every output var over the GLOBAL domain from the ranks' pieces (any mix of domain/misc dims)."""
         out = {}
         for s in solns:
             for v in s.get_vars():
@@ -119,8 +124,19 @@ def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
                 if not vi.is_output:
                     continue
                 f, l = v.domain_box(vi.last_valid_step)
-                a = out.setdefault(vi.name.decode(), np.zeros(n, v.dtype))
-                a[f[1]:l[1] + 1, f[2]:l[2] + 1, f[3]:l[3] + 1] = v.get_elements_in_slice(f, l)
+                shape, sl = [], []
+                for k in range(vi.num_dims):
+                    d = vi.dims[k]
+                    if d.kind == 0:
+                        continue
+                    if d.kind == 1:
+                        shape.append(n[d.domain_index])
+                        sl.append(slice(f[k], l[k] + 1))
+                    else:
+                        shape.append(d.domain_size)
+                        sl.append(slice(0, d.domain_size))
+                a = out.setdefault(vi.name.decode(), np.zeros(shape, v.dtype))
+                a[tuple(sl)] = v.get_elements_in_slice(f, l).reshape([x.stop - x.start for x in sl])
         return out
 
     s0 = capi.Solution(stencil, elem_bytes=0)

@@ -43,7 +43,8 @@ from tests.helpers import field_ulps  # noqa: E402
 
 def _domain(ir, name, arr):
     v = [x for x in ir["vars"] if x["name"] == name][0]
-    return arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) for i, d in enumerate(ir["domain_dims"]))]
+    vd = [d for d in v["dims"] if d != ir["step_dim"]]
+    return arr[tuple(slice(v["halo"][d][0], arr.shape[i] - v["halo"][d][1]) if d in v["halo"] else slice(None) for i, d in enumerate(vd))]
 
 
 from tests.helpers import generated_golden_cases  # noqa: E402

@@ -97,7 +97,7 @@ static void compute_var_geometry(Solution& s, Var& v) {
         if (v.spec.fixed_size) { d.domain = v.spec.fixed_sizes[i]; d.rank_offset = 0; }
         int64_t pl = std::max({d.spec.halo_l, d.min_pad_l, s.min_pad[dd], s.spec.uniform_pad[dd]});
         int64_t pr = std::max({d.spec.halo_r, d.min_pad_r, s.min_pad[dd], s.spec.uniform_pad[dd]});
-        if (i == nd - 1 && i == last_domain) {
+        if (i == last_domain) {
             // unit-stride dim: domain origin on a 128-B boundary, pitch a multiple of 128 B
             pl = (pl + align_elems - 1) / align_elems * align_elems;
             int64_t a = pl + d.domain + pr;
@@ -107,13 +107,17 @@ static void compute_var_geometry(Solution& s, Var& v) {
         d.pad_l = pl; d.pad_r = pr;
         d.alloc = pl + d.domain + pr;
     }
+    // Storage order: domain dims innermost (declared order, last one unit-stride), misc dims outside them -- a var
+    // with misc dims is an array of identically shaped domain boxes (the reference's default "outer misc" layout).
     int64_t stride = 1;
-    for (int i = nd - 1; i >= 0; i--) {
-        Dim& d = v.dims[i];
-        if (d.spec.kind == DIM_STEP) continue;
-        d.stride = stride;
-        stride *= d.alloc;
-    }
+    for (int pass = 0; pass < 2; pass++)
+        for (int i = nd - 1; i >= 0; i--) {
+            Dim& d = v.dims[i];
+            if (d.spec.kind == DIM_STEP) continue;
+            if ((pass == 0) != (d.spec.kind == DIM_DOMAIN)) continue;
+            d.stride = stride;
+            stride *= d.alloc;
+        }
     v.slot_elems = std::max<int64_t>(stride, 1);
     // keep every slot 256-B aligned
     int64_t a256 = 256 / v.elem_bytes;
@@ -135,7 +139,7 @@ struct Slice {
     int64_t t0 = 0, t1 = 0;
     BoxCopy bc{};
     int64_t elems_per_step = 1;
-    int64_t g0[3] = {0, 0, 0};
+    int64_t g0[4] = {0, 0, 0, 0};   // global index of the box origin: last three dims, then the leading 4th dim
 };
 
 static int resolve_slice(const Solution& s, const Var& v, const int64_t* first, const int64_t* last, bool check_steps, Slice& sl) {
@@ -175,6 +179,7 @@ static int resolve_slice(const Solution& s, const Var& v, const int64_t* first, 
     for (int i = 0; i < nd; i++) {
         if (v.dims[i].spec.kind == DIM_STEP) continue;
         if (k <= 3) sl.g0[3 - k + kk] = first[i];
+        else if (k == 4) { if (kk == 0) sl.g0[3] = first[i]; else sl.g0[kk - 1] = first[i]; }
         kk++;
     }
     (void)s;

@@ -78,7 +78,7 @@ __device__ __forceinline__ unsigned long long index_key(long long i0, long long 
     return (((unsigned long long)i0 + OFF) & M) << 40 | (((unsigned long long)i1 + OFF) & M) << 20 | (((unsigned long long)i2 + OFF) & M);
 }
 
-struct G0 { long long g[3]; };
+struct G0 { long long g[3]; long long lead; };   // lead: global index of the 4th (outermost) dim, if any
 
 // global index triple of box coordinate `coord` (box has nd <= 3 dims, left-padded with index 0)
 __device__ __forceinline__ void global_triple(const BoxDev& b, const G0& g0, const long long* coord, long long* g) {
@@ -97,7 +97,12 @@ __global__ void hash_fill_kernel(T* __restrict__ var, BoxDev b, G0 g0, unsigned 
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < b.total; i += (long long)gridDim.x * blockDim.x) {
         long long o = box_offset(b, i, coord);
         global_triple(b, g0, coord, g);
-        unsigned long long key = index_key(g[0], g[1], g[2]) ^ (seedsalt * 0xD6E8FEB86659FD93ull);
+        unsigned long long ss = seedsalt;
+        if (b.nd == 4) {   // 4-D var: the leading index perturbs the salt (yask_b200/synth.py::hash_field)
+            const unsigned long long salt = (seedsalt + (unsigned long long)(g0.lead + coord[0]) * 0x9E3779B1ull) & 0xFFFFFFFFull;
+            ss = (seedsalt & 0xFFFFFFFF00000000ull) | salt;
+        }
+        unsigned long long key = index_key(g[0], g[1], g[2]) ^ (ss * 0xD6E8FEB86659FD93ull);
         unsigned long long h = splitmix64(key);
         double u = __dmul_rn((double)(h >> 40), 1.0 / 16777216.0);
         double val = __dadd_rn(lo, __dmul_rn(hi - lo, u));
@@ -179,9 +184,10 @@ int launch_hash_fill(void* var_slot, const BoxCopy& bc, const int64_t* g0, int e
                      double lo, double hi, cudaStream_t st) {
     BoxDev b = right_align(bc);
     if (b.total == 0) return 0;
-    if (bc.nd > 3) return set_error(YB_EUNSUPPORTED, "hash fill supports at most 3 non-step dims");
+    if (bc.nd > 4) return set_error(YB_EUNSUPPORTED, "hash fill supports at most 4 non-step dims");
     G0 g;
     for (int i = 0; i < 3; i++) g.g[i] = g0[i];
+    g.lead = g0[3];
     unsigned long long ss = ((unsigned long long)seed << 32) | (unsigned long long)salt;
     if (elem_bytes == 4) hash_fill_kernel<float><<<grid_for(b.total), 256, 0, st>>>((float*)var_slot, b, g, ss, lo, hi);
     else hash_fill_kernel<double><<<grid_for(b.total), 256, 0, st>>>((double*)var_slot, b, g, ss, lo, hi);
@@ -197,6 +203,7 @@ int launch_checksum(const void* var_slot, const BoxCopy& bc, const int64_t* g0, 
     if (b.total == 0) return 0;
     G0 g;
     for (int i = 0; i < 3; i++) g.g[i] = g0[i];
+    g.lead = 0;
     if (elem_bytes == 4) checksum_kernel<float><<<grid_for(b.total), 256, 0, st>>>((const float*)var_slot, b, g, dev_out);
     else checksum_kernel<double><<<grid_for(b.total), 256, 0, st>>>((const double*)var_slot, b, g, dev_out);
     YB_CUDA(cudaGetLastError());

@@ -5,7 +5,7 @@
 
 #include "yb_core.h"
 #include "yb_gen.cuh"
-// generated solutions
+// generated solutions: declarations + table (each solution is compiled in its own translation unit)
 #include "gen/gen_all.inc"
 
 namespace yb {
@@ -60,7 +60,11 @@ struct GenEngine : Engine {
             for (size_t k = 0; k < p.acc.size(); k++) {
                 const Var& v = s.vars[p.acc[k].var];
                 const int slot = v.slot_of(t + p.acc[k].toff);
-                P.ptr[k] = v.slot_ptr(slot) + size_t(v.origin_offset()) * v.elem_bytes;
+                int64_t moff = 0;      // constant misc-dim indices select a sub-array
+                int mi = 0;
+                for (auto& d : v.dims)
+                    if (d.spec.kind == DIM_MISC) moff += (p.acc[k].misc[mi++] - d.spec.misc_first) * d.stride;
+                P.ptr[k] = v.slot_ptr(slot) + size_t(v.origin_offset() + moff) * v.elem_bytes;
                 const Dim* d0 = sh <= 0 ? v.domain_dim(0 - sh) : nullptr;
                 const Dim* d1 = sh <= 1 ? v.domain_dim(1 - sh) : nullptr;
                 const Dim* d2 = v.domain_dim(2 - sh);
@@ -115,9 +119,14 @@ int gen_registry_create(const std::string& name, int elem_bytes, StencilSpec& sp
                 d.name = dn;
                 if (g.step_dim == dn) { d.kind = DIM_STEP; }
                 else {
-                    d.kind = DIM_DOMAIN;
+                    d.kind = DIM_MISC;
                     for (size_t k = 0; k < g.domain_dims.size(); k++)
-                        if (g.domain_dims[k] == dn) { d.domain_index = int(k); d.halo_l = gv.halo_l[k]; d.halo_r = gv.halo_r[k]; }
+                        if (g.domain_dims[k] == dn) { d.kind = DIM_DOMAIN; d.domain_index = int(k); d.halo_l = gv.halo_l[k]; d.halo_r = gv.halo_r[k]; }
+                    if (d.kind == DIM_MISC) {
+                        const size_t di = v.dims.size();
+                        d.misc_first = gv.misc_first[di];
+                        d.misc_size = std::max(1, gv.misc_size[di]);
+                    }
                 }
                 v.dims.push_back(d);
             }

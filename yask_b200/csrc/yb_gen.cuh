@@ -10,7 +10,7 @@
 
 namespace yb { namespace gen {
 
-constexpr int GEN_MAX_ACC = 48;   // distinct (var, step-offset) pairs one part may touch
+constexpr int GEN_MAX_ACC = 96;   // distinct (var, step-offset) pairs one part may touch
 // CTA = GEN_BZ x GEN_BY x GEN_BX points (z fastest): neighbouring rows/planes of a point are computed by
 // the same CTA, so their reads of shared neighbours hit L1 instead of going back to L2.
 #ifndef YB_GEN_BZ
@@ -46,8 +46,9 @@ struct GenVar {
     bool is_output;
     int l1_norm;
     std::vector<int> halo_l, halo_r; // per solution domain dim
+    std::vector<int> misc_first, misc_size;   // per declared dim: index range of misc dims (0 size otherwise)
 };
-struct GenAccess { int var, toff; };
+struct GenAccess { int var, toff; int misc[2]; };   // misc: constant indices of the var's misc dims, in declared order
 struct GenPart {
     const char* name;
     int fp_ops, reads, writes;

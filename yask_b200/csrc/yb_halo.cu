@@ -195,51 +195,67 @@ static bool var_talks_to(const Var& v, const int dir[3]) {
 static int push_var_slot(Solution& s, const Neighbor& nb, int vi, int slot, cudaStream_t st) {
     const Var& v = s.vars[vi];
     const BlobVar& pg = nb.var_geom[vi];
-    CopyBox b{};
-    int k3 = 0;
-    long long n3[3] = {1, 1, 1}, ss[3] = {0, 0, 0}, ds[3] = {0, 0, 0};
+    int k4 = 0;
+    long long n4[4] = {1, 1, 1, 1}, ss[4] = {0, 0, 0, 0}, ds[4] = {0, 0, 0, 0};
     long long so = 0, dof = 0;
     for (auto& d : v.dims) {
         if (d.spec.kind == DIM_STEP) continue;
-        if (k3 >= 3) return set_error(YB_EUNSUPPORTED, "halo exchange of vars with more than 3 non-step dims");
+        if (k4 >= 4) return set_error(YB_EUNSUPPORTED, "halo exchange of vars with more than 4 non-step dims");
         long long first_src, count, first_dst;  // in rank-local domain coordinates of sender / receiver
         if (d.spec.kind == DIM_MISC) { first_src = 0; count = d.domain; first_dst = 0; }
         else {
             const int dk = nb.dir[d.spec.domain_index];
-            if (dk < 0) { count = d.spec.halo_r; first_src = 0; first_dst = pg.domain[k3]; }
+            if (dk < 0) { count = d.spec.halo_r; first_src = 0; first_dst = pg.domain[k4]; }
             else if (dk > 0) { count = d.spec.halo_l; first_src = d.domain - count; first_dst = -count; }
             else { count = d.domain; first_src = 0; first_dst = 0; }
             if (count > d.domain) return set_error(YB_EUNSUPPORTED, "rank domain smaller than halo in dim '%s'", d.spec.name.c_str());
-            if (dk == 0 && pg.domain[k3] != d.domain) return set_error(YB_EINVAL, "neighbour has a different size in an unsplit dim");
+            if (dk == 0 && pg.domain[k4] != d.domain) return set_error(YB_EINVAL, "neighbour has a different size in an unsplit dim");
         }
         const long long pad = d.spec.kind == DIM_MISC ? 0 : d.pad_l;
-        n3[k3] = count; ss[k3] = d.stride; ds[k3] = pg.stride[k3];
+        n4[k4] = count; ss[k4] = d.stride; ds[k4] = pg.stride[k4];
         so += (first_src + pad) * d.stride;
-        dof += (first_dst + pg.pad_l[k3]) * pg.stride[k3];
-        k3++;
+        dof += (first_dst + pg.pad_l[k4]) * pg.stride[k4];
+        k4++;
     }
-    for (int i = 0; i < 3; i++) { b.n[i] = 1; b.src_stride[i] = b.dst_stride[i] = 0; }
-    for (int i = 0; i < k3; i++) { b.n[3 - k3 + i] = n3[i]; b.src_stride[3 - k3 + i] = ss[i]; b.dst_stride[3 - k3 + i] = ds[i]; }
-    b.src_off = so; b.dst_off = dof;
-    const long long total = b.n[0] * b.n[1] * b.n[2];
-    if (total == 0) return 0;
-    const char* src = v.slot_ptr(slot);
-    char* dst = nb.var_base[vi] + size_t(slot) * pg.slot_elems * v.elem_bytes;
-    int vec = 1;
-    const int vw = 16 / v.elem_bytes;
-    bool al = (b.n[2] % vw == 0) && (so % vw == 0) && (dof % vw == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-              ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-    for (int i = 0; i < 2; i++) al = al && (b.src_stride[i] % vw == 0) && (b.dst_stride[i] % vw == 0);
-    if (al) vec = vw;
-    const long long work = total / vec;
-    const int grid = int(std::min<long long>((work + 255) / 256, 148 * 8));
-    if (v.elem_bytes == 4) halo_push_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, b, vec);
-    else halo_push_kernel<double><<<grid, 256, 0, st>>>((const double*)src, (double*)dst, b, vec);
-    YB_CUDA(cudaGetLastError());
-    return 1;
+    // Sort the dims by descending source stride so the innermost (unit-stride) dim is last; a 4th (outermost) dim,
+    // i.e. a misc dim, is looped over on the host.
+    int order[4] = {0, 1, 2, 3};
+    std::sort(order, order + k4, [&](int a, int b) { return ss[a] > ss[b]; });
+    const int outer = k4 > 3 ? order[0] : -1;
+    const long long n_outer = outer >= 0 ? n4[outer] : 1;
+    int launched = 0;
+    for (long long io = 0; io < n_outer; io++) {
+        CopyBox b{};
+        for (int i = 0; i < 3; i++) { b.n[i] = 1; b.src_stride[i] = b.dst_stride[i] = 0; }
+        const int first = outer >= 0 ? 1 : 0;
+        const int nin = k4 - first;
+        for (int i = 0; i < nin; i++) {
+            const int d = order[first + i];
+            b.n[3 - nin + i] = n4[d]; b.src_stride[3 - nin + i] = ss[d]; b.dst_stride[3 - nin + i] = ds[d];
+        }
+        b.src_off = so + (outer >= 0 ? io * ss[outer] : 0);
+        b.dst_off = dof + (outer >= 0 ? io * ds[outer] : 0);
+        const long long total = b.n[0] * b.n[1] * b.n[2];
+        if (total == 0) return 0;
+        if (b.src_stride[2] > 1 || b.dst_stride[2] > 1) return set_error(YB_EUNSUPPORTED, "halo push needs a unit-stride innermost dim");
+        const char* src = v.slot_ptr(slot);
+        char* dst = nb.var_base[vi] + size_t(slot) * pg.slot_elems * v.elem_bytes;
+        int vec = 1;
+        const int vw = 16 / v.elem_bytes;
+        bool al = (b.n[2] % vw == 0) && (b.src_off % vw == 0) && (b.dst_off % vw == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && b.src_stride[2] == 1 && b.dst_stride[2] == 1;
+        for (int i = 0; i < 2; i++) al = al && (b.src_stride[i] % vw == 0) && (b.dst_stride[i] % vw == 0);
+        if (al) vec = vw;
+        const long long work = total / vec;
+        const int grid = int(std::min<long long>((work + 255) / 256, 148 * 8));
+        if (v.elem_bytes == 4) halo_push_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, b, vec);
+        else halo_push_kernel<double><<<grid, 256, 0, st>>>((const double*)src, (double*)dst, b, vec);
+        YB_CUDA(cudaGetLastError());
+        launched++;
+    }
+    return launched;
 }
 
-// Push every dirty (var, slot) to every neighbour, signal, then wait for the neighbours' signals.
 // skip_var/skip_x: the stage kernel already stored this var's x-face halos into the peers (fused path).
 static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var) {
     HaloState* h = s.halo;

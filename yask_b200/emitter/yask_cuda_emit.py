@@ -256,13 +256,14 @@ def parse_generated(text: str, name: str) -> dict:
         ir["vars"].append({"name": vname, "dims": dims, "is_output": m.group(3).startswith("updated")})
     if not ir["vars"]:
         raise EmitError("no vars found in the generated file")
+    # domain dims: the front-end's own list ("#define DOMAIN_DIM_IDX_<d> <i>"); step dim: the first dim of an updated var
+    dd = [d for d, _ in sorted(re.findall(r"#define DOMAIN_DIM_IDX_(\w+) (\d+)", text), key=lambda kv: int(kv[1]))]
     step_dim = None
-    dd: list[str] = []
     for v in ir["vars"]:
-        if v["is_output"] and v["dims"]:
+        if v["is_output"] and v["dims"] and v["dims"][0] not in dd:
             step_dim = v["dims"][0]
-            if len(v["dims"]) - 1 > len(dd):
-                dd = v["dims"][1:]
+    if not dd:
+        raise EmitError("no domain dims found in the generated file")
     ir["step_dim"], ir["domain_dims"] = step_dim, dd
     if len(dd) > 3:
         raise EmitError(f"{len(dd)} domain dims: more than 3 are not supported")
@@ -279,7 +280,7 @@ def parse_generated(text: str, name: str) -> dict:
             if d == step_dim:
                 continue
             if d not in dd:
-                raise EmitError(f"var '{n}' uses misc dim '{d}': not supported by this emitter")
+                continue      # misc dim: its index range is derived from the accesses below (as the reference does)
             ml = re.search(rf"const idx_t {n}_left_halo_{d} = (\d+);", text)
             mr = re.search(rf"const idx_t {n}_right_halo_{d} = (\d+);", text)
             v["halo"][d] = [int(ml.group(1)) if ml else 0, int(mr.group(1)) if mr else 0]
@@ -324,20 +325,30 @@ def parse_generated(text: str, name: str) -> dict:
                 raise EmitError(f"index count mismatch for var '{var}'")
             toff = 0
             offs = {}
+            misc = []
             for d, it in zip(v["dims"], idxs):
                 dim, off = parse_index(it, v["dims"])
+                if d != step_dim and d not in dd:      # misc dim: constant index
+                    if dim is not None:
+                        raise EmitError(f"var '{var}': misc dim '{d}' indexed by an expression ('{it}')")
+                    misc.append(off)
+                    rng = v.setdefault("misc_range", {}).setdefault(d, [off, off])
+                    rng[0], rng[1] = min(rng[0], off), max(rng[1], off)
+                    continue
                 if dim is None:
-                    raise EmitError("constant (misc) index not supported")
+                    raise EmitError(f"var '{var}': constant index '{it}' in non-misc dim '{d}'")
                 if dim != d:
                     raise EmitError(f"var '{var}': index '{it}' does not follow declared dim '{d}'")
                 if d == step_dim:
                     toff = off
                 else:
                     offs[d] = off
-            key = (var, toff)
+            if len(misc) > 2:
+                raise EmitError("more than 2 misc dims per var are not supported")
+            key = (var, toff, tuple(misc))
             if key not in acc_index:
                 acc_index[key] = len(part["accesses"])
-                part["accesses"].append({"var": var, "toff": toff})
+                part["accesses"].append({"var": var, "toff": toff, "misc": misc})
             return acc_index[key], [offs.get(d, 0) for d in dd]
 
         for line in body.splitlines():
@@ -459,12 +470,15 @@ def emit_cuda(ir: dict) -> str:
         dims = ", ".join(f'"{d}"' for d in v["dims"])
         hl = ", ".join(str(v["halo"].get(d, [0, 0])[0]) for d in ir["domain_dims"])
         hr = ", ".join(str(v["halo"].get(d, [0, 0])[1]) for d in ir["domain_dims"])
-        L.append(f'    g.vars.push_back(GenVar{{"{v["name"]}", {{{dims}}}, {v["alloc_t"]}, {str(v["is_output"]).lower()}, {v["l1_norm"]}, {{{hl}}}, {{{hr}}}}});')
+        mr = v.get("misc_range", {})
+        mf = ", ".join(str(mr[d][0]) if d in mr else "0" for d in v["dims"])
+        ms = ", ".join(str(mr[d][1] - mr[d][0] + 1) if d in mr else "0" for d in v["dims"])
+        L.append(f'    g.vars.push_back(GenVar{{"{v["name"]}", {{{dims}}}, {v["alloc_t"]}, {str(v["is_output"]).lower()}, {v["l1_norm"]}, {{{hl}}}, {{{hr}}}, {{{mf}}}, {{{ms}}}}});')
     vidx = {v["name"]: i for i, v in enumerate(ir["vars"])}
     for st in ir["stages"]:
         L.append(f'    g.stages.push_back(GenStage{{"{st["name"]}", {{}}}});')
         for p in st["parts"]:
-            acc = ", ".join(f"{{{vidx[a['var']]}, {a['toff']}}}" for a in p["accesses"])
+            acc = ", ".join("{%d, %d, {%s}}" % (vidx[a["var"]], a["toff"], ", ".join(str(m) for m in (a.get("misc", []) + [0, 0])[:2])) for a in p["accesses"])
             outs = ", ".join(str(o["access"]) for o in p["outputs"])
             k = f"{ident}_{p['name']}_kernel"
             fns = f"{{{{GEN_FN({k}, float, 0), GEN_FN({k}, float, 1)}}, {{GEN_FN({k}, double, 0), GEN_FN({k}, double, 1)}}}}"
@@ -516,12 +530,18 @@ def write_registry():
     odir = os.path.join(ROOT, "oracle", "gen")
     man = json.load(open(os.path.join(gdir, "manifest.json")))
     names = sorted(man)
-    cu = ["// GENERATED by yask_b200/emitter/yask_cuda_emit.py: every emitted solution (see manifest.json)."]
-    cu += [f'#include "{c_ident(n)}.gen.cuh"' for n in names]
+    cu = ["// GENERATED by yask_b200/emitter/yask_cuda_emit.py: every emitted solution (see manifest.json).",
+          "// Each solution is its own translation unit (gen/<name>.gen.cu) so that they compile in parallel."]
+    cu += [f"namespace yb {{ namespace gen {{ void {c_ident(n)}_register(GenStencil& g); }} }}" for n in names]
     cu.append("#define YB_GEN_TABLE \\")
-    cu += [f'    {{"{n}", yb::gen::{c_ident(n)}_describe}}, \\' for n in names]
+    cu += [f'    {{"{n}", yb::gen::{c_ident(n)}_register}}, \\' for n in names]
     cu.append("")
     open(os.path.join(gdir, "gen_all.inc"), "w").write("\n".join(cu) + "\n")
+    for n in names:
+        i = c_ident(n)
+        open(os.path.join(gdir, f"{i}.gen.cu"), "w").write(
+            f"// GENERATED: translation unit of solution '{n}'.\n#include \"{i}.gen.cuh\"\n"
+            f"namespace yb {{ namespace gen {{ void {i}_register(GenStencil& g) {{ {i}_describe(g); }} }} }}\n")
     oc = ["/* GENERATED by yask_b200/emitter/yask_cuda_emit.py -- TEST INFRASTRUCTURE ONLY. */"]
     oc += [f'#include "{c_ident(n)}.gen.h"' for n in names]
     oc.append("#define YO_GEN_TABLE \\")
@@ -536,6 +556,7 @@ def main(argv=None):
     ap.add_argument("--elem-bytes", type=int, default=4)
     ap.add_argument("--radius", type=int, default=0)
     ap.add_argument("--name", default=None, help="registry name of the generated solution (default: stencil)")
+    ap.add_argument("--no-registry", action="store_true", help="do not rewrite gen_all.inc (batch use)")
     ap.add_argument("--from-file", default=None, help="parse this already generated file instead of running the compiler")
     a = ap.parse_args(argv)
     name = a.name or a.stencil
@@ -560,7 +581,8 @@ def main(argv=None):
     man = json.load(open(mpath)) if os.path.exists(mpath) else {}
     man[name] = {"stencil": a.stencil, "radius": a.radius, "elem_bytes": ir["elem_bytes"]}
     json.dump(man, open(mpath, "w"), indent=1, sort_keys=True)
-    write_registry()
+    if not a.no_registry:
+        write_registry()
     nst = sum(len(p["stmts"]) for s in ir["stages"] for p in s["parts"])
     print(f"emitted {name}: {len(ir['vars'])} vars, {len(ir['stages'])} stage(s), {nst} statements, elem_bytes {ir['elem_bytes']}")
 

@@ -47,6 +47,9 @@ def hash_field(seed: int, salt: int, first, shape, lo: float, hi: float, dtype=n
     first = list(first)
     shape = list(shape)
     nd = len(shape)
+    if nd == 4:   # 4-D var (e.g. x,y,z + a misc dim): the leading index perturbs the salt, the rest is a 3-D field
+        return np.stack([hash_field(seed, (salt + (first[0] + m) * 0x9E3779B1) & 0xFFFFFFFF, first[1:], shape[1:], lo, hi, dtype)
+                         for m in range(shape[0])])
     assert nd <= 3 and len(first) == nd
     while len(shape) < 3:  # left-pad missing dims with index 0
         shape.insert(0, 1)
