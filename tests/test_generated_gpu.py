@@ -147,7 +147,7 @@ def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     s0.run_solution(0, steps - 1)
     ref = collect([s0])
     s0.close()
-    world = grid[0] * grid[1] * grid[2]
+    world = int(np.prod(grid))
     solns = []
     for r in range(world):
         s = capi.Solution(stencil, elem_bytes=0)
