@@ -52,7 +52,6 @@ def _drive(stencil, n, steps, ins, opts=()):
         return outs
 
 
-@pytest.mark.gpu
 def _driver_cases():
     """Fixtures of the solutions that have a C++ API library (Makefile YK_STENCILS); iso3dfd: default build only."""
     out = []
@@ -63,6 +62,7 @@ def _driver_cases():
     return out
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("path", _driver_cases())
 def test_same_driver_source_reproduces_reference_outputs(path):
     meta, arrays = load_golden(path)
