@@ -227,9 +227,8 @@ typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } y
         for (int64_t y = 0; y < A->ny; y++)                                    \
             for (int64_t z = 0; z < A->nz; z++) {
 #define YO_GEN_LOOP_END }
-#define RD(a, m, ro, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
-#define WR(k, a, m, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
-#define ST(k, a, m)   /* stores happen in WR on the CPU */
+#define RD(a, m, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
+#define WR(a, m, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
 #define C(v) ((T)(v))
 #define G(i) ((i) == 0 ? x + A->off[0] : ((i) == 1 ? y + A->off[1] : z + A->off[2]))
 #define GF(i) A->gfirst[i]

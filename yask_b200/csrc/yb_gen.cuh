@@ -94,37 +94,26 @@ template <typename T> struct GenOp<T, 1> {
     static __device__ __forceinline__ T div(T a, T b) { return a / b; }
 };
 
-constexpr int GEN_MAX_OUT = 16;   // vars one part may write
-// Kernel skeleton.  The GEN_NP bodies of a thread are fully independent: results are parked in registers (wr_) and
-// stored only after ALL bodies have run, and reads of vars the part does not write go through the read-only path
-// (ld.global.nc), so the compiler is free to hoist every load of every body -- the kernels are load-latency bound.
 #define GEN_KERNEL_BEGIN                                                                         \
-    constexpr int GEN_NP = gen_np(int(sizeof(T)));                                               \
     const int z = P.zb + blockIdx.x * GEN_BZ + (threadIdx.x % GEN_BZ);                           \
+    constexpr int GEN_NP = gen_np(int(sizeof(T)));                                               \
     const int y0_ = P.yb + blockIdx.y * (GEN_BY * GEN_NP) + (threadIdx.x / GEN_BZ) % GEN_BY;     \
     const int x = P.xb + blockIdx.z * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);                  \
     if (z >= P.ze || x >= P.xe) return;                                                          \
-    T wr_[GEN_NP][GEN_MAX_OUT];                                                                  \
-    unsigned wmask_ = 0;                                                                         \
     _Pragma("unroll") for (int gp_ = 0; gp_ < GEN_NP; gp_++) {                                   \
         const int y = y0_ + gp_ * GEN_BY;                                                        \
         if (y < P.ye) {
-#define GEN_KERNEL_STORES                                                                        \
-        } }                                                                                      \
-    _Pragma("unroll") for (int gp_ = 0; gp_ < GEN_NP; gp_++) {                                   \
-        const int y = y0_ + gp_ * GEN_BY;                                                        \
-        if ((wmask_ >> gp_) & 1u) {
 #define GEN_KERNEL_END } }
-// m = dim mask of the var (x=1, y=2, z=4).  Full-rank vars (m==7) use the shared geometry: one position per
-// thread, 32-bit neighbour offsets that the compiler shares across vars; lower-rank vars (1-D sponge arrays,
-// scalars) take the general strided path.  ro = 1: the part never writes this var.
+// m = dim mask of the var (x=1, y=2, z=4).  Full-rank vars (m==7) use the shared geometry: one 64-bit position
+// per thread, 32-bit neighbour offsets that the compiler shares across vars; lower-rank vars (1-D sponge
+// arrays, scalars) take the general strided path.
 #define GEN_POS (x * P.SX + y * P.SY + z)   /* 32-bit: the engine refuses slots of 2^31 elements or more */
-#define GEN_ADDR(a, m, dx, dy, dz)                                                                                       \
-    ((m) == 7 ? static_cast<const T*>(P.ptr[a]) + (GEN_POS + ((dx) * P.SX + (dy) * P.SY + (dz)))                          \
-              : static_cast<const T*>(P.ptr[a]) + ((x + (dx)) * P.sx[a] + (y + (dy)) * P.sy[a] + (z + (dz)) * P.sz[a]))
-#define RD(a, m, ro, dx, dy, dz) ((ro) ? __ldg(GEN_ADDR(a, m, dx, dy, dz)) : *GEN_ADDR(a, m, dx, dy, dz))
-#define WR(k, a, m, v) do { wr_[gp_][k] = (v); wmask_ |= 1u << gp_; } while (0)
-#define ST(k, a, m) *const_cast<T*>(GEN_ADDR(a, m, 0, 0, 0)) = wr_[gp_][k]
+#define RD(a, m, dx, dy, dz)                                                                                             \
+    ((m) == 7 ? static_cast<const T*>(P.ptr[a])[GEN_POS + ((dx) * P.SX + (dy) * P.SY + (dz))]                              \
+              : static_cast<const T*>(P.ptr[a])[(x + (dx)) * P.sx[a] + (y + (dy)) * P.sy[a] + (z + (dz)) * P.sz[a]])
+#define WR(a, m, v)                                                                                                      \
+    do { if ((m) == 7) static_cast<T*>(P.ptr[a])[GEN_POS] = (v);                                                         \
+         else static_cast<T*>(P.ptr[a])[x * P.sx[a] + y * P.sy[a] + z * P.sz[a]] = (v); } while (0)
 #define C(v) static_cast<T>(v)
 #define G(i) ((i) == 0 ? x + P.off[0] : ((i) == 1 ? y + P.off[1] : z + P.off[2]))
 #define GF(i) P.gfirst[i]

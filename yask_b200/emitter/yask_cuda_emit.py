@@ -411,21 +411,15 @@ def gen_expr(tree, rd, ops) -> str:
 
 def _stmt_lines(part, ndd, indent="    ", masks=None):
     out = []
-    written = {part["accesses"][o["access"]]["var"] for o in part["outputs"]}
     for s in part["stmts"]:
         def rd(i, s=s):
             a, offs = s["reads"][i]
             offs = [0] * (3 - len(offs)) + list(offs)     # domain dims are right-aligned into the kernel's (x,y,z) slots
-            ro = 0 if part["accesses"][a]["var"] in written else 1   # var not written by this part: read-only cache path
-            return f"RD({a}, {masks[a]}, {ro}, {offs[0]}, {offs[1]}, {offs[2]})"
+            return f"RD({a}, {masks[a]}, {offs[0]}, {offs[1]}, {offs[2]})"
         out.append(f"{indent}const T e{s['dst']} = {gen_expr(s['tree'], rd, {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'})};")
-    for k, o in enumerate(part["outputs"]):
-        out.append(f"{indent}WR({k}, {o['access']}, {masks[o['access']]}, e{o['src']});")
+    for o in part["outputs"]:
+        out.append(f"{indent}WR({o['access']}, {masks[o['access']]}, e{o['src']});")
     return out
-
-
-def _store_lines(part, masks, indent="    "):
-    return [f"{indent}ST({k}, {o['access']}, {masks[o['access']]});" for k, o in enumerate(part["outputs"])]
 
 
 def _masks(ir, part):
@@ -466,8 +460,6 @@ def emit_cuda(ir: dict) -> str:
             L.extend(_stmt_lines(p, len(ir["domain_dims"]), masks=_masks(ir, p)))
             if p.get("cond"):
                 L.append("    }")
-            L.append("    GEN_KERNEL_STORES")
-            L.extend(_store_lines(p, _masks(ir, p)))
             L.append("    GEN_KERNEL_END")
             L.append("}")
     # spec table
