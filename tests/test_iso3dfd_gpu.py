@@ -78,6 +78,18 @@ def test_direct_kernel_all_radii_vs_oracle(radius):
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("fp_mode", [0, 2])
+@pytest.mark.parametrize("radius", [1, 2, 3, 4, 5, 6, 7])
+def test_tma_kernel_other_radii_vs_oracle(radius, fp_mode):
+    """The tiled kernel is instantiated for every radius 1..8 (default variant); same expression order as the oracle."""
+    n = (37, 45, 150)
+    ins = synth_inputs(n, 21, radius)
+    got = run_gpu(n, 3, ins, radius=radius, fp_mode=fp_mode, opts={"kernel": "tma", "lx": 13})
+    h = radius
+    ref = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], radius, 3, fp_mode)[h:-h, h:-h, h:-h]
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
 def test_empty_run_and_halo_untouched():
     n = (16, 16, 32)
     ins = synth_inputs(n, 3)

@@ -7,6 +7,7 @@
 
 #include "yb_core.h"
 #include "yb_iso3dfd.cuh"
+#include "yb_iso3dfd_tiles.h"
 
 namespace yb {
 
@@ -145,16 +146,6 @@ int make_map(CUtensorMap* map, const Var& v, int slot, int bz, int by) {
     return 0;
 }
 
-// Tile configurations of the TMA kernels that are compiled in.
-typedef void (*IsoKernelFn)(const IsoMaps, const IsoParams);
-struct TileCfg {
-    bool fused_ok;      // kernel can store boundary planes into the x neighbours (gen2 PW/U variants)
-    const char* name;
-    int ty, tz, hp, hrows, threads;
-    uint32_t smem;
-    IsoKernelFn fn[4];  // per FP mode (3 = debug memory-only probe, gen2 only)
-};
-
 template <class T>
 TileCfg cfg_gen1(const char* name) {
     return TileCfg{false, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
@@ -249,11 +240,11 @@ struct IsoEngine : Engine {
         YB_CUDA(cudaGetDeviceProperties(&prop, s.device));
         num_sms = prop.multiProcessorCount;
         maps_ok = false;
-        if (radius == 8 && prop.major >= 9) {
+        if (prop.major >= 9 && (radius == 8 || iso_radius_cfg(radius))) {
             const Var& p = s.vars[0];
             const Var& v = s.vars[1];
-            for (int tl = 0; tl < NTILES; tl++) {
-                const TileCfg& c = tile_cfg(tl);
+            for (int tl = 0; tl < (radius == 8 ? NTILES : 1); tl++) {
+                const TileCfg& c = radius == 8 ? tile_cfg(tl) : *iso_radius_cfg(radius);
                 for (int cur = 0; cur < 2; cur++) {
                     IsoMaps& m = maps[tl][cur];
                     if (int rc = make_map(&m.h, p, cur, c.hp, c.hrows)) return rc;
@@ -299,9 +290,10 @@ struct IsoEngine : Engine {
             // thin slabs in y/z (halo faces) are not worth a tile sweep
             if (box.e[1] - box.b[1] < 8 || box.e[2] - box.b[2] < 16) use_tma = false;
         }
-        if (kernel == "tma" && !maps_ok) return set_error(YB_EUNSUPPORTED, "TMA kernel needs radius 8 and sm_90+");
+        if (kernel == "tma" && !maps_ok) return set_error(YB_EUNSUPPORTED, "the tiled TMA kernel needs sm_90+");
         if (use_tma) {
-            const TileCfg& c = tile_cfg(tile);
+            const int ti = radius == 8 ? tile : 0;      // other radii: one compiled variant
+            const TileCfg& c = radius == 8 ? tile_cfg(tile) : *iso_radius_cfg(radius);
             if (mem_probe && c.fn[3]) mode = 3;
             // fused halo exchange: only for whole-domain launches of a kernel that implements the peer stores
             P.peer_lo = P.peer_hi = nullptr;
@@ -333,11 +325,11 @@ struct IsoEngine : Engine {
             P.nchunks = int((nxb + P.lx - 1) / P.lx);
             const int64_t nunits = int64_t(P.nty) * P.ntz * P.nchunks;
             int grid = int(std::min<int64_t>(nunits, gmax));
-            if (!attr_set[tile][mode]) {
+            if (!attr_set[ti][mode]) {
                 YB_CUDA(cudaFuncSetAttribute(c.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
-                attr_set[tile][mode] = true;
+                attr_set[ti][mode] = true;
             }
-            c.fn[mode]<<<grid, c.threads, c.smem, st>>>(maps[tile][cur], P);
+            c.fn[mode]<<<grid, c.threads, c.smem, st>>>(maps[ti][cur], P);
         } else {
             dim3 blk(128, 1, 1);
             dim3 grd(unsigned((box.e[2] - box.b[2] + 127) / 128), unsigned(box.e[1] - box.b[1]), unsigned(box.e[0] - box.b[0]));
