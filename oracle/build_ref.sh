@@ -57,6 +57,8 @@ if [ "${REF_ALL:-1}" = "1" ]; then
     build_kernel awp_elastic "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     build_kernel ssg "-fp64"        8
     build_kernel ssg "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+    build_kernel iso3dfd "-fp64"        8
+    build_kernel iso3dfd "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     # further solutions the CUDA emitter covers; "3axis" is the heat3d-style shape
     for st in awp iso3dfd_sponge 3axis 3axis_with_diags 3plane cube tti awp_elastic_abc awp_abc test_1d test_2d test_3d test_boundary_3d test_stream_3d fsg fsg_abc ssg2 ssg_merged fsg2; do
         build_kernel $st ""        4

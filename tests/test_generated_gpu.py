@@ -171,3 +171,24 @@ def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     for name in ref:
         it = np.uint32 if ref[name].dtype == np.float32 else np.uint64
         assert np.array_equal(got[name].view(it), ref[name].view(it)), name
+
+
+def test_iso3dfd_double_precision_is_served_by_the_generated_kernel():
+    """yk_factory-style request for iso3dfd with 8-byte elements (the reference's validation matrix runs fp64):
+    same solution name, generated fp64 kernel underneath, bit-exact vs the oracle."""
+    n, steps = (24, 20, 40), 2
+    ins, ir = synth_inputs("iso3dfd_fp64", n, 9)
+    s = capi.Solution("iso3dfd", radius=8, elem_bytes=8)
+    assert s.get_name() == "iso3dfd" and s.get_element_bytes() == 8
+    s.set_overall_domain_size_vec(n)
+    s.set_option("fp_mode", 0)
+    s.prepare_solution(0)
+    load_inputs(s, ins)
+    s.run_solution(0, steps - 1)
+    p = s.get_var("p")
+    tl = p.get_last_valid_step_index()
+    got = p.get_elements_in_slice(*p.domain_box(tl))
+    s.close()
+    ref = O.gen_run("iso3dfd_fp64", n, steps, ins)["p"]
+    assert ref[0] == tl and got.dtype == np.float64
+    assert np.array_equal(got.view(np.uint64), ref[1][8:-8, 8:-8, 8:-8].view(np.uint64))

@@ -28,6 +28,13 @@ int registry_create(const std::string& name, int radius, int elem_bytes, Stencil
         if (radius <= 0) radius = 8;
         if (elem_bytes == 0) elem_bytes = 4;
         if (radius > 8) return set_error(YB_EUNSUPPORTED, "iso3dfd: radius %d > 8 is not supported", radius);
+        if (elem_bytes == 8) {
+            // double precision: served by the emitter-generated kernel (radius 8 only); the tiled kernel is fp32
+            if (radius != 8) return set_error(YB_EUNSUPPORTED, "iso3dfd fp64 is generated for radius 8 only");
+            int rc = gen_registry_create("iso3dfd_fp64", 8, spec, eng);
+            if (rc == 0) { spec.name = "iso3dfd"; spec.radius = 8; }
+            return rc;
+        }
         spec = iso3dfd_spec(radius, elem_bytes, false);
         eng = make_iso3dfd_engine();
         return 0;
