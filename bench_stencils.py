@@ -14,10 +14,13 @@ from yask_b200.synth import var_salt
 BYTES = {"awp_elastic": 120, "ssg": 248, "iso3dfd": 16}
 
 
-def run(stencil, n, steps, warm, fp_mode):
+def run(stencil, n, steps, warm, fp_mode, opts=()):
     s = capi.Solution(stencil, elem_bytes=0)
     s.set_overall_domain_size_vec((n, n, n))
     s.set_option("fp_mode", fp_mode)
+    for kv in opts:
+        k, v = kv.split("=", 1)
+        s.set_option(k, v)
     s.prepare_solution(0)
     for v in s.get_vars():
         vi = v.info
@@ -38,11 +41,14 @@ def run(stencil, n, steps, warm, fp_mode):
         pass
     return {"stencil": stencil, "n": n, "steps": steps, "fp_mode": fp_mode, "gpoints_per_s": round(gpts, 2),
             "ms_per_step": round(st.elapsed_secs / steps * 1e3, 4), "algorithmic_gbs": round(gpts * BYTES[stencil], 1),
-            "roofline_frac_of_measured_hbm": round(gpts * BYTES[stencil] / peak, 4), "kernel_launches": st.kernel_launches}
+            "roofline_frac_of_measured_hbm": round(gpts * BYTES[stencil] / peak, 4), "kernel_launches": st.kernel_launches, "options": list(opts)}
 
 
 if __name__ == "__main__":
+    # usage: bench_stencils.py [n] [key=value engine options ...]
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    opts = [a for a in sys.argv[2:] if "=" in a]
+    modes = (2,) if opts else (2, 0)
     for stencil in ("awp_elastic", "ssg"):
-        for mode in (2, 0):
-            print(json.dumps(run(stencil, n, 10, 3, mode)), flush=True)
+        for mode in modes:
+            print(json.dumps(run(stencil, n, 10, 3, mode, opts)), flush=True)

@@ -64,6 +64,15 @@ if [ "${REF_ALL:-1}" = "1" ]; then
         build_kernel $st ""        4
         build_kernel $st "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     done
+    # second batch: remaining example/test solutions (filters, merged/abc FSG variants, 1-D/2-D tests, stages,
+    # scratch vars, step conditions, math functions)
+    for st in box_filter gaussian_filter fsg2_abc fsg_merged fsg_merged_abc test_boundary_1d test_boundary_2d test_partial_3d \
+              test_stages_1d test_stages_2d test_stages_3d test_stream_1d test_stream_2d test_reverse_2d \
+              test_scratch_1d test_scratch_2d test_scratch_3d test_scratch_boundary_1d test_scratch_stages_1d \
+              test_step_cond_1d test_func_1d test_misc_2d wave2d swe2d; do
+        build_kernel $st ""        4
+        build_kernel $st "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
+    done
 fi
 # Strip debug info (the reference builds with -g) and drop the (large) intermediate build tree.
 strip --strip-debug "$OUT"/lib/*.so "$OUT"/bin/*.exe "$OUT"/bin/ref_driver.* 2>/dev/null || true

@@ -68,7 +68,8 @@ def iso3dfd_run(p0: np.ndarray, p1: np.ndarray, v: np.ndarray, radius: int, step
 class _GenArgs(ctypes.Structure):
     _fields_ = [("nx", ctypes.c_int64), ("ny", ctypes.c_int64), ("nz", ctypes.c_int64), ("ptr", ctypes.c_void_p * 96),
                 ("sx", ctypes.c_int64 * 96), ("sy", ctypes.c_int64 * 96), ("sz", ctypes.c_int64 * 96),
-                ("off", ctypes.c_int64 * 3), ("gfirst", ctypes.c_int64 * 3), ("glast", ctypes.c_int64 * 3)]
+                ("off", ctypes.c_int64 * 3), ("gfirst", ctypes.c_int64 * 3), ("glast", ctypes.c_int64 * 3),
+                ("bx", ctypes.c_int64), ("by", ctypes.c_int64), ("bz", ctypes.c_int64), ("t", ctypes.c_int64)]
 
 
 def gen_ir(stencil: str) -> dict:
@@ -88,29 +89,34 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
     L.yo_gen_run_part.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_GenArgs)]
     slots = {}      # var -> list of arrays per slot
     meta = {}
+    nn = [1] * (3 - len(n)) + list(n)      # domain dims right-aligned into the (x,y,z) slots, like the CUDA engine
+    sh = 3 - len(dd)
     for v in ir["vars"]:
         has_step = bool(v["dims"]) and v["dims"][0] == ir["step_dim"]
         a = v["alloc_t"] if has_step else 1
-        arrs = []
-        for t in range(a):
-            arr = np.array(inputs[(v["name"], t)], dtype=dt, copy=True, order="C")
-            arrs.append(arr)
+        if v.get("scratch"):
+            # engine-internal temporary: rank domain + its halo, zero-initialised
+            shape = [n[dd.index(d)] + v["halo"][d][0] + v["halo"][d][1] for d in v["dims"]]
+            slots[v["name"]] = [np.zeros(shape, dtype=dt)]
+            meta[v["name"]] = (v, False, 1)
+            continue
+        arrs = [np.array(inputs[(v["name"], t)], dtype=dt, copy=True, order="C") for t in range(a)]
         # API step t lives in slot t % alloc_t (imod_flr)
-        slots[v["name"]] = [arrs[t % a] if a > 1 else arrs[0] for t in range(a)]
-        if a > 1:
-            slots[v["name"]] = [None] * a
-            for t in range(a):
-                slots[v["name"]][t % a] = arrs[t]
+        slots[v["name"]] = [None] * a
+        for t in range(a):
+            slots[v["name"]][t % a] = arrs[t]
         meta[v["name"]] = (v, has_step, a)
     last = {}
-    nn = [1] * (3 - len(n)) + list(n)      # domain dims right-aligned into the (x,y,z) slots, like the CUDA engine
-    sh = 3 - len(dd)
     for t in range(steps):
-        pi = 0
         for st in ir["stages"]:
+            written = set()      # scratch vars written so far in this stage
             for p in st["parts"]:
                 A = _GenArgs()
                 A.nx, A.ny, A.nz = nn
+                A.t = t
+                wh = [[0, 0]] * sh + (p.get("wh") or [[0, 0]] * len(dd))
+                A.bx, A.by, A.bz = [-w[0] for w in wh]
+                A.nx, A.ny, A.nz = [nn[k] + wh[k][1] for k in range(3)]
                 for d in range(3):
                     A.off[d], A.gfirst[d], A.glast[d] = 0, 0, nn[d] - 1
                 for k, acc in enumerate(p["accesses"]):
@@ -126,11 +132,21 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
                     A.sx[k] = strides.get(dd[0 - sh], 0) if sh <= 0 else 0
                     A.sy[k] = strides.get(dd[1 - sh], 0) if sh <= 1 else 0
                     A.sz[k] = strides.get(dd[2 - sh], 0)
-                rc = L.yo_gen_run_part(stencil.encode(), pi, ctypes.byref(A))
+                if p.get("scratch"):
+                    # a scratch var whose first writer in the stage is conditional starts from zero
+                    # (/root/reference/src/kernel/lib/stencil_calc.cpp:85-109)
+                    for o in p["outputs"]:
+                        sv = p["accesses"][o["access"]]["var"]
+                        if sv not in written:
+                            written.add(sv)
+                            if p.get("conditional"):
+                                slots[sv][0][...] = 0
+                rc = L.yo_gen_run_part(stencil.encode(), p.get("index", 0), ctypes.byref(A))
                 assert rc == 0, rc
-                for o in p["outputs"]:
-                    last[p["accesses"][o["access"]]["var"]] = t + 1
-                pi += 1
+                if not p.get("scratch"):
+                    for o in p["outputs"]:
+                        oa = p["accesses"][o["access"]]
+                        last[oa["var"]] = t + oa["toff"]      # t+1 (t-1 for reverse-time solutions)
     out = {}
     for name, tl in last.items():
         v, has_step, a = meta[name]

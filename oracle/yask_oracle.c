@@ -1,3 +1,4 @@
+#define _GNU_SOURCE   /* sincosf */
 /*
  * TEST INFRASTRUCTURE ONLY -- CPU restatement ("oracle") of the reference's hot path.
  *
@@ -218,25 +219,46 @@ typedef struct {
     void* ptr[YO_GEN_MAX_ACC];          /* element (0,0,0) of each access' step slot */
     int64_t sx[YO_GEN_MAX_ACC], sy[YO_GEN_MAX_ACC], sz[YO_GEN_MAX_ACC];
     int64_t off[3], gfirst[3], glast[3];   /* for sub-domain conditions (global indices) */
+    int64_t bx, by, bz;                 /* first index of the box (0, or -write_halo for scratch parts) */
+    int64_t t;                          /* step index (step conditions) */
 } yo_gen_args;
 typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } yo_gen_part;
 
 #define YO_GEN_LOOP_BEGIN                                                      \
     _Pragma("omp parallel for collapse(2) schedule(static)")                   \
-    for (int64_t x = 0; x < A->nx; x++)                                        \
-        for (int64_t y = 0; y < A->ny; y++)                                    \
-            for (int64_t z = 0; z < A->nz; z++) {
+    for (int64_t x = A->bx; x < A->nx; x++)                                    \
+        for (int64_t y = A->by; y < A->ny; y++)                                \
+            for (int64_t z = A->bz; z < A->nz; z++) {
 #define YO_GEN_LOOP_END }
 #define RD(a, m, dx, dy, dz) (((const T*)A->ptr[a])[(x + (dx)) * A->sx[a] + (y + (dy)) * A->sy[a] + (z + (dz)) * A->sz[a]])
 #define WR(a, m, v) ((T*)A->ptr[a])[x * A->sx[a] + y * A->sy[a] + z * A->sz[a]] = (v)
 #define C(v) ((T)(v))
 #define G(i) ((i) == 0 ? x + A->off[0] : ((i) == 1 ? y + A->off[1] : z + A->off[2]))
+#define GT A->t
 #define GF(i) A->gfirst[i]
 #define GL(i) A->glast[i]
 #define ADD(a, b) ((a) + (b))
 #define SUB(a, b) ((a) - (b))
 #define MUL(a, b) ((a) * (b))
 #define DIV(a, b) ((a) / (b))
+/* DSL math functions: libm of the element type, as the reference's non-SVML build calls them per element
+ * (/root/reference/src/kernel/lib/realv.hpp:648-738). */
+#define YF1(fd, ff, a) (sizeof(T) == 4 ? (T)ff((float)(a)) : (T)fd((double)(a)))
+#define YF_sqrt(a) YF1(sqrt, sqrtf, a)
+#define YF_cbrt(a) YF1(cbrt, cbrtf, a)
+#define YF_fabs(a) YF1(fabs, fabsf, a)
+#define YF_erf(a) YF1(erf, erff, a)
+#define YF_exp(a) YF1(exp, expf, a)
+#define YF_log(a) YF1(log, logf, a)
+#define YF_sin(a) YF1(sin, sinf, a)
+#define YF_cos(a) YF1(cos, cosf, a)
+#define YF_atan(a) YF1(atan, atanf, a)
+#define YF_pow(a, b) (sizeof(T) == 4 ? (T)powf((float)(a), (float)(b)) : (T)pow((double)(a), (double)(b)))
+#define YF_min(a, b) ((b) < (a) ? (b) : (a))
+#define YF_max(a, b) ((a) < (b) ? (b) : (a))
+#define YF_sincos(a, s, c)                                                                        \
+    do { if (sizeof(T) == 4) { float s_, c_; sincosf((float)(a), &s_, &c_); (s) = (T)s_; (c) = (T)c_; } \
+         else { double s_, c_; sincos((double)(a), &s_, &c_); (s) = (T)s_; (c) = (T)c_; } } while (0)
 
 #include "gen/gen_all.inc"
 

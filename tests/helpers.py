@@ -48,7 +48,7 @@ def regen_inputs(meta, dtype=None):
     ins = {}
     for name, g in meta["vars"].items():
         lo, hi = range_of(meta["ranges"], name)
-        has_step = bool(g["dims"]) and g["dims"][0] == "t"
+        has_step = len(g["dims"]) == len(g["in_first"]) + 1      # the boxes cover the non-step dims
         t0, t1 = meta["vars_before"][name]["steps"] if has_step else (0, 0)
         shape = [l - f + 1 for f, l in zip(g["in_first"], g["in_last"])]
         for t in range(t0, t1 + 1):

@@ -78,7 +78,7 @@ static int compute_rank_geometry(Solution& s) {
     return 0;
 }
 
-static void compute_var_geometry(Solution& s, Var& v) {
+void compute_var_geometry(Solution& s, Var& v) {
     const int align_elems = 128 / v.elem_bytes;  // 128-B rows
     int nd = int(v.dims.size());
     int last_domain = -1;
@@ -643,7 +643,6 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
     Solution* s = SOL(s_);
     if (!s) return set_error(YB_EINVAL, "null solution");
     if (!s->prepared) return set_error(YB_ESTATE, "run_solution() called without calling prepare_solution() first");
-    if (last_step < first_step) return set_error(YB_EUNSUPPORTED, "reverse-time stepping is not supported by this engine");
     YB_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = s->stream();
     cudaEvent_t e0, e1;
@@ -655,7 +654,9 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
     int64_t pts = whole.points();
     int rc = 0;
     if (s->halo) rc = halo_exchange_all(*s, st);  // initial exchange of everything dirty (context.cpp:346)
-    for (int64_t t = first_step; t <= last_step && rc >= 0; t++) {
+    // direction from the order of the arguments, as the reference does (context.cpp:237-246)
+    const int64_t step_dir = last_step >= first_step ? 1 : -1;
+    for (int64_t t = first_step; t != last_step + step_dir && rc >= 0; t += step_dir) {
         for (size_t sg = 0; sg < s->spec.stages.size() && rc >= 0; sg++) {
             if (s->halo) {
                 rc = halo_run_stage(*s, int(sg), t, st);
@@ -667,7 +668,7 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
             s->stats.num_writes_done += sp.writes * pts;
             s->stats.num_reads_done += sp.reads * pts;
             s->stats.est_fp_ops_done += sp.fp_ops * pts;
-            for (int vi : sp.outputs) s->vars[vi].update_valid_step(t + 1);
+            for (int vi : sp.outputs) s->vars[vi].update_valid_step(t + sp.out_step_off);
         }
         s->stats.num_steps_done++;
     }

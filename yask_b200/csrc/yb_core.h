@@ -42,7 +42,8 @@ struct VarSpec {
 
 struct StageSpec {
     std::string name;
-    std::vector<int> outputs;  // var indices written (at t+1)
+    std::vector<int> outputs;  // var indices written (at t + out_step_off)
+    int out_step_off = 1;      // +1; -1 for reverse-time solutions (equations defined at t-1)
     std::vector<int> inputs;   // var indices read
     int64_t fp_ops = 0, reads = 0, writes = 0;  // per point, as counted by the reference compiler
 };
@@ -170,6 +171,9 @@ struct Solution {
     int multi_rank() const { return int(num_ranks[0] * num_ranks[1] * num_ranks[2]) > 1; }
     ~Solution();
 };
+
+// storage geometry of one var from the solution's rank geometry (yb_core.cu)
+void compute_var_geometry(Solution& s, Var& v);
 
 // error plumbing
 int set_error(int code, const char* fmt, ...);

@@ -18,22 +18,86 @@ typedef void (*DescribeFn)(GenStencil&);
 struct GenEntry { const char* name; DescribeFn describe; };
 const GenEntry kGen[] = {YB_GEN_TABLE};
 
+VarSpec var_spec_of(const GenStencil& g, const GenVar& gv) {
+    VarSpec v;
+    v.name = gv.name;
+    v.step_alloc = gv.alloc_t;
+    v.is_output = gv.is_output;
+    v.l1_norm = gv.l1_norm;
+    for (auto* dn : gv.dims) {
+        DimSpec d;
+        d.name = dn;
+        if (g.step_dim == dn) { d.kind = DIM_STEP; }
+        else {
+            d.kind = DIM_MISC;
+            for (size_t k = 0; k < g.domain_dims.size(); k++)
+                if (g.domain_dims[k] == dn) { d.kind = DIM_DOMAIN; d.domain_index = int(k); d.halo_l = gv.halo_l[k]; d.halo_r = gv.halo_r[k]; }
+            if (d.kind == DIM_MISC) {
+                const size_t di = v.dims.size();
+                d.misc_first = gv.misc_first[di];
+                d.misc_size = std::max(1, gv.misc_size[di]);
+            }
+        }
+        v.dims.push_back(d);
+    }
+    return v;
+}
+
 struct GenEngine : Engine {
     GenStencil g;
+    // Scratch vars (MAKE_SCRATCH_VAR in the DSL) are engine-internal: one HBM array each over the rank domain plus the
+    // var's halo, in the solution's shared padded geometry.  (The reference keeps one micro-block-sized copy per
+    // thread, /root/reference/src/kernel/lib/setup.cpp:807-; a GPU launch covers the whole rank box at once.)
+    std::vector<Var> scratch;
+    int nreg = 0;      // g.vars[0..nreg) are the API-visible vars, the rest scratch
+    ~GenEngine() override {
+        for (auto& v : scratch)
+            if (v.dev) cudaFree(v.dev);
+    }
+    const Var& var_of(const Solution& s, int gi) const { return gi < nreg ? s.vars[gi] : scratch[gi - nreg]; }
+    // option gen_pf (or env YB_GEN_PF): L2 prefetch distance in x planes (0 = off).  Measured on B200 at 512^3
+    // (profiles/r1_generated.md): 1 plane ahead + 16 MB chunks: awp_elastic 22.5 -> 26.4 GPts/s, ssg 11.3 -> 13.9.
+    int pf_dist = 1;
+    GenEngine() {
+        if (const char* e = getenv("YB_GEN_PF")) pf_dist = std::max(0, atoi(e));
+        if (const char* e = getenv("YB_GEN_L2_MB")) l2_mb = std::max(0, atoi(e));
+    }
+    int l2_mb = 16;    // option gen_l2_mb (env YB_GEN_L2_MB): L2 budget of one y chunk's sweep working set (0 = no chunking)
+    int set_option(Solution&, const std::string& key, const std::string& value) override {
+        if (key == "gen_pf") { pf_dist = std::max(0, atoi(value.c_str())); return 0; }
+        if (key == "gen_l2_mb") { l2_mb = std::max(0, atoi(value.c_str())); return 0; }
+        return YB_EINVAL;
+    }
     int prepare(Solution& s) override {
         if (s.spec.elem_bytes != g.elem_bytes)
             return set_error(YB_EUNSUPPORTED, "solution '%s' was generated for %d-byte elements", g.name.c_str(), g.elem_bytes);
         for (auto& st : g.stages)
             for (auto& p : st.parts)
                 if (int(p.acc.size()) > GEN_MAX_ACC) return set_error(YB_EUNSUPPORTED, "part '%s' touches too many vars", p.name);
+        for (auto& v : scratch)
+            if (v.dev) cudaFree(v.dev);
+        scratch.clear();
+        for (auto& gv : g.vars) {
+            if (!gv.is_scratch) continue;
+            Var v;
+            v.spec = var_spec_of(g, gv);
+            v.elem_bytes = g.elem_bytes;
+            for (auto& ds : v.spec.dims) { Dim d; d.spec = ds; v.dims.push_back(d); }
+            compute_var_geometry(s, v);
+            YB_CUDA(cudaMalloc(&v.dev, v.bytes()));
+            YB_CUDA(cudaMemsetAsync(v.dev, 0, v.bytes(), s.stream()));
+            scratch.push_back(std::move(v));
+        }
         return 0;
     }
     int launch(Solution& s, int stage, int64_t t, const Box& box, cudaStream_t st) override {
         if (box.empty()) return 0;
         const GenStage& gs = g.stages[stage];
         int n = 0;
+        std::vector<char> scratch_written(scratch.size(), 0);
         for (auto& p : gs.parts) {
             GenParams P{};
+            P.t = t;
             // The solution's domain dims are right-aligned into the kernel's (x,y,z) slots: slot k holds domain dim
             // k - sh, so the unit-stride dim always lands in slot z (1-D/2-D solutions leave the outer slots empty).
             const int sh = 3 - s.ndd;
@@ -42,8 +106,8 @@ struct GenEngine : Engine {
             Box pb;
             for (int k = 0; k < 3; k++) {
                 const int d = k - sh;
-                pb.b[k] = d >= 0 ? box.b[d] : 0;
-                pb.e[k] = d >= 0 ? box.e[d] : 1;
+                pb.b[k] = d >= 0 ? box.b[d] - p.wh_l[k] : 0;
+                pb.e[k] = d >= 0 ? box.e[d] + p.wh_r[k] : 1;
                 P.off[k] = d >= 0 ? s.rank_offset[d] : 0;
                 P.gfirst[k] = 0;
                 P.glast[k] = d >= 0 ? s.overall_size[d] - 1 : 0;
@@ -58,7 +122,7 @@ struct GenEngine : Engine {
             P.zb = int(pb.b[2]); P.ze = int(pb.e[2]);
             P.SX = P.SY = 0;
             for (size_t k = 0; k < p.acc.size(); k++) {
-                const Var& v = s.vars[p.acc[k].var];
+                const Var& v = var_of(s, p.acc[k].var);
                 const int slot = v.slot_of(t + p.acc[k].toff);
                 int64_t moff = 0;      // constant misc-dim indices select a sub-array
                 int mi = 0;
@@ -77,11 +141,55 @@ struct GenEngine : Engine {
                         return set_error(YB_EUNSUPPORTED, "var '%s' does not share the solution's padded geometry", v.spec.name.c_str());
                 }
             }
+            // A scratch var whose first writer in this stage is conditional starts from zero
+            // (/root/reference/src/kernel/lib/stencil_calc.cpp:85-109).
+            if (p.is_scratch)
+                for (int o : p.outs) {
+                    const int si = p.acc[o].var - nreg;
+                    if (si < 0 || scratch_written[si]) continue;
+                    scratch_written[si] = 1;
+                    if (p.conditional) YB_CUDA(cudaMemsetAsync(scratch[si].dev, 0, scratch[si].bytes(), st));
+                }
+            // L2 prefetch list: full-rank vars the part only reads (distinct storage)
+            P.npf = 0;
+            P.pfd = pf_dist;
+            if (pf_dist > 0 && P.SX != 0) {
+                for (size_t k = 0; k < p.acc.size(); k++) {
+                    if (P.sx[k] != P.SX || P.sy[k] != P.SY || P.sz[k] != 1) continue;
+                    if (std::find(p.outs.begin(), p.outs.end(), int(k)) != p.outs.end()) continue;
+                    bool dup = false;
+                    for (int q = 0; q < P.npf; q++) dup = dup || P.ptr[P.pf[q]] == P.ptr[k];
+                    if (!dup) P.pf[P.npf++] = (unsigned char)k;
+                }
+            }
             GenKernelFn fn = p.fn[g.elem_bytes == 8 ? 1 : 0][s.fp_mode == 0 ? 0 : 1];
-            dim3 grd(unsigned((pb.e[2] - pb.b[2] + GEN_BZ - 1) / GEN_BZ), unsigned((pb.e[1] - pb.b[1] + GEN_BY * gen_np(g.elem_bytes) - 1) / (GEN_BY * gen_np(g.elem_bytes))),
-                     unsigned((pb.e[0] - pb.b[0] + GEN_BX - 1) / GEN_BX));
-            if (grd.y > 65535 || grd.z > 65535) return set_error(YB_EUNSUPPORTED, "domain too large in x or y for the generated kernels");
-            fn<<<grd, GEN_BLOCK, 0, st>>>(P);
+            const int rows_per_block = GEN_BY * gen_np(g.elem_bytes);
+            P.nzb = int((pb.e[2] - pb.b[2] + GEN_BZ - 1) / GEN_BZ);
+            P.nyb = int((pb.e[1] - pb.b[1] + rows_per_block - 1) / rows_per_block);
+            P.nxb = int((pb.e[0] - pb.b[0] + GEN_BX - 1) / GEN_BX);
+            // y chunk: keep (x span of the stencil) planes of every full-rank var of the part within the L2 budget
+            P.ychunk = P.nyb;
+            if (l2_mb > 0 && P.SX != 0 && P.nxb > 1) {
+                int nfull = 0;
+                for (size_t k = 0; k < p.acc.size(); k++) {
+                    if (P.sx[k] != P.SX) continue;
+                    bool dup = false;
+                    for (size_t q = 0; q < k; q++) dup = dup || P.ptr[q] == P.ptr[k];
+                    nfull += !dup;
+                }
+                const int64_t span = 2 * std::max<int64_t>(s.spec.uniform_pad[std::max(0, 0 - sh)], 0) + 1;
+                const double row_bytes = double(P.SY) * g.elem_bytes * double(span) * std::max(nfull, 1);
+                int64_t rows = int64_t(double(l2_mb) * 1048576.0 / row_bytes);
+                int64_t yc = std::max<int64_t>(rows / rows_per_block, 4);
+                if (yc < P.nyb) {
+                    // equalise the chunks
+                    const int64_t nch = (P.nyb + yc - 1) / yc;
+                    P.ychunk = int((P.nyb + nch - 1) / nch);
+                }
+            }
+            const int64_t nblocks = int64_t(P.nzb) * P.nyb * P.nxb;
+            if (nblocks >= (int64_t(1) << 31)) return set_error(YB_EUNSUPPORTED, "domain too large for the generated kernels");
+            fn<<<unsigned(nblocks), GEN_BLOCK, 0, st>>>(P);
             YB_CUDA(cudaGetLastError());
             n++;
         }
@@ -108,29 +216,13 @@ int gen_registry_create(const std::string& name, int elem_bytes, StencilSpec& sp
         spec.step_dim = g.step_dim;
         spec.domain_dims = g.domain_dims;
         spec.elem_bytes = g.elem_bytes;
+        ge->nreg = 0;
+        bool seen_scratch = false;
         for (auto& gv : g.vars) {
-            VarSpec v;
-            v.name = gv.name;
-            v.step_alloc = gv.alloc_t;
-            v.is_output = gv.is_output;
-            v.l1_norm = gv.l1_norm;
-            for (auto* dn : gv.dims) {
-                DimSpec d;
-                d.name = dn;
-                if (g.step_dim == dn) { d.kind = DIM_STEP; }
-                else {
-                    d.kind = DIM_MISC;
-                    for (size_t k = 0; k < g.domain_dims.size(); k++)
-                        if (g.domain_dims[k] == dn) { d.kind = DIM_DOMAIN; d.domain_index = int(k); d.halo_l = gv.halo_l[k]; d.halo_r = gv.halo_r[k]; }
-                    if (d.kind == DIM_MISC) {
-                        const size_t di = v.dims.size();
-                        d.misc_first = gv.misc_first[di];
-                        d.misc_size = std::max(1, gv.misc_size[di]);
-                    }
-                }
-                v.dims.push_back(d);
-            }
-            spec.vars.push_back(v);
+            if (gv.is_scratch) { seen_scratch = true; continue; }     // scratch vars come last in the table
+            if (seen_scratch) return set_error(YB_EINVAL, "generated table of '%s': scratch var before a regular var", e.name);
+            spec.vars.push_back(var_spec_of(g, gv));
+            ge->nreg++;
         }
         // one padded geometry for all vars: pad every dim to the largest halo any var has there
         for (auto& gv : g.vars)
@@ -141,8 +233,13 @@ int gen_registry_create(const std::string& name, int elem_bytes, StencilSpec& sp
             st.name = gs.name;
             for (auto& p : gs.parts) {
                 st.fp_ops += p.fp_ops; st.reads += p.reads; st.writes += p.writes;
-                for (int o : p.outs) st.outputs.push_back(p.acc[o].var);
-                for (auto& a : p.acc) st.inputs.push_back(a.var);
+                for (int o : p.outs)
+                    if (p.acc[o].var < ge->nreg) {
+                        st.outputs.push_back(p.acc[o].var);
+                        if (p.acc[o].toff != 0) st.out_step_off = p.acc[o].toff;    // +1, or -1 for reverse-time solutions
+                    }
+                for (auto& a : p.acc)
+                    if (a.var < ge->nreg) st.inputs.push_back(a.var);
             }
             spec.stages.push_back(st);
         }

@@ -35,6 +35,16 @@ struct GenParams {
     int SX, SY;
     // sub-domain conditions are written over GLOBAL indices: rank offset and overall first/last index per dim
     long long off[3], gfirst[3], glast[3];
+    // L2 prefetch (option gen_pf): the CTA asks L2 for the lines of its own (y,z) tile `pfd` planes ahead in x of
+    // every full-rank input var, so that the demand loads of the CTA that computes that plane find them in L2.
+    int npf, pfd;
+    unsigned char pf[GEN_MAX_ACC];
+    // CTA order (1-D grid): z blocks fastest, then the y blocks of one y CHUNK, then x, then the next chunk -- the
+    // planes x-h..x+h of a chunk (all vars) stay L2-resident while the sweep moves along x, so every element comes
+    // from DRAM once even when whole x planes of all vars would not fit in L2 (ssg fp64 512^3: 8 planes x 12 vars
+    // x 2 MB).  nzb/nyb/nxb = number of blocks per dim, ychunk = y blocks per chunk.
+    int nzb, nyb, nxb, ychunk;
+    long long t;   // step index the part is evaluated at (step conditions, IF_STEP)
 };
 
 typedef void (*GenKernelFn)(const GenParams);
@@ -47,6 +57,7 @@ struct GenVar {
     int l1_norm;
     std::vector<int> halo_l, halo_r; // per solution domain dim
     std::vector<int> misc_first, misc_size;   // per declared dim: index range of misc dims (0 size otherwise)
+    bool is_scratch = false;         // engine-internal temporary (MAKE_SCRATCH_VAR): not visible through the API
 };
 struct GenAccess { int var, toff; int misc[2]; };   // misc: constant indices of the var's misc dims, in declared order
 struct GenPart {
@@ -58,6 +69,11 @@ struct GenPart {
     // Launch-box bounds derived from the part's sub-domain condition, per domain dim: global index range
     // [lo, hi] with each end = offset relative to 0 / first / last overall index (kind 0/1/2), kind -1 = open.
     struct Bound { int lo_kind, lo_off, hi_kind, hi_off; } bound[3];
+    // Scratch part: writes scratch vars over the launch box EXPANDED by the write halo (per kernel slot x,y,z), before
+    // the parts that read them (/root/reference/src/kernel/lib/stencil_calc.cpp:128-137, setup.cpp:1182-1228).
+    bool is_scratch = false;
+    bool conditional = false;        // has a sub-domain or step condition (scratch outputs are zeroed first)
+    int wh_l[3] = {0, 0, 0}, wh_r[3] = {0, 0, 0};
 };
 struct GenStage { const char* name; std::vector<GenPart> parts; };
 struct GenStencil {
@@ -94,11 +110,45 @@ template <typename T> struct GenOp<T, 1> {
     static __device__ __forceinline__ T div(T a, T b) { return a / b; }
 };
 
+// blockIdx.x -> (x, y, z) block coordinates in chunked sweep order (see GenParams::ychunk)
+__device__ __forceinline__ void gen_block_coords(const GenParams& P, int& bx, int& by, int& bz) {
+    const unsigned per_chunk = unsigned(P.nzb) * unsigned(P.ychunk) * unsigned(P.nxb);
+    const unsigned chunk = blockIdx.x / per_chunk;
+    unsigned rem = blockIdx.x - chunk * per_chunk;
+    const unsigned y0 = chunk * unsigned(P.ychunk);
+    const unsigned yc = min(unsigned(P.ychunk), unsigned(P.nyb) - y0);   // the last chunk may be shorter
+    const unsigned per_plane = unsigned(P.nzb) * yc;
+    bx = int(rem / per_plane);
+    rem -= unsigned(bx) * per_plane;
+    by = int(y0 + rem / unsigned(P.nzb));
+    bz = int(rem % unsigned(P.nzb));
+}
+
+// One 128-byte line per thread and trip: lines of (GEN_BY * NP) rows x GEN_BZ points x GEN_BX planes per var.
+template <typename T>
+__device__ __forceinline__ void gen_prefetch(const GenParams& P, int x0, int y0, int z0) {
+    constexpr int LPR = GEN_BZ * int(sizeof(T)) / 128;              // lines per row
+    constexpr int ROWS = GEN_BY * gen_np(int(sizeof(T))) * GEN_BX;
+    constexpr int EPL = 128 / int(sizeof(T));                        // elements per line
+    const int total = P.npf * (ROWS * LPR);
+    for (int i = threadIdx.x; i < total; i += GEN_BLOCK) {
+        const int v = i / (ROWS * LPR), r = (i / LPR) % ROWS, l = i % LPR;
+        const int xx = x0 + P.pfd + r / (GEN_BY * gen_np(int(sizeof(T)))), yy = y0 + r % (GEN_BY * gen_np(int(sizeof(T)))), zz = z0 + l * EPL;
+        if (xx < P.xe && yy < P.ye && zz < P.ze) {
+            const T* a = static_cast<const T*>(P.ptr[P.pf[v]]) + (xx * P.SX + yy * P.SY + zz);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    }
+}
+
 #define GEN_KERNEL_BEGIN                                                                         \
-    const int z = P.zb + blockIdx.x * GEN_BZ + (threadIdx.x % GEN_BZ);                           \
+    int gbx_, gby_, gbz_;                                                                        \
+    gen_block_coords(P, gbx_, gby_, gbz_);                                                       \
+    const int z = P.zb + gbz_ * GEN_BZ + (threadIdx.x % GEN_BZ);                                 \
     constexpr int GEN_NP = gen_np(int(sizeof(T)));                                               \
-    const int y0_ = P.yb + blockIdx.y * (GEN_BY * GEN_NP) + (threadIdx.x / GEN_BZ) % GEN_BY;     \
-    const int x = P.xb + blockIdx.z * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);                  \
+    const int y0_ = P.yb + gby_ * (GEN_BY * GEN_NP) + (threadIdx.x / GEN_BZ) % GEN_BY;           \
+    const int x = P.xb + gbx_ * GEN_BX + threadIdx.x / (GEN_BZ * GEN_BY);                        \
+    if (P.npf) gen_prefetch<T>(P, P.xb + gbx_ * GEN_BX, P.yb + gby_ * (GEN_BY * GEN_NP), P.zb + gbz_ * GEN_BZ);       \
     if (z >= P.ze || x >= P.xe) return;                                                          \
     _Pragma("unroll") for (int gp_ = 0; gp_ < GEN_NP; gp_++) {                                   \
         const int y = y0_ + gp_ * GEN_BY;                                                        \
@@ -116,12 +166,28 @@ template <typename T> struct GenOp<T, 1> {
          else static_cast<T*>(P.ptr[a])[x * P.sx[a] + y * P.sy[a] + z * P.sz[a]] = (v); } while (0)
 #define C(v) static_cast<T>(v)
 #define G(i) ((i) == 0 ? x + P.off[0] : ((i) == 1 ? y + P.off[1] : z + P.off[2]))
+#define GT P.t
 #define GF(i) P.gfirst[i]
 #define GL(i) P.glast[i]
 #define ADD(a, b) GenOp<T, MODE>::add(a, b)
 #define SUB(a, b) GenOp<T, MODE>::sub(a, b)
 #define MUL(a, b) GenOp<T, MODE>::mul(a, b)
 #define DIV(a, b) GenOp<T, MODE>::div(a, b)
+// DSL math functions (/root/reference/src/kernel/lib/realv.hpp:713-726 call libm per element); CUDA's overloads
+// pick the element type.  sqrt/fabs/min/max are exact, the others agree with libm to a few ulps.
+#define YF_sqrt(a) sqrt(a)
+#define YF_cbrt(a) cbrt(a)
+#define YF_fabs(a) fabs(a)
+#define YF_erf(a) erf(a)
+#define YF_exp(a) exp(a)
+#define YF_log(a) log(a)
+#define YF_sin(a) sin(a)
+#define YF_cos(a) cos(a)
+#define YF_atan(a) atan(a)
+#define YF_pow(a, b) pow(a, b)
+#define YF_min(a, b) ((b) < (a) ? (b) : (a))   /* std::min */
+#define YF_max(a, b) ((a) < (b) ? (b) : (a))   /* std::max */
+#define YF_sincos(a, s, c) sincos(a, &(s), &(c))
 #endif
 
 } }  // namespace yb::gen

@@ -310,7 +310,7 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
     if (outs.size() == 1 && want_fused) {
         const int vi = outs[0];
         const Var& v = s.vars[vi];
-        const int slot = v.slot_of(t + 1);
+        const int slot = v.slot_of(t + s.spec.stages[stage].out_step_off);
         const Dim* dx = v.domain_dim(0);
         for (auto& nb : h->nbrs) {
             if (nb.dir[1] != 0 || nb.dir[2] != 0 || nb.dir[0] == 0 || !dx) continue;
@@ -330,7 +330,7 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
     s.stats.kernel_launches += rc;
     for (int vi : s.spec.stages[stage].outputs) {
         const Var& v = s.vars[vi];
-        h->dirty[vi][v.slot_of(t + 1)] = 1;
+        h->dirty[vi][v.slot_of(t + s.spec.stages[stage].out_step_off)] = 1;
     }
     const int skip = s.fused_x.used ? s.fused_x.var : -1;
     s.fused_x = Solution::FusedX();

@@ -175,12 +175,17 @@ def parse_domain_cond(text: str, dd: list[str]) -> dict:
     return {"expr": t, "bounds": {str(k): v for k, v in bounds.items()} if ok else None, "text": text.strip()}
 
 
+# DSL math functions (/root/reference/src/kernel/lib/realv.hpp:713-726) -> number of arguments
+MATH_FUNCS = {"sqrt": 1, "cbrt": 1, "fabs": 1, "erf": 1, "exp": 1, "log": 1, "sin": 1, "cos": 1, "atan": 1,
+              "pow": 2, "min": 2, "max": 2}
+
+
 class Parser:
     """Tiny recursive-descent parser for the RHS of generated statements: + - * / with C precedence and
     left associativity, parentheses, unary minus, numeric literals, expr_temp refs and read placeholders."""
 
     def __init__(self, text: str):
-        self.toks = re.findall(r"@\d+|expr_temp\d+|" + r"\d+\.\d*(?:[eE][-+]?\d+)?|\d+(?:[eE][-+]?\d+)?" + r"|[-+*/()]", text)
+        self.toks = re.findall(r"@\d+|(?:arg\d+|res|expr)_temp\d+|yask_\w+|" + r"\d+\.\d*(?:[eE][-+]?\d+)?|\d+(?:[eE][-+]?\d+)?" + r"|[-+*/(),]", text)
         joined = "".join(self.toks)
         if joined != re.sub(r"\s+", "", text):
             raise EmitError(f"unsupported construct in expression: '{text}'")
@@ -236,8 +241,24 @@ class Parser:
             return e
         if t.startswith("@"):
             return ("read", int(t[1:]))
-        if t.startswith("expr_temp"):
-            return ("tmp", int(t[len("expr_temp"):]))
+        m = re.fullmatch(r"(expr|res|arg(\d+))_temp(\d+)", t)
+        if m:
+            return ("tmp", {"expr": "e", "res": "r"}.get(m.group(1), f"a{m.group(2)}_") + m.group(3))
+        if t.startswith("yask_"):
+            fn = t[len("yask_"):]
+            if fn not in MATH_FUNCS:
+                raise EmitError(f"unsupported math function '{t}'")
+            if self.next() != "(":
+                raise EmitError(f"'(' expected after {t}")
+            args = [self.expr()]
+            while self.peek() == ",":
+                self.next()
+                args.append(self.expr())
+            if self.next() != ")":
+                raise EmitError("missing ')'")
+            if len(args) != MATH_FUNCS[fn]:
+                raise EmitError(f"{t}: {len(args)} argument(s)")
+            return ("call", fn, args)
         return ("const", t)
 
 
@@ -247,13 +268,15 @@ def parse_generated(text: str, name: str) -> dict:
     m = re.search(r"#define REAL_BYTES \((\d+)\)", text) or re.search(r"REAL_BYTES\s+\(?(\d+)\)?", text)
     ir["elem_bytes"] = int(m.group(1)) if m else None
     # ---- vars -----------------------------------------------------------------------------------------
-    for m in re.finditer(r"// The (?:(\d+)-D var|scalar value) '(\w+)', which is (updated by one or more equations|not updated by any equation)[^\n]*\n"
+    for m in re.finditer(r"// The (?:(\d+)-D var|scalar value) '(\w+)', which is\s+(updated by one or more equations|not updated by any equation|a scratch variable)[^\n]*\n"
                          r"(?:\s*// Dimensions in parameter \(declaration\) order: ([^\n]*)\n)?", text):
         vname = m.group(2)
         dims = re.findall(r"'(\w+)'\(#\d+\)", m.group(4) or "")
         if any(v["name"] == vname for v in ir["vars"]):
             continue
-        ir["vars"].append({"name": vname, "dims": dims, "is_output": m.group(3).startswith("updated")})
+        ir["vars"].append({"name": vname, "dims": dims, "is_output": m.group(3).startswith("updated"),
+                           "scratch": m.group(3).startswith("a scratch")})
+    ir["vars"].sort(key=lambda v: v["scratch"])      # scratch vars last (stable): they are engine-internal storage
     if not ir["vars"]:
         raise EmitError("no vars found in the generated file")
     # domain dims: the front-end's own list ("#define DOMAIN_DIM_IDX_<d> <i>"); step dim: the first dim of an updated var
@@ -267,11 +290,9 @@ def parse_generated(text: str, name: str) -> dict:
     ir["step_dim"], ir["domain_dims"] = step_dim, dd
     if len(dd) > 3:
         raise EmitError(f"{len(dd)} domain dims: more than 3 are not supported")
-    if "thread_core_data.var_" in text:
-        raise EmitError("scratch vars are not supported by this emitter")
     for v in ir["vars"]:
         n = v["name"]
-        m = re.search(rf"const idx_t {n}_alloc_t = (\d+);", text)
+        m = re.search(rf"const idx_t {n}_alloc_{step_dim} = (\d+);", text)
         v["alloc_t"] = int(m.group(1)) if m else 1
         m = re.search(rf"const int {n}_l1_norm = (\d+);", text)
         v["l1_norm"] = int(m.group(1)) if m else 0
@@ -287,34 +308,42 @@ def parse_generated(text: str, name: str) -> dict:
     vindex = {v["name"]: i for i, v in enumerate(ir["vars"])}
     # ---- stages / parts ---------------------------------------------------------------------------------
     stage_pos = [(m.start(), m.group(1)) for m in re.finditer(r"//////// Stencil stage '(\w+)' //////", text)]
-    part_iter = list(re.finditer(r"////// Stencil part '(\w+)' ([^\n]*?)//////", text))
+    part_iter = list(re.finditer(r"////// Stencil (scratch )?part '(\w+)' ([^\n]*?)//////", text))
     if not part_iter:
         raise EmitError("no parts found")
+    # scratch parts hang off the non-scratch parts that need them, in evaluation order
+    # (StencilPartBase::get_reqd_parts, /root/reference/src/kernel/lib/stencil_calc.cpp:74-77)
+    children: dict = {}
+    for m in re.finditer(r"^\s*(\w+)\.add_scratch_child\(&(\w+)\);", text, re.M):
+        children.setdefault(m.group(1), []).append(m.group(2))
+    ir["scratch_parts"] = []
     for pm in part_iter:
-        pname, cond = pm.group(1), pm.group(2)
-        if "w/o step condition" not in cond:
-            raise EmitError(f"part '{pname}' has a step condition: not supported by this emitter")
+        is_scratch_part, pname, cond = bool(pm.group(1)), pm.group(2), pm.group(3)
+        has_step_cond = "w/o step condition" not in cond
         has_dom_cond = "w/o domain condition" not in cond
-        stage = [s for pos, s in stage_pos if pos < pm.start()][-1]
+        stage = None
+        if not is_scratch_part:
+            stage = [s for pos, s in stage_pos if pos < pm.start()][-1]
         body_start = text.index("static void calc_scalar(", pm.end())
         body_end = text.index("} // calc_scalar.", body_start)
         body = text[body_start:body_end]
         head = text[pm.end():body_start]
-        if re.search(r"_is_scratch = true", head):
-            raise EmitError(f"part '{pname}' is a scratch part: not supported by this emitter")
+        if bool(re.search(r"_is_scratch = true", head)) != is_scratch_part:
+            raise EmitError(f"part '{pname}': inconsistent scratch markers")
         dom_cond = None
         if has_dom_cond:
             mm = re.search(r"is_in_valid_domain\(.*?\n(?:.*?\n)*?\s*return (.*);", head)
             if not mm:
                 raise EmitError(f"part '{pname}': cannot find its sub-domain expression")
             dom_cond = parse_domain_cond(mm.group(1), dd)
-        part = {"name": pname, "stage": stage, "cond": dom_cond,
+        part = {"name": pname, "stage": stage, "cond": dom_cond, "scratch": is_scratch_part, "children": children.get(pname, []),
                 "fp_ops": int(re.search(r"_scalar_fp_ops = (\d+);", head).group(1)),
                 "reads": int(re.search(r"_scalar_points_read = (\d+);", head).group(1)),
                 "writes": int(re.search(r"_scalar_points_written = (\d+);", head).group(1)),
                 "accesses": [], "stmts": [], "outputs": []}
         ptr = {}   # expr_tempN (pointer) -> var name
-        for m in re.finditer(r"auto\* (expr_temp\d+) = core_data->var_(\w+)_core_p\.get\(\);", body):
+        ptr_re = r"auto\* (expr_temp\d+) = (?:core_data->|thread_core_data\.)var_(\w+)_core_p\.get\(\);"
+        for m in re.finditer(ptr_re, body):
             ptr[m.group(1)] = m.group(2)
         acc_index: dict = {}
 
@@ -351,35 +380,89 @@ def parse_generated(text: str, name: str) -> dict:
                 part["accesses"].append({"var": var, "toff": toff, "misc": misc})
             return acc_index[key], [offs.get(d, 0) for d in dd]
 
+        READ_RE = r"(expr_temp\d+)->read_elem\(\{([^}]*)\}, \w+\)"
+
+        def tmp_name(tok: str) -> str:
+            """expr_temp12 -> e12, arg0_temp3 -> a0_3, res_temp14 -> r14 (names of the generated scalars)"""
+            m = re.fullmatch(r"(expr|res|arg(\d+))_temp(\d+)", tok)
+            return {"expr": "e", "res": "r"}.get(m.group(1), f"a{m.group(2)}_") + m.group(3)
+
+        def parse_rhs(rhs_text: str):
+            reads = []
+
+            def repl(mm):
+                a, offs = access(ptr[mm.group(1)], mm.group(2))
+                reads.append((a, offs))
+                return f"@{len(reads) - 1}"
+
+            return Parser(re.sub(READ_RE, repl, rhs_text)).parse(), reads
+
+        # step condition (IF_STEP): a boolean over the step index and, possibly, elements of (misc-dim) vars;
+        # evaluated inside the kernel so that conditions on var contents need no host round trip
+        if has_step_cond:
+            mm = re.search(r"is_in_valid_step\(.*?\n((?:.*?\n)*?)\s*return (.*);", head)
+            if not mm:
+                raise EmitError(f"part '{pname}': cannot find its step-condition expression")
+            sc_ptr = {m.group(1): m.group(2) for m in re.finditer(ptr_re, mm.group(1))}   # its own temp numbering
+            sc_reads = []
+
+            def sc_repl(m2):
+                a, offs = access(sc_ptr[m2.group(1)], m2.group(2))
+                sc_reads.append((a, offs))
+                return f"@{len(sc_reads) - 1}"
+
+            ctext = re.sub(READ_RE, sc_repl, mm.group(2))
+            ctext = re.sub(rf"(?<![\w@]){step_dim}(?!\w)", "GT", ctext)
+            left = re.sub(r"@\d+|GT|\d+(?:\.\d*)?(?:[eE][-+]?\d+)?|[-+*/%()<>=!&| ]", "", ctext)
+            if left:
+                raise EmitError(f"unsupported token(s) '{left}' in step condition of part '{pname}'")
+            part["step_cond"] = {"expr": ctext, "reads": sc_reads,
+                                 "text": re.search(r"w/step condition '(.*)'", cond).group(1)}
+
         for line in body.splitlines():
             line = line.strip()
             if not line or line.startswith("//"):
                 continue
-            m = re.fullmatch(r"real_t (expr_temp\d+) = (.*);", line)
+            m = re.fullmatch(r"real_t ((?:arg\d+|res|expr)_temp\d+) = (.*);", line)
             if m:
-                reads = []
-
-                def repl(mm):
-                    a, offs = access(ptr[mm.group(1)], mm.group(2))
-                    reads.append((a, offs))
-                    return f"@{len(reads) - 1}"
-
-                rhs = re.sub(r"(expr_temp\d+)->read_elem\(\{([^}]*)\}, \w+\)", repl, m.group(2))
-                tree = Parser(rhs).parse()
-                part["stmts"].append({"dst": int(m.group(1)[len("expr_temp"):]), "tree": tree, "reads": reads})
+                if re.fullmatch(r"arg\d+_temp\d+", m.group(1)) and m.group(2).strip() == "0":
+                    continue        # declaration of a multi-result function's output (set by the call below)
+                tree, reads = parse_rhs(m.group(2))
+                part["stmts"].append({"dst": tmp_name(m.group(1)), "tree": tree, "reads": reads})
                 continue
-            m = re.fullmatch(r"(expr_temp\d+)->write_elem\((expr_temp\d+), \{([^}]*)\}, \w+\);", line)
+            m = re.fullmatch(r"yask_(cos_and_sin|sin_and_cos)\((arg\d+_temp\d+), (arg\d+_temp\d+), (.*)\);", line)
+            if m:
+                tree, reads = parse_rhs(m.group(4))
+                first, second = tmp_name(m.group(2)), tmp_name(m.group(3))
+                cs = (first, second) if m.group(1) == "cos_and_sin" else (second, first)
+                part["stmts"].append({"kind": "sincos", "cos": cs[0], "sin": cs[1], "tree": tree, "reads": reads})
+                continue
+            m = re.fullmatch(r"(expr_temp\d+)->write_elem\(((?:arg\d+|res|expr)_temp\d+), \{([^}]*)\}, \w+\);", line)
             if m:
                 a, offs = access(ptr[m.group(1)], m.group(3))
                 if any(offs):
                     raise EmitError("write with a spatial offset is not supported")
-                part["outputs"].append({"access": a, "src": int(m.group(2)[len("expr_temp"):])})
+                part["outputs"].append({"access": a, "src": tmp_name(m.group(2))})
                 continue
             if re.match(r"(static void calc_scalar|host_assert|auto& thread_core_data|idx_t \w+ = idxs|auto\* expr_temp|const auto step_temp)", line):
                 continue
             raise EmitError(f"unrecognised statement in calc_scalar of {pname}: {line[:120]}")
         if not part["outputs"]:
             raise EmitError(f"part {pname} writes nothing")
+        if is_scratch_part:
+            # write halo = largest halo of the scratch vars it writes (find_scratch_write_halos, setup.cpp:1182-1228)
+            vmap = {v["name"]: v for v in ir["vars"]}
+            wh = [[0, 0] for _ in dd]
+            for o in part["outputs"]:
+                ov = vmap[part["accesses"][o["access"]]["var"]]
+                if not ov["scratch"]:
+                    raise EmitError(f"scratch part '{pname}' writes the non-scratch var '{ov['name']}'")
+                for i, d in enumerate(dd):
+                    h = ov["halo"].get(d, [0, 0])
+                    wh[i] = [max(wh[i][0], h[0]), max(wh[i][1], h[1])]
+            part["wh"] = wh
+            ir["scratch_parts"].append(part)
+            continue
         st = next((s for s in ir["stages"] if s["name"] == stage), None)
         if st is None:
             st = {"name": stage, "parts": []}
@@ -400,7 +483,9 @@ def gen_expr(tree, rd, ops) -> str:
     if k == "const":
         return f"C({_const_text(tree[1])})"
     if k == "tmp":
-        return f"e{tree[1]}"
+        return tree[1]
+    if k == "call":
+        return f"YF_{tree[1]}(" + ", ".join(gen_expr(a, rd, ops) for a in tree[2]) + ")"
     if k == "read":
         return rd(tree[1])
     if k == "neg":
@@ -409,17 +494,88 @@ def gen_expr(tree, rd, ops) -> str:
     return f"{ops[k]}({a}, {b})"
 
 
+OPS = {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'}
+
+
+def _rd_text(a, offs, masks):
+    offs = [0] * (3 - len(offs)) + list(offs)     # domain dims are right-aligned into the kernel's (x,y,z) slots
+    return f"RD({a}, {masks[a]}, {offs[0]}, {offs[1]}, {offs[2]})"
+
+
 def _stmt_lines(part, ndd, indent="    ", masks=None):
     out = []
     for s in part["stmts"]:
         def rd(i, s=s):
-            a, offs = s["reads"][i]
-            offs = [0] * (3 - len(offs)) + list(offs)     # domain dims are right-aligned into the kernel's (x,y,z) slots
-            return f"RD({a}, {masks[a]}, {offs[0]}, {offs[1]}, {offs[2]})"
-        out.append(f"{indent}const T e{s['dst']} = {gen_expr(s['tree'], rd, {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'})};")
+            return _rd_text(*s["reads"][i], masks)
+        if s.get("kind") == "sincos":
+            out.append(f"{indent}T {s['sin']}, {s['cos']};")
+            out.append(f"{indent}YF_sincos({gen_expr(s['tree'], rd, OPS)}, {s['sin']}, {s['cos']});")
+            continue
+        out.append(f"{indent}const T {s['dst']} = {gen_expr(s['tree'], rd, OPS)};")
     for o in part["outputs"]:
-        out.append(f"{indent}WR({o['access']}, {masks[o['access']]}, e{o['src']});")
+        out.append(f"{indent}WR({o['access']}, {masks[o['access']]}, {o['src']});")
     return out
+
+
+def _cond_text(part, masks):
+    """C text of the part's combined sub-domain and step conditions (None if unconditional)."""
+    terms = []
+    if part.get("cond"):
+        terms.append(f"({part['cond']['expr']})")
+    sc = part.get("step_cond")
+    if sc:
+        terms.append("(" + re.sub(r"@(\d+)", lambda m: "(double)" + _rd_text(*sc["reads"][int(m.group(1))], masks), sc["expr"]) + ")")
+    return " && ".join(terms) if terms else None
+
+
+def _cond_comment(part):
+    c = []
+    if part.get("cond"):
+        c.append("sub-domain: " + part["cond"]["text"])
+    if part.get("step_cond"):
+        c.append("step condition: " + part["step_cond"]["text"])
+    return "; ".join(c)
+
+
+def _all_parts(ir):
+    """Every part in evaluation order: (stage name or None, part).  Scratch parts first (table order = index)."""
+    return [(None, p) for p in ir.get("scratch_parts", [])] + [(st["name"], p) for st in ir["stages"] for p in st["parts"]]
+
+
+def _stage_sequence(ir, st):
+    """Evaluation order of one stage: each part preceded by the scratch parts it requires that have not been
+    evaluated yet in this stage (parts_done, /root/reference/src/kernel/lib/stencil_calc.cpp:118-127)."""
+    smap = {p["name"]: p for p in ir.get("scratch_parts", [])}
+    svars = {v["name"] for v in ir["vars"] if v.get("scratch")}
+
+    def reads_of(p):
+        outs = {o["access"] for o in p["outputs"]}
+        return {a["var"] for i, a in enumerate(p["accesses"]) if i not in outs and a["var"] in svars}
+
+    def writes_of(p):
+        return {p["accesses"][o["access"]]["var"] for o in p["outputs"]}
+
+    seq, done = [], set()
+    for p in st["parts"]:
+        # The reference lists every scratch part a part depends on, directly or through OTHER NON-SCRATCH parts; only
+        # those reachable through scratch vars are needed to evaluate it (the others were evaluated for the part that
+        # reads them), so the rest is skipped here.
+        needed, frontier = set(), reads_of(p)
+        while frontier:
+            needed |= frontier
+            nxt = set()
+            for c in p.get("children", []):
+                if writes_of(smap[c]) & frontier:
+                    nxt |= reads_of(smap[c]) - needed
+            frontier = nxt
+        for c in p.get("children", []):
+            if not (writes_of(smap[c]) & needed):
+                continue
+            if c not in done:
+                done.add(c)
+                seq.append(smap[c])
+        seq.append(p)
+    return seq
 
 
 def _masks(ir, part):
@@ -449,19 +605,21 @@ def emit_cuda(ir: dict) -> str:
     L.append("#pragma once")
     L.append('#include "../yb_gen.cuh"')
     L.append("namespace yb { namespace gen {")
-    for st in ir["stages"]:
-        for p in st["parts"]:
-            L.append(f"// part '{p['name']}' of stage '{st['name']}': {p['fp_ops']} FP ops, {p['reads']} reads, {p['writes']} writes per point")
-            L.append("template <typename T, int MODE>")
-            L.append(f"__global__ void __launch_bounds__(GEN_BLOCK) {ident}_{p['name']}_kernel(const __grid_constant__ GenParams P) {{")
-            L.append("    GEN_KERNEL_BEGIN")
-            if p.get("cond"):
-                L.append(f"    if ({p['cond']['expr']}) {{   // sub-domain: {p['cond']['text']}")
-            L.extend(_stmt_lines(p, len(ir["domain_dims"]), masks=_masks(ir, p)))
-            if p.get("cond"):
-                L.append("    }")
-            L.append("    GEN_KERNEL_END")
-            L.append("}")
+    for stname, p in _all_parts(ir):
+        where = f"of stage '{stname}'" if stname else "(scratch: evaluated over the box expanded by its write halo, before the parts that read it)"
+        L.append(f"// part '{p['name']}' {where}: {p['fp_ops']} FP ops, {p['reads']} reads, {p['writes']} writes per point")
+        L.append("template <typename T, int MODE>")
+        L.append(f"__global__ void __launch_bounds__(GEN_BLOCK) {ident}_{p['name']}_kernel(const __grid_constant__ GenParams P) {{")
+        L.append("    GEN_KERNEL_BEGIN")
+        masks = _masks(ir, p)
+        ct = _cond_text(p, masks)
+        if ct:
+            L.append(f"    if ({ct}) {{   // {_cond_comment(p)}")
+        L.extend(_stmt_lines(p, len(ir["domain_dims"]), masks=masks))
+        if ct:
+            L.append("    }")
+        L.append("    GEN_KERNEL_END")
+        L.append("}")
     # spec table
     L.append(f"inline void {ident}_describe(GenStencil& g) {{")
     L.append(f'    g.name = "{n}"; g.elem_bytes = {ir["elem_bytes"]}; g.step_dim = "{ir["step_dim"]}";')
@@ -473,11 +631,12 @@ def emit_cuda(ir: dict) -> str:
         mr = v.get("misc_range", {})
         mf = ", ".join(str(mr[d][0]) if d in mr else "0" for d in v["dims"])
         ms = ", ".join(str(mr[d][1] - mr[d][0] + 1) if d in mr else "0" for d in v["dims"])
-        L.append(f'    g.vars.push_back(GenVar{{"{v["name"]}", {{{dims}}}, {v["alloc_t"]}, {str(v["is_output"]).lower()}, {v["l1_norm"]}, {{{hl}}}, {{{hr}}}, {{{mf}}}, {{{ms}}}}});')
+        L.append(f'    g.vars.push_back(GenVar{{"{v["name"]}", {{{dims}}}, {v["alloc_t"]}, {str(v["is_output"]).lower()}, {v["l1_norm"]}, {{{hl}}}, {{{hr}}}, {{{mf}}}, {{{ms}}}, {str(bool(v.get("scratch"))).lower()}}});')
     vidx = {v["name"]: i for i, v in enumerate(ir["vars"])}
+    sh = 3 - len(ir["domain_dims"])
     for st in ir["stages"]:
         L.append(f'    g.stages.push_back(GenStage{{"{st["name"]}", {{}}}});')
-        for p in st["parts"]:
+        for p in _stage_sequence(ir, st):
             acc = ", ".join("{%d, %d, {%s}}" % (vidx[a["var"]], a["toff"], ", ".join(str(m) for m in (a.get("misc", []) + [0, 0])[:2])) for a in p["accesses"])
             outs = ", ".join(str(o["access"]) for o in p["outputs"])
             k = f"{ident}_{p['name']}_kernel"
@@ -488,7 +647,12 @@ def emit_cuda(ir: dict) -> str:
             for d in range(3):
                 lo, hi = bnds.get(str(d), [None, None])
                 bl.append(f"{{{kind[lo[0]] if lo else -1}, {lo[1] if lo else 0}, {kind[hi[0]] if hi else -1}, {hi[1] if hi else 0}}}")
-            L.append(f'    g.stages.back().parts.push_back(GenPart{{"{p["name"]}", {p["fp_ops"]}, {p["reads"]}, {p["writes"]}, {{{acc}}}, {{{outs}}}, {fns}, {{{", ".join(bl)}}}}});')
+            wh = [[0, 0]] * sh + (p.get("wh") or [[0, 0]] * len(ir["domain_dims"]))     # right-aligned into the (x,y,z) slots
+            whl = ", ".join(str(w[0]) for w in wh)
+            whr = ", ".join(str(w[1]) for w in wh)
+            conditional = str(bool(p.get("cond") or p.get("step_cond"))).lower()
+            L.append(f'    g.stages.back().parts.push_back(GenPart{{"{p["name"]}", {p["fp_ops"]}, {p["reads"]}, {p["writes"]}, {{{acc}}}, {{{outs}}}, {fns}, {{{", ".join(bl)}}}, '
+                     f'{str(p["scratch"]).lower()}, {conditional}, {{{whl}}}, {{{whr}}}}});')
     L.append("}")
     L.append("} }  // namespace yb::gen")
     return "\n".join(L) + "\n"
@@ -504,22 +668,22 @@ def emit_oracle(ir: dict) -> str:
     L.append(" * calc_scalar()), evaluated as the reference's VECTOR path does: constants rounded to the element")
     L.append(" * type, every operation in the element type, no contraction (compile with -ffp-contract=off).")
     L.append(" * Pinned against the reference built with -ffp-contract=off (tests/golden). */")
-    for st in ir["stages"]:
-        for p in st["parts"]:
-            L.append(f"static void yo_{ident}_{p['name']}(const yo_gen_args* A) {{")
-            L.append(f"    typedef {T} T;")
-            L.append("    YO_GEN_LOOP_BEGIN")
-            if p.get("cond"):
-                L.append(f"        if ({p['cond']['expr']}) {{   /* sub-domain: {p['cond']['text']} */")
-            L.extend(_stmt_lines(p, len(ir["domain_dims"]), indent="        ", masks=_masks(ir, p)))
-            if p.get("cond"):
-                L.append("        }")
-            L.append("    YO_GEN_LOOP_END")
-            L.append("}")
+    for _, p in _all_parts(ir):
+        L.append(f"static void yo_{ident}_{p['name']}(const yo_gen_args* A) {{")
+        L.append(f"    typedef {T} T;")
+        L.append("    YO_GEN_LOOP_BEGIN")
+        masks = _masks(ir, p)
+        ct = _cond_text(p, masks)
+        if ct:
+            L.append(f"        if ({ct}) {{   /* {_cond_comment(p)} */")
+        L.extend(_stmt_lines(p, len(ir["domain_dims"]), indent="        ", masks=masks))
+        if ct:
+            L.append("        }")
+        L.append("    YO_GEN_LOOP_END")
+        L.append("}")
     L.append(f"static const yo_gen_part yo_{ident}_parts[] = {{")
-    for st in ir["stages"]:
-        for p in st["parts"]:
-            L.append(f'    {{"{p["name"]}", yo_{ident}_{p["name"]}, {len(p["accesses"])}}},')
+    for _, p in _all_parts(ir):
+        L.append(f'    {{"{p["name"]}", yo_{ident}_{p["name"]}, {len(p["accesses"])}}},')
     L.append("};")
     return "\n".join(L) + "\n"
 
@@ -551,6 +715,16 @@ def write_registry():
 
 
 def main(argv=None):
+    if argv is None and "--all" in sys.argv[1:]:
+        # re-emit every solution of the manifest (after an emitter change)
+        man = json.load(open(os.path.join(ROOT, "yask_b200", "csrc", "gen", "manifest.json")))
+        for name, m in sorted(man.items()):
+            args = ["--stencil", m["stencil"], "--elem-bytes", str(m["elem_bytes"]), "--name", name, "--no-registry"]
+            if m.get("radius"):
+                args += ["--radius", str(m["radius"])]
+            main(args)
+        write_registry()
+        return
     ap = argparse.ArgumentParser()
     ap.add_argument("--stencil", required=True)
     ap.add_argument("--elem-bytes", type=int, default=4)
@@ -573,9 +747,17 @@ def main(argv=None):
     open(os.path.join(gdir, f"{ident}.gen.cuh"), "w").write(emit_cuda(ir))
     open(os.path.join(odir, f"{ident}.gen.h"), "w").write(emit_oracle(ir))
     slim = {k: v for k, v in ir.items() if k != "stages"}
-    slim["stages"] = [{"name": s["name"], "parts": [{"name": p["name"], "fp_ops": p["fp_ops"], "reads": p["reads"], "writes": p["writes"],
-                                                       "accesses": p["accesses"], "outputs": p["outputs"], "cond": p.get("cond")} for p in s["parts"]]}
-                      for s in ir["stages"]]
+    slim = {k: v for k, v in slim.items() if k != "scratch_parts"}
+    table = [p["name"] for _, p in _all_parts(ir)]      # index of a part in the oracle's function table
+
+    def slim_part(p):
+        return {"name": p["name"], "index": table.index(p["name"]), "fp_ops": p["fp_ops"], "reads": p["reads"], "writes": p["writes"],
+                "accesses": p["accesses"], "outputs": p["outputs"], "cond": p.get("cond"), "scratch": p["scratch"], "wh": p.get("wh"),
+                "conditional": bool(p.get("cond") or p.get("step_cond")),
+                "step_cond": (p.get("step_cond") or {}).get("text")}
+
+    # "parts" of a stage = its evaluation sequence (required scratch parts first)
+    slim["stages"] = [{"name": s["name"], "parts": [slim_part(p) for p in _stage_sequence(ir, s)]} for s in ir["stages"]]
     json.dump(slim, open(os.path.join(gdir, f"{name}.json"), "w"), indent=1)
     mpath = os.path.join(gdir, "manifest.json")
     man = json.load(open(mpath)) if os.path.exists(mpath) else {}
