@@ -90,3 +90,42 @@ def test_reference_kernel_api_test_passes_unmodified(stencil):
 def test_reference_kernel_api_exception_test_passes_unmodified():
     r = subprocess.run([_bin("ref_kernel_api_exception_test.iso3dfd")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])
+
+
+# ---- command-line harness (yask_b200/csrc/yk_main.cpp -> yask_b200/bin/yask_kernel.<stencil>.b200.exe) -----------
+def _exe(stencil):
+    p = os.path.join(ROOT, "yask_b200", "bin", f"yask_kernel.{stencil}.b200.exe")
+    if not os.path.exists(p):
+        pytest.skip("harness not built (run __graft_entry__.build())")
+    return p
+
+
+def test_harness_help_and_loud_failure_without_device():
+    r = subprocess.run([_exe("iso3dfd"), "-help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "-trial_steps" in r.stdout and "-g<dim>" in r.stdout
+    from yask_b200 import capi
+    if capi.device_count() == 0:
+        r = subprocess.run([_exe("iso3dfd"), "-g", "64"], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CUDA device" in r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("stencil,args", [("iso3dfd", ["-g", "128"]), ("awp_elastic", ["-g", "64"]), ("ssg", ["-gx", "48", "-gy", "40", "-gz", "64"])])
+def test_harness_prints_the_reference_report_keys(stencil, args):
+    """A reference-style command line (its CPU tuning flags included) runs and prints the report lines that
+    the reference's log scrapers key on (yask_main.cpp:513-536)."""
+    cmd = [_exe(stencil)] + args + ["-trial_steps", "4", "-num_trials", "3", "-no-pre_auto_tune", "-no-auto_tune", "-outer_threads", "8",
+                                    "-b", "64", "-sleep", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for key in ("num-trials:", "best-throughput (num-points/sec):", "mid-throughput (num-points/sec):", "best-elapsed-time (sec):",
+                "num-points-per-step:", "YASK DONE"):
+        assert key in r.stdout, key
+    line = [l for l in r.stdout.splitlines() if "best-num-steps-done" in l][0]
+    assert line.split()[-1] == "4"
+
+
+@pytest.mark.gpu
+def test_harness_validate_iso3dfd():
+    r = subprocess.run([_exe("iso3dfd"), "-g", "96", "-validate"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "TEST PASSED" in r.stdout, r.stdout + r.stderr

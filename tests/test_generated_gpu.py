@@ -13,6 +13,12 @@ from yask_b200.synth import hash_field, var_salt
 
 pytestmark = pytest.mark.gpu
 
+# Solutions that call DSL math functions: the reference evaluates them with the host libm, the kernels with CUDA's
+# device functions (documented max error 1-2 ulp for sin/cos/atan/cbrt in fp32), so these are compared within
+# MATH_ULPS field-ulps instead of bit for bit.
+MATH_FUNC_STENCILS = {"test_func_1d"}
+MATH_ULPS = 16.0
+
 
 def load_inputs(s, ins):
     for v in s.get_vars():
@@ -54,7 +60,9 @@ def test_generated_vs_reference_golden(path):
     for name, (tl, got) in out.items():
         ref = arrays[f"{name}.t{tl}"]
         assert got.shape == ref.shape and got.dtype == ref.dtype
-        if strict:
+        if meta["stencil"] in MATH_FUNC_STENCILS:
+            assert field_ulps(got, ref) <= MATH_ULPS, (name, field_ulps(got, ref))
+        elif strict:
             it = np.uint32 if got.dtype == np.float32 else np.uint64
             assert np.array_equal(got.view(it), ref.view(it)), name
         else:
@@ -66,6 +74,8 @@ def synth_inputs(stencil, n, seed):
     dt = np.float32 if ir["elem_bytes"] == 4 else np.float64
     ins = {}
     for v in ir["vars"]:
+        if v.get("scratch"):
+            continue      # engine-internal temporaries: not inputs
         lo, hi = range_of(RANGES[stencil], v["name"])
         vd = [d for d in v["dims"] if d != ir["step_dim"]]
         mr = v.get("misc_range", {})
@@ -84,7 +94,14 @@ def synth_inputs(stencil, n, seed):
                                              ("tti", (18, 20, 66), 2), ("3axis", (30, 20, 100), 3), ("iso3dfd_sponge", (20, 24, 80), 2),
                                              ("awp_elastic_abc", (19, 23, 40), 3), ("awp_abc", (16, 18, 37), 2),
                                              ("test_2d", (37, 150), 3), ("test_1d", (300,), 4), ("test_boundary_3d", (20, 20, 70), 3),
-                                             ("ssg2", (20, 18, 50), 2), ("fsg2", (14, 12, 40), 2)])
+                                             ("ssg2", (20, 18, 50), 2), ("fsg2", (14, 12, 40), 2),
+                                             # scratch vars (write halos), step conditions, reverse time, stages
+                                             ("test_scratch_3d", (20, 18, 70), 3), ("test_scratch_2d", (40, 150), 3),
+                                             ("test_scratch_1d", (300,), 3), ("test_scratch_boundary_1d", (300,), 3),
+                                             ("test_scratch_stages_1d", (200,), 3), ("test_step_cond_1d", (200,), 5),
+                                             ("test_reverse_2d", (37, 150), 3), ("test_stages_3d", (18, 20, 66), 3),
+                                             ("test_partial_3d", (20, 18, 70), 2), ("gaussian_filter", (60, 150), 3),
+                                             ("wave2d", (40, 150), 3), ("swe2d", (40, 150), 3)])
 def test_generated_vs_oracle_ragged(stencil, n, steps):
     ins, ir = synth_inputs(stencil, n, 31)
     out, _ = run_gpu(stencil, n, steps, ins, 0)
@@ -103,7 +120,11 @@ def test_generated_vs_oracle_ragged(stencil, n, steps):
                                                    ("awp", (32, 24, 48), (2, 2, 1), 2), ("tti", (36, 36, 48), (2, 2, 2), 2),
                                                    ("cube", (32, 32, 64), (2, 2, 2), 2),
                                                    ("awp_elastic_abc", (24, 24, 40), (2, 1, 2), 3), ("awp_abc", (24, 20, 36), (1, 2, 3), 2),
-                                                   ("ssg2", (32, 24, 40), (2, 2, 1), 2), ("test_2d", (64, 96), (2, 2), 3)])
+                                                   ("ssg2", (32, 24, 40), (2, 2, 1), 2), ("test_2d", (64, 96), (2, 2), 3),
+                                                   # scratch parts are evaluated over boxes expanded into the exchanged halos
+                                                   ("test_scratch_3d", (32, 24, 48), (2, 2, 2), 3), ("test_scratch_2d", (64, 96), (2, 2), 3),
+                                                   ("test_scratch_boundary_1d", (256,), (4,), 3), ("test_stages_2d", (64, 96), (2, 2), 3),
+                                                   ("wave2d", (64, 96), (2, 2), 3), ("swe2d", (48, 64), (2, 2), 3)])
 def test_generated_rank_grid_matches_single_rank(stencil, n, grid, steps):
     """Two-stage solutions exchange halos after each stage; static vars (rho, mu, ...) are exchanged once."""
     ir = O.gen_ir(stencil)

@@ -547,7 +547,7 @@ struct B200Solution : yk_solution {
                     for (auto& d : dims) if (key == ps + d) { idx_t v = atoll(take().c_str()); if (ps == "b") block_size[d] = v; used = true; break; }
                     if (used) break;
                 }
-                if (!used) for (const char* k : {"fp_mode", "kernel", "tile", "lx", "grid"})
+                if (!used) for (const char* k : {"fp_mode", "kernel", "tile", "lx", "grid", "gen_pf", "gen_l2_mb", "fused_halo"})
                     if (key == k) { std::string v = take(); chk(yb_set_option(h->s, k, v.c_str())); used = true; break; }
                 if (!used && key == "device") { device = atoi(take().c_str()); used = true; }
             }

@@ -1,0 +1,195 @@
+// Command-line harness for one solution: the B200 counterpart of the reference's kernel driver
+// (/root/reference/src/kernel/yask_main.cpp), built as bin/yask_kernel.<stencil>.b200.exe.  It uses ONLY the
+// public kernel API (yask_kernel_api.hpp), accepts the reference's command lines (its CPU-tuning options are
+// recognised and ignored by apply_command_line_options) and prints the same "key: value" report lines
+// (yask_main.cpp:513-536, soln_apis.cpp:455-470), so log scrapers written for the reference keep working.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <vector>
+
+#include "yask_kernel_api.hpp"
+
+using namespace yask;
+
+namespace {
+
+const char* DIV = "───────────────────────────────────────────────────────────\n";
+
+// engineering notation as the reference prints it ("3.12G", "17.2M"; common_utils.cpp make_num_str)
+std::string num_str(double v) {
+    static const char* sfx[] = {"", "K", "M", "G", "T", "P"};
+    int k = 0;
+    double a = std::fabs(v);
+    while (a >= 1000. && k < 5) { a /= 1000.; v /= 1000.; k++; }
+    std::ostringstream os;
+    os << std::setprecision(4) << v << sfx[k];
+    return os.str();
+}
+
+struct Trial { idx_t nsteps; double secs, pts_ps, reads_ps, writes_ps, flops; };
+
+void usage(const char* exe, yk_solution_ptr soln) {
+    std::cout << "Usage: " << exe << " [options]\n"
+              << " -h | -help              this text\n"
+              << " -trial_steps <n>        steps per performance trial (default 50)\n"
+              << " -num_trials <n>         number of trials (default 3)\n"
+              << " -warmup_steps <n>       untimed steps before the trials (default 5)\n"
+              << " -init_val <x>           value every var is initialised to (default 0.1, var k gets x*(1+k/16))\n"
+              << " -validate               iso3dfd only: cross-check the tiled kernel against the direct kernel on the device\n"
+              << "Solution options:\n" << soln->get_command_line_help();
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    try {
+        yk_factory kfac;
+        auto env = kfac.new_env();
+        auto soln = kfac.new_solution(env);
+        std::cout << "YASK-compatible kernel harness, solution '" << soln->get_name() << "', target " << soln->get_target()
+                  << ", " << soln->get_element_bytes() << "-byte elements, API version " << kfac.get_version_string() << "\n";
+
+        idx_t trial_steps = 50, num_trials = 3, warmup_steps = 5;
+        double init_val = 0.1;
+        bool validate = false;
+        // harness options first; everything else goes to the solution (as yask_main.cpp:199-259 does)
+        string_vec rest;
+        for (int i = 1; i < argc; i++) {
+            std::string a = argv[i];
+            auto val = [&]() -> std::string {
+                if (i + 1 >= argc) { std::cerr << "Error: no argument for option '" << a << "'\n"; std::exit(1); }
+                return argv[++i];
+            };
+            if (a == "-h" || a == "-help" || a == "--help") { usage(argv[0], soln); return 0; }
+            else if (a == "-trial_steps" || a == "-t") trial_steps = atoll(val().c_str());
+            else if (a == "-num_trials") num_trials = atoll(val().c_str());
+            else if (a == "-warmup_steps") warmup_steps = atoll(val().c_str());
+            else if (a == "-init_val" || a == "-init_seed") init_val = atof(val().c_str());
+            else if (a == "-trial_time" || a == "-sleep") val();      // reference options with no meaning here
+            else if (a == "-validate" || a == "-v") validate = true;
+            else rest.push_back(a);
+        }
+        std::string unused = soln->apply_command_line_options(rest);
+        if (!unused.empty()) { std::cerr << "Error: extraneous parameter(s): '" << unused << "'; run with '-help' for usage.\n"; return 1; }
+        if (trial_steps < 1 || num_trials < 1) { std::cerr << "Error: -trial_steps and -num_trials must be positive.\n"; return 1; }
+
+        soln->prepare_solution();
+        auto dims = soln->get_domain_dim_names();
+        idx_t pts = 1;
+        std::cout << DIV << "Problem:\n";
+        std::ostringstream gs, ls;
+        for (auto& d : dims) {
+            gs << (gs.str().empty() ? "" : " * ") << d << "=" << soln->get_overall_domain_size(d);
+            ls << (ls.str().empty() ? "" : " * ") << d << "=" << soln->get_rank_domain_size(d);
+            pts *= soln->get_rank_domain_size(d);
+        }
+        std::cout << " global-domain-size:     " << gs.str() << "\n"
+                  << " local-domain-size:      " << ls.str() << "\n"
+                  << " num-ranks:              " << env->get_num_ranks() << "\n"
+                  << " num-points-per-step:    " << num_str(double(pts)) << "\n";
+
+        // data: every var constant, slightly different per var (the reference's init_same pattern)
+        int k = 0;
+        for (auto& v : soln->get_vars()) v->set_all_elements_same(init_val * (1.0 + double(k++) / 16.0));
+
+        if (validate) {
+            if (soln->get_name() != "iso3dfd" || soln->get_element_bytes() != 4) {
+                std::cerr << "Error: -validate needs an independent implementation of the solution; this build has one for iso3dfd "
+                             "fp32 only (the direct kernel).  The parity tests (tests/, CPU oracle + reference fixtures) cover the rest.\n";
+                return 1;
+            }
+            // the same steps with the sweep kernel and with the one-thread-per-point kernel must agree bit for bit
+            auto p = soln->get_var("p");
+            auto other = kfac.new_solution(env, soln);
+            other->apply_command_line_options("-kernel direct");
+            other->prepare_solution();
+            k = 0;
+            for (auto& v : other->get_vars()) v->set_all_elements_same(init_val * (1.0 + double(k++) / 16.0));
+            // a bump in the middle so that the field is not constant
+            idx_t_vec mid;
+            mid.push_back(0);
+            for (auto& d : dims) mid.push_back(soln->get_overall_domain_size(d) / 2);
+            p->set_element(1.0, mid);
+            other->get_var("p")->set_element(1.0, mid);
+            const idx_t vsteps = std::min<idx_t>(trial_steps, 4);
+            soln->run_solution(0, vsteps - 1);
+            other->run_solution(0, vsteps - 1);
+            auto q = other->get_var("p");
+            idx_t tl = p->get_last_valid_step_index();
+            idx_t_vec f{tl}, l{tl};
+            for (auto& d : dims) { f.push_back(p->get_first_rank_domain_index(d)); l.push_back(p->get_last_rank_domain_index(d)); }
+            const size_t np = size_t(pts);
+            std::vector<float> a(np), b(np);
+            p->get_elements_in_slice(a.data(), a.size(), f, l);
+            q->get_elements_in_slice(b.data(), b.size(), f, l);
+            idx_t bad = 0;
+            for (size_t i = 0; i < a.size(); i++) bad += a[i] != b[i];
+            other->end_solution();
+            std::cout << DIV << (bad ? "TEST FAILED: " : "TEST PASSED: ") << bad << " mismatch(es) between the sweep and the direct kernel over "
+                      << vsteps << " step(s).\n";
+            soln->end_solution();
+            return bad ? 1 : 0;
+        }
+
+        if (warmup_steps > 0) soln->run_solution(0, warmup_steps - 1);
+        idx_t first_t = warmup_steps;
+        std::vector<Trial> trials;
+        for (idx_t tr = 0; tr < num_trials; tr++) {
+            soln->clear_stats();
+            soln->run_solution(first_t, first_t + trial_steps - 1);
+            first_t += trial_steps;
+            auto st = soln->get_stats();      // waits for the device
+            Trial t;
+            t.nsteps = st->get_num_steps_done();
+            t.secs = st->get_elapsed_secs();
+            t.pts_ps = double(st->get_num_elements()) * double(t.nsteps) / t.secs;
+            t.writes_ps = double(st->get_num_writes_done()) / t.secs;
+            t.reads_ps = 0.;
+            t.flops = double(st->get_est_fp_ops_done()) / t.secs;
+            trials.push_back(t);
+            std::cout << DIV << "Trial " << (tr + 1) << ":\n"
+                      << " num-steps-done:               " << t.nsteps << "\n"
+                      << " elapsed-time (sec):           " << num_str(t.secs) << "\n"
+                      << " throughput (num-writes/sec):  " << num_str(t.writes_ps) << "\n"
+                      << " throughput (est-FLOPS):       " << num_str(t.flops) << "\n"
+                      << " throughput (num-points/sec):  " << num_str(t.pts_ps) << "\n";
+        }
+        std::vector<Trial> sorted = trials;
+        std::sort(sorted.begin(), sorted.end(), [](const Trial& a, const Trial& b) { return a.pts_ps > b.pts_ps; });
+        const Trial& best = sorted.front();
+        const Trial& mid = sorted[sorted.size() / 2];
+        double sum = 0, sum2 = 0;
+        for (auto& t : trials) { sum += t.pts_ps; sum2 += t.pts_ps * t.pts_ps; }
+        const double n = double(trials.size());
+        const double sd = n > 2 ? std::sqrt(std::max(0., (sum2 - sum * sum / n) / (n - 1.))) : 0.;
+        std::cout << DIV << "Throughput stats across trials:\n"
+                  << " num-trials:                          " << trials.size() << "\n"
+                  << " min-throughput (num-points/sec):     " << num_str(sorted.back().pts_ps) << "\n"
+                  << " max-throughput (num-points/sec):     " << num_str(best.pts_ps) << "\n"
+                  << " ave-throughput (num-points/sec):     " << num_str(sum / n) << "\n"
+                  << " std-dev-throughput (num-points/sec): " << num_str(sd) << "\n"
+                  << DIV << "Performance stats of best trial:\n"
+                  << " best-num-steps-done:              " << best.nsteps << "\n"
+                  << " best-elapsed-time (sec):          " << num_str(best.secs) << "\n"
+                  << " best-throughput (num-writes/sec): " << num_str(best.writes_ps) << "\n"
+                  << " best-throughput (est-FLOPS):      " << num_str(best.flops) << "\n"
+                  << " best-throughput (num-points/sec): " << num_str(best.pts_ps) << "\n"
+                  << DIV << "Performance stats of 50th-percentile trial:\n"
+                  << " mid-num-steps-done:               " << mid.nsteps << "\n"
+                  << " mid-elapsed-time (sec):           " << num_str(mid.secs) << "\n"
+                  << " mid-throughput (num-writes/sec):  " << num_str(mid.writes_ps) << "\n"
+                  << " mid-throughput (est-FLOPS):       " << num_str(mid.flops) << "\n"
+                  << " mid-throughput (num-points/sec):  " << num_str(mid.pts_ps) << "\n";
+        soln->end_solution();
+        env->finalize();
+        std::cout << "YASK DONE\n";
+        return 0;
+    } catch (yask_exception& e) {
+        std::cerr << "YASK kernel harness: " << e.get_message() << "\n";
+        return 1;
+    }
+}
