@@ -162,6 +162,10 @@ int yb_var_get_slice(yb_solution* s, int var, void* host_buf, const int64_t* fir
 /* Same, but the buffer is DEVICE memory on the solution's device (no host round trip). */
 int yb_var_set_slice_device(yb_solution* s, int var, const void* dev_buf, const int64_t* first, const int64_t* last, int64_t* n_done);
 int yb_var_get_slice_device(yb_solution* s, int var, void* dev_buf, const int64_t* first, const int64_t* last, int64_t* n_done);
+/* Reductions over a slice, on the device, accumulated in double in a fixed order: yk_var::reduce_elements_in_slice
+ * (aux/yk_var_api.hpp:984-1110; /root/reference/src/kernel/lib/yk_var.hpp:1367-1450).
+ * out = {sum, sum of squares, product, max, min}; *n_done = number of elements reduced (may be NULL). */
+int yb_var_reduce_slice(yb_solution* s, int var, const int64_t* first, const int64_t* last, double out[5], int64_t* n_done);
 /* set_all_elements_same (writes every storage element incl. pads, yk_var.hpp:1786-1793). */
 int yb_var_set_all_same(yb_solution* s, int var, double value);
 /* set_elements_in_slice_same. */

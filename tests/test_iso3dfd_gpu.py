@@ -125,6 +125,32 @@ def test_device_hash_fill_matches_numpy_generator():
     s.close()
 
 
+def test_device_reductions_match_numpy():
+    """yk_var::reduce_elements_in_slice on the device (double accumulation, fixed order): sum / sum of squares to
+    1e-12 relative, max / min exact, product on a small box; repeatable bit for bit."""
+    n = (40, 36, 100)
+    s = capi.Solution("iso3dfd")
+    s.set_overall_domain_size_vec(n)
+    s.prepare_solution(0)
+    p = s.get_var("p")
+    p.fill_hash(0, 5, var_salt("p", 0), -1.0, 1.0)
+    p.fill_hash(1, 5, var_salt("p", 1), 0.5, 1.5)
+    for first, last in (((0, 0, 0, 0), (0, 39, 35, 99)), ((0, -8, -8, -8), (1, 47, 43, 107)), ((1, 3, 5, 7), (1, 20, 9, 64)),
+                        ((1, 10, 10, 10), (1, 10, 10, 10))):
+        ref = np.concatenate([p.get_elements_in_slice((t,) + tuple(first[1:]), (t,) + tuple(last[1:])).astype(np.float64).ravel()
+                              for t in range(first[0], last[0] + 1)])
+        r = p.reduce_elements_in_slice(first, last)
+        assert r["num"] == ref.size
+        assert abs(r["sum"] - ref.sum()) <= 1e-12 * np.abs(ref).sum()
+        assert abs(r["sum_squares"] - (ref * ref).sum()) <= 1e-12 * (ref * ref).sum()
+        assert r["max"] == ref.max() and r["min"] == ref.min()
+        assert r == p.reduce_elements_in_slice(first, last)
+    small = ((1, 4, 4, 4), (1, 6, 6, 9))
+    ref = p.get_elements_in_slice(*small).astype(np.float64).ravel()
+    assert abs(p.reduce_elements_in_slice(*small)["product"] - np.prod(ref)) <= 1e-12 * abs(np.prod(ref))
+    s.close()
+
+
 @pytest.mark.parametrize("n,steps", [((256, 256, 256), 3), ((300, 130, 200), 2)])
 def test_tma_equals_direct_on_device_large(n, steps):
     """Size-independent property: both kernels evaluate the same expression tree, so their results

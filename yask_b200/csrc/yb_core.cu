@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "yb_core.h"
 #include "yb_halo.h"
@@ -541,6 +542,33 @@ int yb_var_set_slice_device(yb_solution* s, int var, const void* buf, const int6
 }
 int yb_var_get_slice_device(yb_solution* s, int var, void* buf, const int64_t* first, const int64_t* last, int64_t* n) {
     return slice_copy(*SOL(s), var, buf, first, last, n, false, true);
+}
+
+int yb_var_reduce_slice(yb_solution* s_, int var, const int64_t* first, const int64_t* last, double out[5], int64_t* n_done) {
+    Solution* s = SOL(s_);
+    if (int rc = check_var(s, var)) return rc;
+    if (!first || !last || !out) return set_error(YB_EINVAL, "null argument");
+    if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
+    Var& v = s->vars[var];
+    Slice sl;
+    if (int rc = resolve_slice(*s, v, first, last, true, sl)) return rc;
+    YB_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = size_t(reduce_scratch_entries()) * sizeof(RedVals);
+    if (int rc = ensure_stage(*s, bytes)) return rc;
+    RedVals* part = static_cast<RedVals*>(s->stage_dev);
+    RedVals tot{0.0, 0.0, 1.0, -HUGE_VAL, HUGE_VAL};
+    for (int64_t t = sl.t0; t <= sl.t1; t++) {
+        if (sl.elems_per_step == 0) break;
+        if (int rc = launch_box_reduce(v.slot_ptr(v.slot_of(t)), sl.bc, v.elem_bytes, part, s->stream())) return rc;
+        RedVals r;
+        YB_CUDA(cudaMemcpyAsync(&r, part + (reduce_scratch_entries() - 1), sizeof r, cudaMemcpyDeviceToHost, s->stream()));
+        YB_CUDA(cudaStreamSynchronize(s->stream()));
+        tot.sum += r.sum; tot.sumsq += r.sumsq; tot.prod *= r.prod;
+        tot.mx = std::max(tot.mx, r.mx); tot.mn = std::min(tot.mn, r.mn);
+    }
+    out[0] = tot.sum; out[1] = tot.sumsq; out[2] = tot.prod; out[3] = tot.mx; out[4] = tot.mn;
+    if (n_done) *n_done = sl.elems_per_step * (sl.t1 - sl.t0 + 1);
+    return 0;
 }
 
 int yb_var_set_all_same(yb_solution* s_, int var, double value) {

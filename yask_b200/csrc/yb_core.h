@@ -201,6 +201,9 @@ struct BoxCopy {
     int64_t var_stride[4];        // element strides in var storage
     int64_t var_off;              // element offset of the box origin in the slot
 };
+struct RedVals { double sum, sumsq, prod, mx, mn; };
+int reduce_scratch_entries();
+int launch_box_reduce(const void* var_slot, const BoxCopy& bc, int elem_bytes, RedVals* partial, cudaStream_t st);
 int launch_box_copy(void* var_slot, void* dense, const BoxCopy& bc, int elem_bytes, bool to_var, cudaStream_t st);
 int launch_box_fill(void* var_slot, const BoxCopy& bc, int elem_bytes, double value, cudaStream_t st);
 int launch_fill_all(void* ptr, int64_t n, int elem_bytes, double value, cudaStream_t st);

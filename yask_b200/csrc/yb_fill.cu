@@ -126,6 +126,63 @@ __global__ void checksum_kernel(const T* __restrict__ var, BoxDev b, G0 g0, unsi
     if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// ---- reductions over a strided box (yk_var::reduce_elements_in_slice, aux/yk_var_api.hpp:984-1048, 1050-1110) --------
+// All five results are accumulated in double, in a FIXED order (grid-stride per thread, shuffle tree per warp,
+// warp 0 over the warps, one final block over the per-block partials), so a given box always reduces to the same bits.
+__device__ __forceinline__ void red_init(RedVals& r) {
+    r.sum = 0.0; r.sumsq = 0.0; r.prod = 1.0;
+    r.mx = -__longlong_as_double(0x7ff0000000000000ll);
+    r.mn = __longlong_as_double(0x7ff0000000000000ll);
+}
+__device__ __forceinline__ void red_merge(RedVals& a, const RedVals& b) {
+    a.sum += b.sum; a.sumsq += b.sumsq; a.prod *= b.prod;
+    a.mx = fmax(a.mx, b.mx); a.mn = fmin(a.mn, b.mn);
+}
+__device__ __forceinline__ RedVals red_shfl(const RedVals& r, int delta) {
+    RedVals o;
+    o.sum = __shfl_down_sync(0xffffffffu, r.sum, delta);
+    o.sumsq = __shfl_down_sync(0xffffffffu, r.sumsq, delta);
+    o.prod = __shfl_down_sync(0xffffffffu, r.prod, delta);
+    o.mx = __shfl_down_sync(0xffffffffu, r.mx, delta);
+    o.mn = __shfl_down_sync(0xffffffffu, r.mn, delta);
+    return o;
+}
+// block-wide merge; the result is valid in thread 0
+__device__ __forceinline__ void red_block(RedVals& r) {
+    __shared__ RedVals wsum[8];
+    for (int d = 16; d > 0; d >>= 1) { RedVals o = red_shfl(r, d); red_merge(r, o); }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) wsum[w] = r;
+    __syncthreads();
+    if (w == 0) {
+        RedVals t;
+        red_init(t);
+        if (threadIdx.x < (blockDim.x >> 5)) t = wsum[threadIdx.x];
+        for (int d = 4; d > 0; d >>= 1) { RedVals o = red_shfl(t, d); red_merge(t, o); }
+        r = t;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) box_reduce_kernel(const T* __restrict__ var, BoxDev b, RedVals* __restrict__ partial) {
+    long long coord[4];
+    RedVals r;
+    red_init(r);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < b.total; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)var[box_offset(b, i, coord)];
+        r.sum += v; r.sumsq += v * v; r.prod *= v;
+        r.mx = fmax(r.mx, v); r.mn = fmin(r.mn, v);
+    }
+    red_block(r);
+    if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+__global__ void __launch_bounds__(256) reduce_final_kernel(const RedVals* __restrict__ partial, int n, RedVals* __restrict__ out) {
+    RedVals r;
+    red_init(r);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) red_merge(r, partial[i]);
+    red_block(r);
+    if (threadIdx.x == 0) *out = r;
+}
+
 int grid_for(long long total) {
     long long g = (total + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
@@ -191,6 +248,21 @@ int launch_hash_fill(void* var_slot, const BoxCopy& bc, const int64_t* g0, int e
     unsigned long long ss = ((unsigned long long)seed << 32) | (unsigned long long)salt;
     if (elem_bytes == 4) hash_fill_kernel<float><<<grid_for(b.total), 256, 0, st>>>((float*)var_slot, b, g, ss, lo, hi);
     else hash_fill_kernel<double><<<grid_for(b.total), 256, 0, st>>>((double*)var_slot, b, g, ss, lo, hi);
+    YB_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int reduce_scratch_entries() { return 148 * 16 + 1; }
+
+// partial: device array of reduce_scratch_entries() RedVals; the result lands in partial[0] ... [last entry]
+int launch_box_reduce(const void* var_slot, const BoxCopy& bc, int elem_bytes, RedVals* partial, cudaStream_t st) {
+    BoxDev b = right_align(bc);
+    const int g = grid_for(b.total);
+    RedVals* out = partial + (reduce_scratch_entries() - 1);
+    if (elem_bytes == 4) box_reduce_kernel<float><<<g, 256, 0, st>>>((const float*)var_slot, b, partial);
+    else box_reduce_kernel<double><<<g, 256, 0, st>>>((const double*)var_slot, b, partial);
+    YB_CUDA(cudaGetLastError());
+    reduce_final_kernel<<<1, 256, 0, st>>>(partial, g, out);
     YB_CUDA(cudaGetLastError());
     return 0;
 }

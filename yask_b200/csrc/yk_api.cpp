@@ -368,13 +368,13 @@ struct B200Var : yk_var {
     }
     yk_reduction_result_ptr reduce_elements_in_slice(int mask, const idx_t_vec& f, const idx_t_vec& l, bool) override {
         need_storage("reduce_elements_in_slice");
-        size_t n = slice_elems(f, l);
-        std::vector<double> tmp(n);
-        get_elements_in_slice(tmp.data(), n, f, l);
+        (void)slice_elems(f, l);   // validates the index vectors
         auto r = std::make_shared<B200Reduction>();
+        double out[5];
+        int64_t n = 0;
+        chk(yb_var_reduce_slice(h->s, vi, f.data(), l.data(), out, &n));   // on the device, in double
         r->mask = mask; r->n = idx_t(n);
-        if (n) { r->mx = r->mn = tmp[0]; }
-        for (double v : tmp) { r->sum += v; r->sumsq += v * v; r->prod *= v; r->mx = std::max(r->mx, v); r->mn = std::min(r->mn, v); }
+        r->sum = out[0]; r->sumsq = out[1]; r->prod = out[2]; r->mx = out[3]; r->mn = out[4];
         return r;
     }
     std::string format_indices(const idx_t_vec& indices) const override {
