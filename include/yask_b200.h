@@ -162,6 +162,10 @@ int yb_var_get_slice(yb_solution* s, int var, void* host_buf, const int64_t* fir
 /* Same, but the buffer is DEVICE memory on the solution's device (no host round trip). */
 int yb_var_set_slice_device(yb_solution* s, int var, const void* dev_buf, const int64_t* first, const int64_t* last, int64_t* n_done);
 int yb_var_get_slice_device(yb_solution* s, int var, void* dev_buf, const int64_t* first, const int64_t* last, int64_t* n_done);
+/* yk_solution::run_auto_tuner_now (aux/yk_solution_api.hpp:858-882): times the engine's launch variants over the rank
+ * domain right now (no halo exchange; var contents are NOT preserved), keeps the fastest for later run_solution()
+ * calls, clears the stats.  `report` (may be NULL) receives one line per trial. */
+int yb_solution_auto_tune(yb_solution* s, char* report, size_t report_len);
 /* Reductions over a slice, on the device, accumulated in double in a fixed order: yk_var::reduce_elements_in_slice
  * (aux/yk_var_api.hpp:984-1110; /root/reference/src/kernel/lib/yk_var.hpp:1367-1450).
  * out = {sum, sum of squares, product, max, min}; *n_done = number of elements reduced (may be NULL). */

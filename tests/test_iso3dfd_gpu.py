@@ -125,6 +125,37 @@ def test_device_hash_fill_matches_numpy_generator():
     s.close()
 
 
+def test_auto_tuner_picks_a_variant_and_results_stay_exact():
+    """run_auto_tuner_now: times the compiled sweep variants (data not preserved), keeps the fastest, clears the stats;
+    a run with fresh data afterwards is still bit-exact vs the oracle."""
+    n, steps, seed = (64, 48, 160), 2, 21
+    s = capi.Solution("iso3dfd")
+    s.set_overall_domain_size_vec(n)
+    s.prepare_solution(0)
+    rep = s.run_auto_tuner_now()
+    assert "best: tile=" in rep and rep.count("ms/step") >= 6, rep
+    assert s.get_stats().num_steps_done == 0
+    assert int(s.get_option("tile")) in (2, 3, 8, 9, 10, 11)
+    ins = {("p", t): hash_field(seed, var_salt("p", t), (-8, -8, -8), [i + 16 for i in n], -1, 1) for t in (0, 1)}
+    vv = hash_field(seed, var_salt("v", 0), (0, 0, 0), n, 0.05, 0.3)
+    p, v = s.get_var("p"), s.get_var("v")
+    for t in (0, 1):
+        p.set_elements_in_slice(ins[("p", t)], *p.halo_box(t))
+    v.set_elements_in_slice(vv, *v.halo_box(0))
+    s.run_solution(0, steps - 1)
+    tl = p.get_last_valid_step_index()
+    got = p.get_elements_in_slice(*p.domain_box(tl))
+    ref = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], vv, 8, steps, 2)[8:-8, 8:-8, 8:-8]
+    s.close()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    g = capi.Solution("awp_elastic", elem_bytes=0)
+    g.set_overall_domain_size_vec((48, 40, 96))
+    g.prepare_solution(0)
+    rep = g.run_auto_tuner_now()
+    assert "best: gen_pf=" in rep, rep
+    g.close()
+
+
 def test_device_reductions_match_numpy():
     """yk_var::reduce_elements_in_slice on the device (double accumulation, fixed order): sum / sum of squares to
     1e-12 relative, max / min exact, product on a small box; repeatable bit for bit."""

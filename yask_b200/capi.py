@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "yb_get_first_rank_domain_index", "yb_get_last_rank_domain_index", "yb_set_option", "yb_get_option", "yb_set_stream",
     "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_create", "yb_var_set_min_pad",
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
-    "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_var_fill_hash", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
+    "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_var_fill_hash", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
     "yb_exchange_halos",
 ]
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
             getattr(L, nm).restype = i64
         L.yb_set_option.argtypes = [p, C.c_char_p, C.c_char_p]
         L.yb_get_option.argtypes = [p, C.c_char_p, C.c_char_p, C.c_size_t]
+        L.yb_solution_auto_tune.argtypes = [p, C.c_char_p, C.c_size_t]
         L.yb_set_stream.argtypes = [p, p]
         L.yb_solution_plan_geometry.argtypes = [p]
         L.yb_solution_prepare.argtypes = [p, i32]
@@ -309,6 +310,12 @@ class Solution:
 
     def set_option(self, key: str, value):
         _chk(lib().yb_set_option(self._h, key.encode(), str(value).encode()))
+
+    def run_auto_tuner_now(self) -> str:
+        """Offline auto-tuner: times the engine's launch variants, keeps the fastest; var contents are not preserved."""
+        buf = C.create_string_buffer(8192)
+        _chk(lib().yb_solution_auto_tune(self._h, buf, 8192))
+        return buf.value.decode()
 
     def get_option(self, key: str) -> str:
         buf = C.create_string_buffer(256)

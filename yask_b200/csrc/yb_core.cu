@@ -739,6 +739,18 @@ int yb_get_stats(yb_solution* s_, yb_stats* out) {
     return 0;
 }
 
+int yb_solution_auto_tune(yb_solution* s_, char* report, size_t n) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    if (!s->prepared) return set_error(YB_ESTATE, "run_auto_tuner_now() called without calling prepare_solution() first");
+    YB_CUDA(cudaSetDevice(s->device));
+    std::string rep;
+    if (int rc = s->engine->auto_tune(*s, s->stream(), rep)) return rc;
+    YB_CUDA(cudaStreamSynchronize(s->stream()));
+    if (report && n) snprintf(report, n, "%s", rep.c_str());
+    return yb_clear_stats(s_);      // the reference clears the stats when the tuner is done (yk_solution_api.hpp:872)
+}
+
 int yb_clear_stats(yb_solution* s_) {
     Solution* s = SOL(s_);
     if (!s) return set_error(YB_EINVAL, "null solution");

@@ -126,6 +126,9 @@ struct Engine {
     // launch stage `stage` of step t (computing t+1) over `box` on `stream`; returns #kernels launched or <0
     virtual int launch(Solution& s, int stage, int64_t t, const Box& box, cudaStream_t stream) = 0;
     virtual int set_option(Solution&, const std::string&, const std::string&) { return YB_EINVAL; }
+    // Offline auto-tuner (yk_solution::run_auto_tuner_now): time the engine's launch variants over the rank box on
+    // `stream`, keep the fastest, describe the trials in `report`.  Var contents are not preserved.  Default: nothing to tune.
+    virtual int auto_tune(Solution&, cudaStream_t, std::string& report) { report = "nothing to tune"; return 0; }
     virtual bool get_option(const Solution&, const std::string&, std::string&) const { return false; }
 };
 
@@ -174,6 +177,25 @@ struct Solution {
 
 // storage geometry of one var from the solution's rank geometry (yb_core.cu)
 void compute_var_geometry(Solution& s, Var& v);
+
+// Times `reps` calls of fn() on `st` with CUDA events after one untimed call; returns ms per call (<0 on error).
+template <class F>
+inline double time_launches(cudaStream_t st, int reps, F fn) {
+    cudaEvent_t e0, e1;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1;
+    double ms = -1;
+    if (fn() >= 0) {
+        cudaEventRecord(e0, st);
+        bool ok = true;
+        for (int i = 0; i < reps && ok; i++) ok = fn() >= 0;
+        cudaEventRecord(e1, st);
+        float f = 0;
+        if (ok && cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&f, e0, e1) == cudaSuccess) ms = double(f) / reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return ms;
+}
 
 // error plumbing
 int set_error(int code, const char* fmt, ...);

@@ -90,6 +90,44 @@ struct GenEngine : Engine {
         }
         return 0;
     }
+    // Offline tuner: L2 prefetch distance x sweep-chunk budget, timed over one full step of the rank box.
+    int auto_tune(Solution& s, cudaStream_t st, std::string& report) override {
+        Box whole;
+        for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = d < s.ndd ? s.rank_size[d] : 1; }
+        const int pfs[] = {0, 1, 2};
+        const int l2s[] = {0, 8, 16, 32};
+        const int keep_pf = pf_dist, keep_l2 = l2_mb;
+        double best = 1e30;
+        int best_pf = pf_dist, best_l2 = l2_mb;
+        char line[128];
+        report.clear();
+        int64_t t = 0;
+        for (auto& v : s.vars) t = std::max(t, v.last_valid_step());
+        for (int pf : pfs)
+            for (int l2 : l2s) {
+                pf_dist = pf; l2_mb = l2;
+                const double ms = time_launches(st, 2, [&]() {
+                    int n = 0;
+                    for (size_t sg = 0; sg < g.stages.size(); sg++) {
+                        const int rc = launch(s, int(sg), t, whole, st);
+                        if (rc < 0) return rc;
+                        n += rc;
+                    }
+                    return n;
+                });
+                if (ms < 0) { pf_dist = keep_pf; l2_mb = keep_l2; return set_error(YB_ECUDA, "auto-tuner: a trial launch failed"); }
+                snprintf(line, sizeof line, " gen_pf=%d gen_l2_mb=%d: %.4f ms/step\n", pf, l2, ms);
+                report += line;
+                if (ms < best) { best = ms; best_pf = pf; best_l2 = l2; }
+            }
+        pf_dist = best_pf; l2_mb = best_l2;
+        snprintf(line, sizeof line, "best: gen_pf=%d gen_l2_mb=%d (%.4f ms/step)\n", pf_dist, l2_mb, best);
+        report += line;
+        s.options["gen_pf"] = std::to_string(pf_dist);
+        s.options["gen_l2_mb"] = std::to_string(l2_mb);
+        return 0;
+    }
+
     int launch(Solution& s, int stage, int64_t t, const Box& box, cudaStream_t st) override {
         if (box.empty()) return 0;
         const GenStage& gs = g.stages[stage];

@@ -343,6 +343,41 @@ struct IsoEngine : Engine {
         YB_CUDA(cudaGetLastError());
         return 1;
     }
+
+    // Offline tuner: the compiled sweep variants (tile shape, producer warpgroup, planes per trip) x sweep chunk
+    // lengths, timed over the whole rank box; the analogue of the reference's block-size search
+    // (/root/reference/src/kernel/lib/auto_tuner.cpp) for the knobs this engine has.
+    int auto_tune(Solution& s, cudaStream_t st, std::string& report) override {
+        if (!maps_ok || radius != 8 || kernel == "direct") { report = "iso3dfd: no tiled variants to tune for this configuration"; return 0; }
+        Box whole;
+        for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = s.rank_size[d]; }
+        if (whole.e[1] < 8 || whole.e[2] < 16) { report = "iso3dfd: domain too thin for the tiled kernel"; return 0; }
+        const int64_t t0 = s.vars[0].last_valid_step();
+        const int tiles[] = {11, 10, 9, 8, 3, 2};
+        const int lxs[] = {0, 256, 512, 1024};
+        const int keep_tile = tile, keep_lx = lx;
+        double best = 1e30;
+        int best_tile = tile, best_lx = lx;
+        char line[160];
+        report.clear();
+        for (int ti : tiles)
+            for (int l : lxs) {
+                if (l > whole.e[0]) continue;
+                tile = ti; lx = l;
+                int64_t t = t0;
+                const double ms = time_launches(st, 3, [&]() { return launch(s, 0, t++, whole, st); });
+                if (ms < 0) { tile = keep_tile; lx = keep_lx; return set_error(YB_ECUDA, "auto-tuner: a trial launch failed"); }
+                snprintf(line, sizeof line, " tile=%d (%s) lx=%d: %.4f ms/step\n", ti, tile_cfg(ti).name, l, ms);
+                report += line;
+                if (ms < best) { best = ms; best_tile = ti; best_lx = l; }
+            }
+        tile = best_tile; lx = best_lx;
+        snprintf(line, sizeof line, "best: tile=%d lx=%d (%.4f ms/step)\n", tile, lx, best);
+        report += line;
+        s.options["tile"] = std::to_string(tile);
+        s.options["lx"] = std::to_string(lx);
+        return 0;
+    }
 };
 
 }  // namespace

@@ -624,9 +624,13 @@ struct B200Solution : yk_solution {
     void clear_stats() override { chk(yb_clear_stats(h->s)); }
     void reset_auto_tuner(bool, bool) override {}    // no CPU block sizes to tune
     bool is_auto_tuner_enabled() const override { return false; }
-    void run_auto_tuner_now(bool) override {
-        // auto_tuner.cpp raises when called before prepare_solution(); there are no CPU block sizes to tune on the GPU
+    void run_auto_tuner_now(bool verbose) override {
+        // auto_tuner.cpp raises when called before prepare_solution().  What is tuned here are the engine's launch
+        // variants (sweep tile / chunk length, prefetch distance, L2 chunking), not CPU block sizes.
         if (!yb_solution_is_prepared(h->s)) fail("run_auto_tuner_now() called without calling prepare_solution() first");
+        char report[8192];
+        chk(yb_solution_auto_tune(h->s, report, sizeof report));
+        if (verbose) { auto out = yk_env::get_debug_output(); if (out) out->get_ostream() << "auto-tuner:\n" << report; }
     }
     void set_min_pad_size(const std::string& dim, idx_t size) override { chk(yb_set_min_pad_size(h->s, dpos(dim, "set_min_pad_size"), size)); min_pad[dim] = size; }
     std::map<std::string, idx_t> min_pad;
