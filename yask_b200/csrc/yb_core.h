@@ -212,6 +212,10 @@ const char* registry_name(int i);
 // builds spec + engine; returns 0 or error
 int registry_create(const std::string& name, int radius, int elem_bytes, StencilSpec& spec, std::unique_ptr<Engine>& eng);
 
+// CUtensorMap (passed as void* to keep <cuda.h> out of this header) over one step slot of a full-rank 3-D var,
+// box (box_z, box_y, 1) -- yb_iso3dfd.cu
+int make_var_tensor_map(void* map, const Var& v, int slot, int box_z, int box_y);
+
 // engines
 std::unique_ptr<Engine> make_iso3dfd_engine();
 StencilSpec iso3dfd_spec(int radius, int elem_bytes, bool sponge);

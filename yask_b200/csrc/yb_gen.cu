@@ -2,9 +2,11 @@
 // one kernel per part and stage (the reference runs the parts of a stage back to back over each
 // micro-block, /root/reference/src/kernel/lib/context.cpp:1158; parts of a stage are independent).
 #include <algorithm>
+#include <cstring>
+#include <map>
 
 #include "yb_core.h"
-#include "yb_gen.cuh"
+#include "yb_gen_sweep.cuh"
 // generated solutions: declarations + table (each solution is compiled in its own translation unit)
 #include "gen/gen_all.inc"
 
@@ -61,11 +63,17 @@ struct GenEngine : Engine {
     GenEngine() {
         if (const char* e = getenv("YB_GEN_PF")) pf_dist = std::max(0, atoi(e));
         if (const char* e = getenv("YB_GEN_L2_MB")) l2_mb = std::max(0, atoi(e));
+        if (const char* e = getenv("YB_GEN_SWEEP")) sweep = atoi(e) != 0;
     }
+    int sweep = 0;     // option gen_sweep (env YB_GEN_SWEEP): 1 = use the TMA-staged sweep variant where a part has one (experimental)
+    int sweep_lx = 128;  // option gen_sweep_lx: x planes per sweep chunk
+    std::map<const void*, bool> sweep_attr;   // kernels whose dynamic shared-memory limit has been raised
     int l2_mb = 16;    // option gen_l2_mb (env YB_GEN_L2_MB): L2 budget of one y chunk's sweep working set (0 = no chunking)
     int set_option(Solution&, const std::string& key, const std::string& value) override {
         if (key == "gen_pf") { pf_dist = std::max(0, atoi(value.c_str())); return 0; }
         if (key == "gen_l2_mb") { l2_mb = std::max(0, atoi(value.c_str())); return 0; }
+        if (key == "gen_sweep") { sweep = atoi(value.c_str()) != 0; return 0; }
+        if (key == "gen_sweep_lx") { sweep_lx = std::max(8, atoi(value.c_str())); return 0; }
         return YB_EINVAL;
     }
     int prepare(Solution& s) override {
@@ -188,6 +196,41 @@ struct GenEngine : Engine {
                     scratch_written[si] = 1;
                     if (p.conditional) YB_CUDA(cudaMemsetAsync(scratch[si].dev, 0, scratch[si].bytes(), st));
                 }
+            // Sweep variant: TMA-staged shared-memory planes (yb_gen_sweep.cuh), for whole-box launches of parts that have one.
+            const int fi = g.elem_bytes == 8 ? 1 : 0, mi = s.fp_mode == 0 ? 0 : 1;
+            if (sweep && p.sweep.fn[fi][mi] && P.SX != 0 && pb.e[1] - pb.b[1] >= 1 && pb.e[2] - pb.b[2] >= 32) {
+                GenSweepParams SP;
+                memset(&SP, 0, sizeof SP);
+                SP.g = P;
+                const GenSweep& sw = p.sweep;
+                bool first = true;
+                for (size_t k = 0; k < sw.streams.size(); k++) {
+                    const GenSweepStream& ss = sw.streams[k];
+                    const Var& v = var_of(s, p.acc[ss.acc].var);
+                    const Dim *d0 = v.domain_dim(0), *d1 = v.domain_dim(1), *d2 = v.domain_dim(2);
+                    if (!d0 || !d1 || !d2) return set_error(YB_EUNSUPPORTED, "sweep kernel: var '%s' is not full rank", v.spec.name.c_str());
+                    if (first) { SP.px = int(d0->pad_l); SP.py = int(d1->pad_l); SP.pz = int(d2->pad_l); first = false; }
+                    if (d0->pad_l != SP.px || d1->pad_l != SP.py || d2->pad_l != SP.pz)
+                        return set_error(YB_EUNSUPPORTED, "sweep kernel: var '%s' does not share the solution's padded geometry", v.spec.name.c_str());
+                    if (int rc = make_var_tensor_map(&SP.map[k], v, v.slot_of(t + p.acc[ss.acc].toff), ss.pz, ss.rows)) return rc;
+                }
+                SP.lx = int(std::min<int64_t>(sweep_lx, pb.e[0] - pb.b[0]));
+                SP.nchunks = int((pb.e[0] - pb.b[0] + SP.lx - 1) / SP.lx);
+                SP.nzb = int((pb.e[2] - pb.b[2] + GEN_SW_TZ - 1) / GEN_SW_TZ);
+                SP.nyb = int((pb.e[1] - pb.b[1] + sw.ty - 1) / sw.ty);
+                SP.bar_off = sw.bar_off;
+                GenSweepFn sfn = sw.fn[fi][mi];
+                if (!sweep_attr[(const void*)sfn]) {
+                    YB_CUDA(cudaFuncSetAttribute((const void*)sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, sw.smem));
+                    sweep_attr[(const void*)sfn] = true;
+                }
+                const int64_t nb = int64_t(SP.nzb) * SP.nyb * SP.nchunks;
+                if (nb >= (int64_t(1) << 31)) return set_error(YB_EUNSUPPORTED, "domain too large for the sweep kernels");
+                sfn<<<unsigned(nb), GEN_SW_TZ, sw.smem, st>>>(SP);
+                YB_CUDA(cudaGetLastError());
+                n++;
+                continue;
+            }
             // L2 prefetch list: full-rank vars the part only reads (distinct storage)
             P.npf = 0;
             P.pfd = pf_dist;

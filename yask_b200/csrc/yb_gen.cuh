@@ -49,6 +49,16 @@ struct GenParams {
 
 typedef void (*GenKernelFn)(const GenParams);
 
+// Sweep variant (yb_gen_sweep.cuh): host-side description of one part's TMA streams; empty when the part has none.
+struct GenSweepParams;
+typedef void (*GenSweepFn)(const GenSweepParams);
+struct GenSweepStream { int acc, xl, xr, yl, yr, zl, zr, rows, pz, slot_bytes, ns, off; };
+struct GenSweep {
+    GenSweepFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [fp64?][mode]
+    int ty = 0, pf = 0, smem = 0, bar_off = 0;
+    std::vector<GenSweepStream> streams;
+};
+
 struct GenVar {
     const char* name;
     std::vector<const char*> dims;   // declared order, step dim first if any
@@ -74,6 +84,7 @@ struct GenPart {
     bool is_scratch = false;
     bool conditional = false;        // has a sub-domain or step condition (scratch outputs are zeroed first)
     int wh_l[3] = {0, 0, 0}, wh_r[3] = {0, 0, 0};
+    GenSweep sweep;                  // TMA-staged variant of the same statements, when the emitter could build one
 };
 struct GenStage { const char* name; std::vector<GenPart> parts; };
 struct GenStencil {

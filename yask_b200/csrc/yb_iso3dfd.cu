@@ -146,6 +146,31 @@ int make_map(CUtensorMap* map, const Var& v, int slot, int bz, int by) {
     return 0;
 }
 
+}  // namespace
+
+// 3-D tiled map over one step slot of a full-rank var of any element size (generated sweep kernels, yb_gen.cu).
+int make_var_tensor_map(void* map_, const Var& v, int slot, int box_z, int box_y) {
+    CUtensorMap* map = static_cast<CUtensorMap*>(map_);
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return set_error(YB_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    const Dim* dx = v.domain_dim(0);
+    const Dim* dy = v.domain_dim(1);
+    const Dim* dz = v.domain_dim(2);
+    if (!dx || !dy || !dz || dz->stride != 1) return set_error(YB_EUNSUPPORTED, "tensor map: var '%s' is not a full-rank 3-D var", v.spec.name.c_str());
+    const cuuint64_t eb = cuuint64_t(v.elem_bytes);
+    cuuint64_t gdim[3] = {cuuint64_t(dz->alloc), cuuint64_t(dy->alloc), cuuint64_t(dx->alloc)};
+    cuuint64_t gstr[2] = {cuuint64_t(dy->stride) * eb, cuuint64_t(dx->stride) * eb};
+    cuuint32_t box[3] = {cuuint32_t(box_z), cuuint32_t(box_y), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, v.elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, v.slot_ptr(slot), gdim, gstr,
+                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(YB_ECUDA, "cuTensorMapEncodeTiled failed with code %d (var '%s')", int(r), v.spec.name.c_str());
+    return 0;
+}
+
+namespace {
+
 template <class T>
 TileCfg cfg_gen1(const char* name) {
     return TileCfg{false, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,

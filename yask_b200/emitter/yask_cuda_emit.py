@@ -578,6 +578,123 @@ def _stage_sequence(ir, st):
     return seq
 
 
+
+# ----------------------------------------------------------------------------------------------------
+# sweep variant (TMA-staged shared-memory planes, yask_b200/csrc/yb_gen_sweep.cuh)
+# ----------------------------------------------------------------------------------------------------
+SWEEP_TZ = 128
+SWEEP_SMEM_LIMIT = 200 * 1024
+SWEEP_MAX_STREAMS = 24
+
+
+def _roundup(v, m):
+    return (v + m - 1) // m * m
+
+
+def sweep_plan(ir, p, ty=4, pf=2):
+    """Shared-memory layout of part `p` for the sweep kernel, or None when the part does not qualify: 3-D solutions,
+    unconditional non-scratch parts, full-rank outputs, no misc-dim vars among the full-rank reads, and rings that
+    fit in shared memory (x reach + pf slots per stream)."""
+    if len(ir["domain_dims"]) != 3 or p.get("cond") or p.get("step_cond") or p.get("scratch") or p.get("children"):
+        return None
+    masks = _masks(ir, p)
+    if any(masks[o["access"]] != 7 for o in p["outputs"]):
+        return None
+    vmap = {v["name"]: v for v in ir["vars"]}
+    ext = {}
+    for st in p["stmts"]:
+        for a, offs in st["reads"]:
+            e = ext.setdefault(a, [[0, 0], [0, 0], [0, 0]])
+            for d in range(3):
+                e[d][0], e[d][1] = min(e[d][0], offs[d]), max(e[d][1], offs[d])
+    eb = ir["elem_bytes"]
+    align = 16 // eb
+    streams, off = [], 0
+    for a in sorted(ext):
+        if masks[a] != 7:
+            continue
+        acc = p["accesses"][a]
+        if acc.get("misc") or vmap[acc["var"]].get("scratch"):
+            return None
+        (xl, xr), (yl, yr), (zl, zr) = ext[a]
+        rows = ty + yr - yl
+        pz = _roundup(SWEEP_TZ + zr - zl, align)
+        slot = _roundup(rows * pz * eb, 128)
+        ns = xr - xl + 1 + pf
+        streams.append({"acc": a, "xl": xl, "xr": xr, "yl": yl, "yr": yr, "zl": zl, "zr": zr, "rows": rows, "pz": pz,
+                        "slot": slot, "ns": ns, "off": off})
+        off += ns * slot
+    if not streams or len(streams) > SWEEP_MAX_STREAMS:
+        return None
+    bar_off = off
+    smem = bar_off + 8 * (pf + 1)
+    if smem > SWEEP_SMEM_LIMIT:
+        return None
+    return {"ty": ty, "pf": pf, "streams": streams, "bar_off": bar_off, "smem": smem,
+            "bytes0": sum((s_["xr"] - s_["xl"] + 1) * s_["rows"] * s_["pz"] * eb for s_ in streams),
+            "bytes1": sum(s_["rows"] * s_["pz"] * eb for s_ in streams)}
+
+
+def emit_sweep_kernel(ir, p, plan, ident) -> list:
+    masks = _masks(ir, p)
+    sidx = {s_["acc"]: k for k, s_ in enumerate(plan["streams"])}
+    L = []
+    L.append(f"// sweep variant of part '{p['name']}' (yb_gen_sweep.cuh): {len(plan['streams'])} TMA streams, {plan['ty']} rows x {SWEEP_TZ} z per CTA, "
+             f"{plan['pf']} planes of prefetch, {plan['smem']} B of shared memory")
+    L.append("template <typename T, int MODE>")
+    L.append(f"__global__ void __launch_bounds__(GEN_SW_TZ) {ident}_{p['name']}_sweep_kernel(const __grid_constant__ GenSweepParams SP) {{")
+    L.append(f"    GEN_SWEEP_BEGIN({plan['ty']}, {plan['pf']})")
+    L.append("    auto sw_issue = [&](int j) {     // everything first needed at sweep iteration j")
+    L.append("        uint64_t* bar = &sw_bar[j % SW_NB];")
+    L.append(f"        mbar_arrive_expect_tx(bar, j == 0 ? {plan['bytes0']}u : {plan['bytes1']}u);")
+    for k, s_ in enumerate(plan["streams"]):
+        acc = p["accesses"][s_["acc"]]
+        L.append(f"        SW_LOAD({k}, {s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['xr']}, {s_['yl']}, {s_['zl']})   // {acc['var']}"
+                 f"(t{acc['toff']:+d}): x {s_['xl']}..{s_['xr']}, y {s_['yl']}..{s_['yr']}, z {s_['zl']}..{s_['zr']}")
+    L.append("    };")
+    L.append("    if (threadIdx.x == 0)")
+    L.append("        for (int j = 0; j < SW_PF && j < sw_len; j++) sw_issue(j);")
+    L.append("    for (int it = 0; it < sw_len; it++) {")
+    L.append("        if (threadIdx.x == 0 && it + SW_PF < sw_len) sw_issue(it + SW_PF);")
+    L.append("        mbar_wait(&sw_bar[it % SW_NB], (unsigned(it) / SW_NB) & 1u);")
+    L.append("        const int x = xs + it;")
+    # plane base pointers per (stream, dx) actually read
+    used = {}
+    for st in p["stmts"]:
+        for a, offs in st["reads"]:
+            if a in sidx:
+                used.setdefault((sidx[a], offs[0]), None)
+    for (k, dx) in sorted(used):
+        s_ = plan["streams"][k]
+        nm = f"s{k}_{'m' if dx < 0 else 'p'}{abs(dx)}"
+        used[(k, dx)] = nm
+        L.append(f"        const T* {nm} = SW_PLANE({s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['zl']}, {dx});")
+    L.append("        _Pragma(\"unroll\") for (int r = 0; r < SW_TY; r++) {")
+    L.append("            const int y = y0_ + r;")
+    L.append("            if (y < P.ye && z < P.ze) {")
+
+    for st in p["stmts"]:
+        def rd(i, st=st):
+            a, offs = st["reads"][i]
+            if a in sidx:
+                s_ = plan["streams"][sidx[a]]
+                return f"{used[(sidx[a], offs[0])]}[(r + {offs[1] - s_['yl']}) * {s_['pz']} + ({offs[2]})]"
+            return _rd_text(a, offs, masks)
+        if st.get("kind") == "sincos":
+            L.append(f"                T {st['sin']}, {st['cos']};")
+            L.append(f"                YF_sincos({gen_expr(st['tree'], rd, OPS)}, {st['sin']}, {st['cos']});")
+            continue
+        L.append(f"                const T {st['dst']} = {gen_expr(st['tree'], rd, OPS)};")
+    for o in p["outputs"]:
+        L.append(f"                WR({o['access']}, {masks[o['access']]}, {o['src']});")
+    L.append("            }")
+    L.append("        }")
+    L.append("        __syncthreads();     // every thread is done with the oldest slots before they are refilled")
+    L.append("    }")
+    L.append("}")
+    return L
+
+
 def _masks(ir, part):
     """Per access: bit k set if the var spans the domain dim held by kernel slot k (slots x=1, y=2, z=4; the
     solution's domain dims are right-aligned into the slots, so the unit-stride dim is always slot z)."""
@@ -603,7 +720,7 @@ def emit_cuda(ir: dict) -> str:
     L.append("// tree in the reference's evaluation order (generated calc_scalar(), emitted by")
     L.append("// /root/reference/src/compiler/lib/YaskKernel.cpp:429- / Cpp.cpp), every op in the element type.")
     L.append("#pragma once")
-    L.append('#include "../yb_gen.cuh"')
+    L.append('#include "../yb_gen_sweep.cuh"')
     L.append("namespace yb { namespace gen {")
     for stname, p in _all_parts(ir):
         where = f"of stage '{stname}'" if stname else "(scratch: evaluated over the box expanded by its write halo, before the parts that read it)"
@@ -620,6 +737,13 @@ def emit_cuda(ir: dict) -> str:
             L.append("    }")
         L.append("    GEN_KERNEL_END")
         L.append("}")
+    plans = {}
+    for st in ir["stages"]:
+        for p in st["parts"]:
+            plan = sweep_plan(ir, p)
+            if plan:
+                plans[p["name"]] = plan
+                L.extend(emit_sweep_kernel(ir, p, plan, ident))
     # spec table
     L.append(f"inline void {ident}_describe(GenStencil& g) {{")
     L.append(f'    g.name = "{n}"; g.elem_bytes = {ir["elem_bytes"]}; g.step_dim = "{ir["step_dim"]}";')
@@ -653,6 +777,18 @@ def emit_cuda(ir: dict) -> str:
             conditional = str(bool(p.get("cond") or p.get("step_cond"))).lower()
             L.append(f'    g.stages.back().parts.push_back(GenPart{{"{p["name"]}", {p["fp_ops"]}, {p["reads"]}, {p["writes"]}, {{{acc}}}, {{{outs}}}, {fns}, {{{", ".join(bl)}}}, '
                      f'{str(p["scratch"]).lower()}, {conditional}, {{{whl}}}, {{{whr}}}}});')
+            plan = plans.get(p["name"])
+            if plan:
+                ks = f"{ident}_{p['name']}_sweep_kernel"
+                L.append("    {")
+                L.append("        GenSweep& sw = g.stages.back().parts.back().sweep;")
+                L.append(f"        sw.fn[0][0] = GEN_SW_FN({ks}, float, 0); sw.fn[0][1] = GEN_SW_FN({ks}, float, 1);")
+                L.append(f"        sw.fn[1][0] = GEN_SW_FN({ks}, double, 0); sw.fn[1][1] = GEN_SW_FN({ks}, double, 1);")
+                L.append(f"        sw.ty = {plan['ty']}; sw.pf = {plan['pf']}; sw.smem = {plan['smem']}; sw.bar_off = {plan['bar_off']};")
+                for s_ in plan["streams"]:
+                    L.append("        sw.streams.push_back(GenSweepStream{%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d});" % (
+                        s_["acc"], s_["xl"], s_["xr"], s_["yl"], s_["yr"], s_["zl"], s_["zr"], s_["rows"], s_["pz"], s_["slot"], s_["ns"], s_["off"]))
+                L.append("    }")
     L.append("}")
     L.append("} }  // namespace yb::gen")
     return "\n".join(L) + "\n"
