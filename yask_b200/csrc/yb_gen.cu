@@ -55,6 +55,7 @@ struct GenEngine : Engine {
     ~GenEngine() override {
         for (auto& v : scratch)
             if (v.dev) cudaFree(v.dev);
+        for (auto& kv : sweep_maps) cudaFree(kv.second);
     }
     const Var& var_of(const Solution& s, int gi) const { return gi < nreg ? s.vars[gi] : scratch[gi - nreg]; }
     // option gen_pf (or env YB_GEN_PF): L2 prefetch distance in x planes (0 = off).  Measured on B200 at 512^3
@@ -68,6 +69,13 @@ struct GenEngine : Engine {
     int sweep = 0;     // option gen_sweep (env YB_GEN_SWEEP): 1 = use the TMA-staged sweep variant where a part has one (experimental)
     int sweep_lx = 128;  // option gen_sweep_lx: x planes per sweep chunk
     std::map<const void*, bool> sweep_attr;   // kernels whose dynamic shared-memory limit has been raised
+    // tensor maps of a part's streams live in device memory, one array per combination of step slots (they depend only on
+    // the vars' storage, fixed after prepare)
+    std::map<std::pair<const GenPart*, std::string>, void*> sweep_maps;
+    void free_sweep_maps() {
+        for (auto& kv : sweep_maps) cudaFree(kv.second);
+        sweep_maps.clear();
+    }
     int l2_mb = 16;    // option gen_l2_mb (env YB_GEN_L2_MB): L2 budget of one y chunk's sweep working set (0 = no chunking)
     int set_option(Solution&, const std::string& key, const std::string& value) override {
         if (key == "gen_pf") { pf_dist = std::max(0, atoi(value.c_str())); return 0; }
@@ -85,6 +93,7 @@ struct GenEngine : Engine {
         for (auto& v : scratch)
             if (v.dev) cudaFree(v.dev);
         scratch.clear();
+        free_sweep_maps();
         for (auto& gv : g.vars) {
             if (!gv.is_scratch) continue;
             Var v;
@@ -181,7 +190,13 @@ struct GenEngine : Engine {
                 P.sx[k] = d0 ? d0->stride : 0;
                 P.sy[k] = d1 ? d1->stride : 0;
                 P.sz[k] = d2 ? d2->stride : 0;
-                if (d0 && d1 && d2) {   // full-rank var: must share the solution-wide geometry
+                // full-rank var declared in the solution's dim order: must share the solution-wide geometry (a var that
+                // permutes the dims -- H(y, z, x) -- is addressed through its own strides; the emitter gives it mask 15)
+                bool in_order = true;
+                int last_di = -1;
+                for (auto& d : v.dims)
+                    if (d.spec.kind == DIM_DOMAIN) { in_order = in_order && d.spec.domain_index > last_di; last_di = d.spec.domain_index; }
+                if (d0 && d1 && d2 && in_order) {
                     if (P.SX == 0) { P.SX = int(d0->stride); P.SY = int(d1->stride); }
                     if (d0->stride != P.SX || d1->stride != P.SY || d2->stride != 1 || v.slot_elems >= (int64_t(1) << 31))
                         return set_error(YB_EUNSUPPORTED, "var '%s' does not share the solution's padded geometry", v.spec.name.c_str());
@@ -204,6 +219,7 @@ struct GenEngine : Engine {
                 SP.g = P;
                 const GenSweep& sw = p.sweep;
                 bool first = true;
+                std::string key;
                 for (size_t k = 0; k < sw.streams.size(); k++) {
                     const GenSweepStream& ss = sw.streams[k];
                     const Var& v = var_of(s, p.acc[ss.acc].var);
@@ -212,8 +228,23 @@ struct GenEngine : Engine {
                     if (first) { SP.px = int(d0->pad_l); SP.py = int(d1->pad_l); SP.pz = int(d2->pad_l); first = false; }
                     if (d0->pad_l != SP.px || d1->pad_l != SP.py || d2->pad_l != SP.pz)
                         return set_error(YB_EUNSUPPORTED, "sweep kernel: var '%s' does not share the solution's padded geometry", v.spec.name.c_str());
-                    if (int rc = make_var_tensor_map(&SP.map[k], v, v.slot_of(t + p.acc[ss.acc].toff), ss.pz, ss.rows)) return rc;
+                    key.push_back(char('0' + v.slot_of(t + p.acc[ss.acc].toff)));
                 }
+                auto mk = std::make_pair(&p, key);
+                auto it = sweep_maps.find(mk);
+                if (it == sweep_maps.end()) {
+                    std::vector<CUtensorMap> hm(sw.streams.size());
+                    for (size_t k = 0; k < sw.streams.size(); k++) {
+                        const GenSweepStream& ss = sw.streams[k];
+                        const Var& v = var_of(s, p.acc[ss.acc].var);
+                        if (int rc = make_var_tensor_map(&hm[k], v, v.slot_of(t + p.acc[ss.acc].toff), ss.pz, ss.rows)) return rc;
+                    }
+                    void* dm = nullptr;
+                    YB_CUDA(cudaMalloc(&dm, hm.size() * sizeof(CUtensorMap)));
+                    YB_CUDA(cudaMemcpy(dm, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+                    it = sweep_maps.emplace(mk, dm).first;
+                }
+                SP.maps = static_cast<const CUtensorMap*>(it->second);
                 SP.lx = int(std::min<int64_t>(sweep_lx, pb.e[0] - pb.b[0]));
                 SP.nchunks = int((pb.e[0] - pb.b[0] + SP.lx - 1) / SP.lx);
                 SP.nzb = int((pb.e[2] - pb.b[2] + GEN_SW_TZ - 1) / GEN_SW_TZ);

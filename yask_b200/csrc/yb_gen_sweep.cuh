@@ -18,7 +18,8 @@ constexpr int GEN_SW_TZ = 128;          // z extent of a tile = threads per CTA
 
 struct GenSweepParams {
     GenParams g;                               // box, pointers and strides as for the direct kernel
-    CUtensorMap map[GEN_SW_MAX_STREAMS];       // one per stream: 3-D (z, y, x) view of the var's step slot, box (pz, rows, 1)
+    const CUtensorMap* maps;                   // device array, one per stream: 3-D (z, y, x) view of the var's step slot,
+                                               // box (pz, rows, 1); built once per slot combination and cached (yb_gen.cu)
     int px, py, pz;                            // left pads of the shared geometry (tensor coordinate of local index 0)
     int lx, nchunks;                           // planes per sweep chunk, chunks along x
     int nzb, nyb;                              // tiles along z and y
@@ -56,10 +57,10 @@ struct GenSweepParams {
 #define SW_LOAD(k, OFF, SLOT, NS, XL, XR, YL, ZL)                                                            \
     if (j == 0) {                                                                                            \
         for (int dx = (XL); dx <= (XR); dx++)                                                                \
-            tma_load_3d(sw_smem + (OFF) + ((dx - (XL)) % (NS)) * (SLOT), &SP.map[k], bar, SP.pz + z0 + (ZL), \
+            tma_load_3d(sw_smem + (OFF) + ((dx - (XL)) % (NS)) * (SLOT), &SP.maps[k], bar, SP.pz + z0 + (ZL), \
                         SP.py + y0_ + (YL), SP.px + xs + dx);                                                \
     } else {                                                                                                 \
-        tma_load_3d(sw_smem + (OFF) + ((j + (XR) - (XL)) % (NS)) * (SLOT), &SP.map[k], bar, SP.pz + z0 + (ZL), \
+        tma_load_3d(sw_smem + (OFF) + ((j + (XR) - (XL)) % (NS)) * (SLOT), &SP.maps[k], bar, SP.pz + z0 + (ZL), \
                     SP.py + y0_ + (YL), SP.px + xs + j + (XR));                                              \
     }
 

@@ -707,6 +707,11 @@ def _masks(ir, part):
         for i, d in enumerate(dd):
             if d in vmap[a["var"]]["dims"]:
                 m |= 1 << (i + sh)
+        # a var that declares its domain dims in another order than the solution (H(y, z, x)) is stored in ITS order:
+        # bit 8 keeps it off the shared-geometry fast path (mask 7) -- it is addressed through its own strides
+        vd = [d for d in vmap[a["var"]]["dims"] if d in dd]
+        if vd != [d for d in dd if d in vd]:
+            m |= 8
         out.append(m)
     return out
 
