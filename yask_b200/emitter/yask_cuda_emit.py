@@ -617,6 +617,10 @@ def sweep_plan(ir, p, ty=4, pf=2):
         if acc.get("misc") or vmap[acc["var"]].get("scratch"):
             return None
         (xl, xr), (yl, yr), (zl, zr) = ext[a]
+        # The box must START on a 16-byte boundary in global memory (pads and tile origins are multiples of 128 B, so
+        # only the z reach matters): measured on B200 -- UTMALDG raises "illegal instruction" for a start coordinate
+        # that is not a multiple of 16 B (z reach -1, -2, -3 with 4-byte elements), reach -4 and 0 are fine.
+        zl = -_roundup(-zl, align)
         rows = ty + yr - yl
         pz = _roundup(SWEEP_TZ + zr - zl, align)
         slot = _roundup(rows * pz * eb, 128)
