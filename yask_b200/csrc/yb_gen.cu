@@ -257,7 +257,7 @@ struct GenEngine : Engine {
                 }
                 const int64_t nb = int64_t(SP.nzb) * SP.nyb * SP.nchunks;
                 if (nb >= (int64_t(1) << 31)) return set_error(YB_EUNSUPPORTED, "domain too large for the sweep kernels");
-                sfn<<<unsigned(nb), GEN_SW_TZ, sw.smem, st>>>(SP);
+                sfn<<<unsigned(nb), GEN_SW_THREADS, sw.smem, st>>>(SP);
                 YB_CUDA(cudaGetLastError());
                 n++;
                 continue;

@@ -1,7 +1,7 @@
 // "Sweep" variant of the emitter-generated kernels: TMA-staged shared-memory planes with the same 2.5-D march along x
 // as the hand-written iso3dfd kernel, for multi-var stencils.  EXPERIMENTAL (option gen_sweep=1, off by default).
 //
-// A CTA of 128 threads owns a (TY rows x 128 z) tile and marches over a chunk of x planes.  Every full-rank var the
+// A CTA of 256 threads (two row groups of 128) owns a (TY rows x 128 z) tile and marches over a chunk of x planes.  Every full-rank var the
 // part reads is a *stream*: its planes arrive by TMA (cp.async.bulk.tensor.3d, box = tile + the stream's y/z reach)
 // into a shared-memory ring of (x reach + PF) slots, PF planes ahead of their first use, and complete on one mbarrier
 // per sweep iteration.  The statements are the same as in the direct kernel (same order, same rounding); only the
@@ -14,7 +14,8 @@
 namespace yb { namespace gen {
 
 constexpr int GEN_SW_MAX_STREAMS = 24;
-constexpr int GEN_SW_TZ = 128;          // z extent of a tile = threads per CTA
+constexpr int GEN_SW_TZ = 128;          // z extent of a tile
+constexpr int GEN_SW_THREADS = 256;     // two row groups of GEN_SW_TZ threads: thread (tz, g) computes rows g*TY/2 .. g*TY/2 + TY/2 - 1
 
 struct GenSweepParams {
     GenParams g;                               // box, pointers and strides as for the direct kernel
@@ -45,7 +46,8 @@ struct GenSweepParams {
     const int y0_ = P.yb + sw_by * SW_TY;                                                                    \
     const int xs = P.xb + sw_bc * SP.lx;                                                                     \
     const int sw_len = min(SP.lx, P.xe - xs);                                                                \
-    const int tz = int(threadIdx.x);                                                                         \
+    const int tz = int(threadIdx.x) & (GEN_SW_TZ - 1);                                                       \
+    const int sw_rb = (int(threadIdx.x) / GEN_SW_TZ) * (SW_TY / 2);   /* first row of this thread's group */  \
     const int z = z0 + tz;                                                                                   \
     if (threadIdx.x == 0) {                                                                                  \
         for (int b = 0; b < SW_NB; b++) mbar_init(&sw_bar[b], 1);                                            \
@@ -64,9 +66,9 @@ struct GenSweepParams {
                     SP.py + y0_ + (YL), SP.px + xs + j + (XR));                                              \
     }
 
-// Base pointer of stream k's plane x+dx for this thread: row (YL) of the box, this thread's z column.
-#define SW_PLANE(OFF, SLOT, NS, XL, ZL, dx)                                                                  \
-    (reinterpret_cast<const T*>(sw_smem + (OFF) + ((unsigned(it) + unsigned((dx) - (XL))) % unsigned(NS)) * (SLOT)) + (tz - (ZL)))
+// Base pointer of stream k's plane x+dx for this thread: box row (YL) of the thread's first row, its z column.
+#define SW_PLANE(OFF, SLOT, NS, XL, ZL, dx, PZ)                                                              \
+    (reinterpret_cast<const T*>(sw_smem + (OFF) + ((unsigned(it) + unsigned((dx) - (XL))) % unsigned(NS)) * (SLOT)) + (tz - (ZL)) + sw_rb * (PZ))
 #endif
 
 } }  // namespace yb::gen

@@ -584,6 +584,7 @@ def _stage_sequence(ir, st):
 # ----------------------------------------------------------------------------------------------------
 SWEEP_TZ = 128
 SWEEP_SMEM_LIMIT = 200 * 1024
+SWEEP_TWO_CTA_SMEM = 113 * 1024
 SWEEP_MAX_STREAMS = 24
 
 
@@ -591,12 +592,20 @@ def _roundup(v, m):
     return (v + m - 1) // m * m
 
 
-def sweep_plan(ir, p, ty=4, pf=2):
+def sweep_plan(ir, p, ty=4, pf=None):
     """Shared-memory layout of part `p` for the sweep kernel, or None when the part does not qualify: 3-D solutions,
     unconditional non-scratch parts, full-rank outputs, no misc-dim vars among the full-rank reads, and rings that
     fit in shared memory (x reach + pf slots per stream)."""
     if len(ir["domain_dims"]) != 3 or p.get("cond") or p.get("step_cond") or p.get("scratch") or p.get("children"):
         return None
+    if pf is None:
+        # two planes of prefetch unless one plane lets two CTAs share an SM (2 x 113 KB)
+        plan = sweep_plan(ir, p, ty, 2)
+        if plan and plan["smem"] > SWEEP_TWO_CTA_SMEM:
+            plan1 = sweep_plan(ir, p, ty, 1)
+            if plan1 and plan1["smem"] <= SWEEP_TWO_CTA_SMEM:
+                return plan1
+        return plan or sweep_plan(ir, p, ty, 1)
     masks = _masks(ir, p)
     if any(masks[o["access"]] != 7 for o in p["outputs"]):
         return None
@@ -643,10 +652,10 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     masks = _masks(ir, p)
     sidx = {s_["acc"]: k for k, s_ in enumerate(plan["streams"])}
     L = []
-    L.append(f"// sweep variant of part '{p['name']}' (yb_gen_sweep.cuh): {len(plan['streams'])} TMA streams, {plan['ty']} rows x {SWEEP_TZ} z per CTA, "
+    L.append(f"// sweep variant of part '{p['name']}' (yb_gen_sweep.cuh): {len(plan['streams'])} TMA streams, {plan['ty']} rows x {SWEEP_TZ} z per CTA (256 threads), "
              f"{plan['pf']} planes of prefetch, {plan['smem']} B of shared memory")
     L.append("template <typename T, int MODE>")
-    L.append(f"__global__ void __launch_bounds__(GEN_SW_TZ) {ident}_{p['name']}_sweep_kernel(const __grid_constant__ GenSweepParams SP) {{")
+    L.append(f"__global__ void __launch_bounds__(GEN_SW_THREADS) {ident}_{p['name']}_sweep_kernel(const __grid_constant__ GenSweepParams SP) {{")
     L.append(f"    GEN_SWEEP_BEGIN({plan['ty']}, {plan['pf']})")
     L.append("    auto sw_issue = [&](int j) {     // everything first needed at sweep iteration j")
     L.append("        uint64_t* bar = &sw_bar[j % SW_NB];")
@@ -672,9 +681,9 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
         s_ = plan["streams"][k]
         nm = f"s{k}_{'m' if dx < 0 else 'p'}{abs(dx)}"
         used[(k, dx)] = nm
-        L.append(f"        const T* {nm} = SW_PLANE({s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['zl']}, {dx});")
-    L.append("        _Pragma(\"unroll\") for (int r = 0; r < SW_TY; r++) {")
-    L.append("            const int y = y0_ + r;")
+        L.append(f"        const T* {nm} = SW_PLANE({s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['zl']}, {dx}, {s_['pz']});")
+    L.append("        _Pragma(\"unroll\") for (int r = 0; r < SW_TY / 2; r++) {     // r: row within this thread's group")
+    L.append("            const int y = y0_ + sw_rb + r;")
     L.append("            if (y < P.ye && z < P.ze) {")
 
     for st in p["stmts"]:
