@@ -3,6 +3,13 @@ import sys
 
 import pytest
 
+# The rank-grid tests run up to 8 ranks INSIDE ONE PROCESS on one GPU (2 streams each).  With the default 8 hardware work
+# queues several streams share a queue, and a rank's halo wait kernel (a bounded spin on a peer's flag) at the head of a
+# queue can hold back the very kernel that would publish that flag -> a timing-dependent stall that ends in the wait
+# kernel's trap.  One process per GPU (the product's launch mode) has 2-3 streams and cannot alias.  Must be set before
+# CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
