@@ -182,7 +182,7 @@ def test_device_reductions_match_numpy():
     s.close()
 
 
-@pytest.mark.parametrize("n,steps", [((256, 256, 256), 3), ((300, 130, 200), 2)])
+@pytest.mark.parametrize("n,steps", [((256, 256, 256), 3), ((300, 130, 200), 2), ((1024, 1024, 1024), 2)])   # last: BASELINE.json's full size
 def test_tma_equals_direct_on_device_large(n, steps):
     """Size-independent property: both kernels evaluate the same expression tree, so their results
     must be bit-identical at any size; compared by an order-independent checksum plus a sub-box vs
