@@ -164,7 +164,7 @@ def main_reference(args):
     cb = run_reference_cpu(size, total_steps)
     wall = time.time() - t0
     pts = size ** 3
-    line = {"metric": "GPoints/s, iso3dfd-16 fp32", "value": cb["value"], "unit": "GPoints/s", "impl": "reference", "n_gpus": args.gpus,
+    line = {"metric": f"GPoints/s, iso3dfd-16 fp32 {size}^3 per GPU", "value": cb["value"], "unit": "GPoints/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": pts / (cb["value"] * 1e9) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"iso3dfd r=8 fp32 {size}^3 on the host CPU (reference OpenMP/AVX path)", "wall_s": round(wall, 1)},
@@ -331,7 +331,7 @@ def main_b200(args):
             cpu = {"value": None, "unit": "GPoints/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
 
     if rank == 0:
-        line = {"metric": "GPoints/s, iso3dfd-16 fp32 1024^3 per GPU", "value": round(value, 2), "unit": "GPoints/s", "n_gpus": world,
+        line = {"metric": f"GPoints/s, iso3dfd-16 fp32 {N}^3 per GPU", "value": round(value, 2), "unit": "GPoints/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": round(dev_s / K * 1e3, 4), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"iso3dfd radius 8 (16th order) fp32, {N}^3 points per GPU, rank grid {world}x1x1",
