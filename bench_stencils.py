@@ -10,7 +10,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from tests.golden.make_golden import RANGES, range_of  # value ranges only  (no oracle code is executed)
+from tests.golden.ranges import RANGES, range_of  # value ranges only: pure data, nothing under oracle/ is imported
 from yask_b200 import capi
 from yask_b200.synth import var_salt
 

@@ -7,7 +7,7 @@ import pytest
 
 from oracle import oracle as O
 from tests.helpers import field_ulps, generated_golden_cases, load_golden, range_of, regen_inputs
-from tests.golden.make_golden import RANGES
+from tests.golden.ranges import RANGES
 from yask_b200 import capi, multi
 from yask_b200.synth import hash_field, var_salt
 
