@@ -197,6 +197,16 @@ inline double time_launches(cudaStream_t st, int reps, F fn) {
     return ms;
 }
 
+// Force the (lazily loaded) kernel `fn` into the context now.  CUDA loads a kernel at its first launch, and that load may
+// need the context to go idle; a first launch issued while a halo wait kernel is spinning on a peer whose work the same
+// host thread has not enqueued yet (several ranks driven from ONE process, as the in-process rank-grid tests do) would
+// then never return.  Every kernel the run loop can launch is therefore touched once in prepare().
+inline void preload_kernel(const void* fn) {
+    if (!fn) return;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) (void)cudaGetLastError();
+}
+
 // error plumbing
 int set_error(int code, const char* fmt, ...);
 #define YB_CUDA(call)                                                                              \

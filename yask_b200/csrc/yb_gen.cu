@@ -90,6 +90,12 @@ struct GenEngine : Engine {
         for (auto& st : g.stages)
             for (auto& p : st.parts)
                 if (int(p.acc.size()) > GEN_MAX_ACC) return set_error(YB_EUNSUPPORTED, "part '%s' touches too many vars", p.name);
+        for (auto& st : g.stages)
+            for (auto& p : st.parts)
+                for (int m = 0; m < 2; m++) {
+                    preload_kernel((const void*)p.fn[g.elem_bytes == 8 ? 1 : 0][m]);
+                    preload_kernel((const void*)p.sweep.fn[g.elem_bytes == 8 ? 1 : 0][m]);
+                }
         for (auto& v : scratch)
             if (v.dev) cudaFree(v.dev);
         scratch.clear();

@@ -147,6 +147,10 @@ int halo_prepare(Solution& s) {
     auto* h = new HaloState();
     s.halo = h;
     h->device = s.device;
+    preload_kernel((const void*)halo_push_kernel<float>);
+    preload_kernel((const void*)halo_push_kernel<double>);
+    preload_kernel((const void*)halo_signal_kernel);
+    preload_kernel((const void*)halo_wait_kernel);
     YB_CUDA(cudaMalloc(&h->flags, NDIRS * sizeof(unsigned long long)));
     YB_CUDA(cudaMemset(h->flags, 0, NDIRS * sizeof(unsigned long long)));
     h->dirty.resize(s.vars.size());

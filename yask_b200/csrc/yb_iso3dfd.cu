@@ -279,7 +279,12 @@ struct IsoEngine : Engine {
                 }
             }
             maps_ok = true;
+            const TileCfg& c = radius == 8 ? tile_cfg(tile) : *iso_radius_cfg(radius);
+            for (int m = 0; m < 4; m++) preload_kernel((const void*)c.fn[m]);
         }
+        preload_kernel((const void*)iso3dfd_direct_kernel<0>);
+        preload_kernel((const void*)iso3dfd_direct_kernel<1>);
+        preload_kernel((const void*)iso3dfd_direct_kernel<2>);
         return 0;
     }
 
