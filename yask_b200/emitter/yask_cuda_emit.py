@@ -592,12 +592,16 @@ def _roundup(v, m):
     return (v + m - 1) // m * m
 
 
-def sweep_plan(ir, p, ty=4, pf=None):
+def sweep_plan(ir, p, ty=None, pf=None):
     """Shared-memory layout of part `p` for the sweep kernel, or None when the part does not qualify: 3-D solutions,
     unconditional non-scratch parts, full-rank outputs, no misc-dim vars among the full-rank reads, and rings that
     fit in shared memory (x reach + pf slots per stream)."""
     if len(ir["domain_dims"]) != 3 or p.get("cond") or p.get("step_cond") or p.get("scratch") or p.get("children"):
         return None
+    if ty is None:
+        ty = int(os.environ.get("YB_EMIT_SWEEP_TY", "4"))      # rows per tile (even: two row groups); tuning knob
+    if pf is None and os.environ.get("YB_EMIT_SWEEP_PF"):
+        pf = int(os.environ["YB_EMIT_SWEEP_PF"])                # planes of prefetch; default: chosen below
     if pf is None:
         # two planes of prefetch unless one plane lets two CTAs share an SM (2 x 113 KB)
         plan = sweep_plan(ir, p, ty, 2)
