@@ -177,6 +177,11 @@ int yb_var_set_slice_same(yb_solution* s, int var, double value, const int64_t* 
 /* Deterministic synthetic data on the device: value = lo + (hi-lo)*u(hash(seed, salt, global idx))
  * over the rank's halo box of API step `step` (same function as yask_b200/synth.py). */
 int yb_var_fill_hash(yb_solution* s, int var, int64_t step, uint32_t seed, uint32_t salt, double lo, double hi);
+/* Same, with `shift[d]` (one entry per solution domain dim; NULL = zeros) added to the global index of every point:
+ * a small stand-alone solution can then hold exactly the values a window of a larger (multi-rank) problem holds --
+ * bench.py's halo check recomputes the rank interfaces this way. */
+int yb_var_fill_hash_shifted(yb_solution* s, int var, int64_t step, uint32_t seed, uint32_t salt, double lo, double hi,
+                             const int64_t* shift);
 /* Order-independent 64-bit checksum (sum of per-element bit patterns mixed with the global index)
  * over the rank-domain box of API step `step`. */
 int yb_var_checksum(yb_solution* s, int var, int64_t step, uint64_t* out);

@@ -13,8 +13,14 @@
 # but shipped by gpurun) and never needs /root/reference.
 #
 # usage: [REF_ALL=1] oracle/build_ref.sh [arch]     (arch: avx512 (default) | avx2 | intel64)
-#   default: the iso3dfd reference only (what bench.py's CPU arm and the iso3dfd fixtures need; ~2 min);
+#   default: the references bench.py's CPU arms and the live-reference tests need: iso3dfd (default + strict),
+#            awp_elastic fp32 and ssg fp64 (default flags), ~4 min;
 #   REF_ALL=1: every solution the golden fixtures were generated from (~90 kernel builds, over an hour).
+#
+# Outputs: oracle/_ref/yask/  the reference's own output tree (stays in the build container);
+#          oracle/_ref/ship/  the few binaries the GPU box runs (copied from the tree; travels with gpurun);
+#          tools/_refc/       the reference's stencil COMPILER, which the product's build-time CUDA emitter
+#                             (yask_b200/emitter) drives as its front-end -- a build tool, not part of the oracle.
 set -e
 REF=${YASK_REFERENCE:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -30,10 +36,17 @@ mkdir -p "$OUT"
 LOG=$HERE/_ref/build.log
 : > "$LOG"
 
-if [ ! -x "$OUT/bin/yask_compiler.exe" ]; then
-    echo "[build_ref] yask compiler"
-    make -C "$REF/src/compiler" YASK_OUTPUT_DIR="$OUT" mpi=0 arch=$ARCH -j$J compiler >> "$LOG" 2>&1
+REFC=$(cd "$HERE/.." && pwd)/tools/_refc
+if [ ! -x "$REFC/bin/yask_compiler.exe" ]; then
+    echo "[build_ref] yask compiler -> tools/_refc"
+    mkdir -p "$REFC"
+    make -C "$REF/src/compiler" YASK_OUTPUT_DIR="$REFC" mpi=0 arch=$ARCH -j$J compiler >> "$LOG" 2>&1
+    rm -rf "$REFC/build"
 fi
+# the reference's kernel makefile looks for the compiler in its own output tree
+mkdir -p "$OUT/bin" "$OUT/lib"
+ln -sf "$REFC/bin/yask_compiler.exe" "$OUT/bin/yask_compiler.exe"
+ln -sf "$REFC/lib/libyask_compiler.so" "$OUT/lib/libyask_compiler.so"
 
 # stencil  suffix  real_bytes  extra-make-args
 build_kernel() {
@@ -54,10 +67,12 @@ build_kernel() {
 # "-strict" (-ffp-contract=off: pure IEEE mul/add in DSL order), SURVEY.md section 7 hard part 1.
 build_kernel iso3dfd ""        4
 build_kernel iso3dfd "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
-if [ "${REF_ALL:-0}" = "1" ]; then
+if [ "$ARCH" = "avx512" ]; then
     build_kernel awp_elastic ""        4
-    build_kernel awp_elastic "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     build_kernel ssg "-fp64"        8
+fi
+if [ "${REF_ALL:-0}" = "1" ]; then
+    build_kernel awp_elastic "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     build_kernel ssg "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
     build_kernel iso3dfd "-fp64"        8
     build_kernel iso3dfd "-fp64-strict" 8 EXTRA_YK_CXXFLAGS=-ffp-contract=off
@@ -77,6 +92,14 @@ if [ "${REF_ALL:-0}" = "1" ]; then
     done
 fi
 # Strip debug info (the reference builds with -g) and drop the (large) intermediate build tree.
-strip --strip-debug "$OUT"/lib/*.so "$OUT"/bin/*.exe "$OUT"/bin/ref_driver.* 2>/dev/null || true
+strip --strip-debug "$OUT"/lib/libyask_kernel.*.so "$OUT"/bin/yask_kernel.*.exe "$OUT"/bin/ref_driver.* 2>/dev/null || true
 if [ "${KEEP_BUILD:-0}" != "1" ]; then rm -rf "$OUT/build"; fi
+# what the GPU box runs: the reference harnesses of the three benchmarked stencils and the iso3dfd API drivers
+SHIP=$HERE/_ref/ship
+mkdir -p "$SHIP/bin" "$SHIP/lib"
+for tag in iso3dfd.$ARCH iso3dfd-strict.$ARCH awp_elastic.$ARCH ssg-fp64.$ARCH; do
+    [ -f "$OUT/lib/libyask_kernel.$tag.so" ] || continue
+    cp -u "$OUT/lib/libyask_kernel.$tag.so" "$SHIP/lib/"
+    cp -u "$OUT/bin/yask_kernel.$tag.exe" "$OUT/bin/ref_driver.$tag" "$SHIP/bin/" 2>/dev/null || true
+done
 echo "[build_ref] done: $(ls "$OUT/bin" | grep -c ref_driver) reference driver(s) under $OUT/bin"

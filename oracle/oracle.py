@@ -157,7 +157,10 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
 # ---------------------------------------------------------------------------------------
 # Prebuilt reference (oracle/_ref): only usable where build_ref.sh has been run.
 # ---------------------------------------------------------------------------------------
+# The build container has the reference's whole output tree (_ref/yask); the GPU box only what build_ref.sh staged (_ref/ship).
 REF_BIN = os.path.join(HERE, "_ref", "yask", "bin")
+if not os.path.isdir(REF_BIN):
+    REF_BIN = os.path.join(HERE, "_ref", "ship", "bin")
 
 
 def ref_available(tag: str) -> bool:

@@ -1,5 +1,5 @@
 """The CUDA emitter (yask_b200/emitter/yask_cuda_emit.py) re-run on the reference compiler's output must reproduce the
-committed generated sources (kernels + oracle restatement) -- build container only (needs oracle/_ref's yask_compiler.exe);
+committed generated sources (kernels + oracle restatement) -- build container only (needs tools/_refc/bin/yask_compiler.exe, built by oracle/build_ref.sh);
 plus parser unit checks that need no reference."""
 import json
 import os

@@ -59,7 +59,7 @@ def test_bit_exact_vs_reference_golden(path, kernel):
 
 
 @pytest.mark.parametrize("fp_mode", [0, 1, 2])
-@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("tile", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("n,steps,lx", [((40, 70, 150), 2, 16), ((17, 33, 65), 3, 7), ((64, 64, 128), 1, 128), ((9, 8, 16), 2, 4)])
 def test_tma_kernel_vs_oracle(n, steps, lx, tile, fp_mode):
     ins = synth_inputs(n, 99)
@@ -135,7 +135,7 @@ def test_auto_tuner_picks_a_variant_and_results_stay_exact():
     rep = s.run_auto_tuner_now()
     assert "best: tile=" in rep and rep.count("ms/step") >= 6, rep
     assert s.get_stats().num_steps_done == 0
-    assert int(s.get_option("tile")) in (2, 3, 8, 9, 10, 11)
+    assert int(s.get_option("tile")) in (0, 1, 4, 5, 6, 7)
     ins = {("p", t): hash_field(seed, var_salt("p", t), (-8, -8, -8), [i + 16 for i in n], -1, 1) for t in (0, 1)}
     vv = hash_field(seed, var_salt("v", 0), (0, 0, 0), n, 0.05, 0.3)
     p, v = s.get_var("p"), s.get_var("v")

@@ -34,7 +34,7 @@ if __name__ == "__main__":
     variants = []
     for rep in range(2):
         for (cs, pc, ph) in ((0, 0, 0), (1, 0, 0), (1, 2, 0), (1, 2, 2), (0, 2, 2), (1, 0, 2)):
-            variants.append(dict(kernel="tma", tile=11, st_cs=cs, pol_c=pc, pol_h=ph))
+            variants.append(dict(kernel="tma", tile=7, st_cs=cs, pol_c=pc, pol_h=ph))
     for opts in variants:
         steps = 3 if opts.get("kernel") == "direct" else 40
         g, ms, cs = run(n, steps, 3, **opts)

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "yb_get_first_rank_domain_index", "yb_get_last_rank_domain_index", "yb_set_option", "yb_get_option", "yb_set_stream",
     "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_create", "yb_var_set_min_pad",
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
-    "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_var_fill_hash", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
+    "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_var_fill_hash", "yb_var_fill_hash_shifted", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
     "yb_exchange_halos",
 ]
@@ -113,6 +113,7 @@ def lib() -> C.CDLL:
         L.yb_var_set_slice_same.argtypes = [p, i32, C.c_double, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         L.yb_var_reduce_slice.argtypes = [p, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_double), C.POINTER(i64)]
         L.yb_var_fill_hash.argtypes = [p, i32, i64, C.c_uint32, C.c_uint32, C.c_double, C.c_double]
+        L.yb_var_fill_hash_shifted.argtypes = [p, i32, i64, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.POINTER(i64)]
         L.yb_var_checksum.argtypes = [p, i32, i64, C.POINTER(C.c_uint64)]
         L.yb_var_device_ptr.argtypes = [p, i32, i64, C.POINTER(p)]
         L.yb_solution_run.argtypes = [p, i64, i64]
@@ -224,8 +225,14 @@ class Var:
         _chk(lib().yb_var_reduce_slice(self.soln._h, self.index, _arr(first), _arr(last), out, C.byref(n)))
         return {"num": n.value, "sum": out[0], "sum_squares": out[1], "product": out[2], "max": out[3], "min": out[4]}
 
-    def fill_hash(self, step: int, seed: int, salt: int, lo: float, hi: float):
-        _chk(lib().yb_var_fill_hash(self.soln._h, self.index, int(step), seed & 0xFFFFFFFF, salt & 0xFFFFFFFF, lo, hi))
+    def fill_hash(self, step: int, seed: int, salt: int, lo: float, hi: float, shift: Sequence[int] | None = None):
+        """Hash field over the rank's halo box of `step`; `shift` (per solution domain dim) moves the window of global
+        indices the values are drawn from."""
+        if shift is None:
+            _chk(lib().yb_var_fill_hash(self.soln._h, self.index, int(step), seed & 0xFFFFFFFF, salt & 0xFFFFFFFF, lo, hi))
+        else:
+            _chk(lib().yb_var_fill_hash_shifted(self.soln._h, self.index, int(step), seed & 0xFFFFFFFF, salt & 0xFFFFFFFF, lo, hi,
+                                                _arr(list(shift) + [0] * (3 - len(shift)))))
 
     def checksum(self, step: int) -> int:
         out = C.c_uint64(0)

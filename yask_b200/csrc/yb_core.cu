@@ -613,6 +613,11 @@ static void var_box(const Var& v, int64_t step, bool with_halo, int64_t* first, 
 }
 
 int yb_var_fill_hash(yb_solution* s_, int var, int64_t step, uint32_t seed, uint32_t salt, double lo, double hi) {
+    return yb_var_fill_hash_shifted(s_, var, step, seed, salt, lo, hi, nullptr);
+}
+
+int yb_var_fill_hash_shifted(yb_solution* s_, int var, int64_t step, uint32_t seed, uint32_t salt, double lo, double hi,
+                             const int64_t* shift) {
     Solution* s = SOL(s_);
     if (int rc = check_var(s, var)) return rc;
     if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
@@ -622,6 +627,19 @@ int yb_var_fill_hash(yb_solution* s_, int var, int64_t step, uint32_t seed, uint
     Slice sl;
     if (int rc = resolve_slice(*s, v, first, last, false, sl)) return rc;
     YB_CUDA(cudaSetDevice(s->device));
+    if (shift) {
+        // sl.g0 holds the global index of the box origin for the LAST three non-step dims (left padded); add the shift of
+        // the domain dims among them
+        int nns = 0;
+        for (auto& d : v.dims) nns += d.spec.kind != DIM_STEP;
+        int k = 0;
+        for (auto& d : v.dims) {
+            if (d.spec.kind == DIM_STEP) continue;
+            const int pos = nns <= 3 ? 3 - nns + k : (k == 0 ? 3 : k - 1);
+            if (d.spec.kind == DIM_DOMAIN) sl.g0[pos] += shift[d.spec.domain_index];
+            k++;
+        }
+    }
     if (int rc = launch_hash_fill(v.slot_ptr(v.slot_of(step)), sl.bc, sl.g0, v.elem_bytes, seed, salt, lo, hi, s->stream())) return rc;
     v.update_valid_step(step);
     if (s->halo) halo_mark_dirty(*s, var);
@@ -665,18 +683,38 @@ int yb_copy_to_host(void* host_dst, const void* dev_src, size_t bytes) {
 }
 
 // ---- run_solution ----------------------------------------------------------------------------------
-// Mirrors /root/reference/src/kernel/lib/context.cpp:220-624 for the no-wave-front case: for each
-// step, for each stage: [exterior slabs -> start exchange] -> interior -> finish exchange.
+// Mirrors /root/reference/src/kernel/lib/context.cpp:220-624 for the no-wave-front case.  Single rank: one launch per
+// stage part over the whole rank box.  Multi-rank (halo_run_stage, yb_halo.cu): for each step, for each stage:
+// finish the previous exchange -> exterior slabs -> start this stage's exchange -> interior.
 int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
     Solution* s = SOL(s_);
     if (!s) return set_error(YB_EINVAL, "null solution");
     if (!s->prepared) return set_error(YB_ESTATE, "run_solution() called without calling prepare_solution() first");
     YB_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = s->stream();
-    cudaEvent_t e0, e1;
-    YB_CUDA(cudaEventCreate(&e0));
-    YB_CUDA(cudaEventCreate(&e1));
+    // Timing events: pairs of finished runs are folded into the stats and recycled here, so that calling
+    // run_solution(t) once per step (the reference's usual pattern) keeps a bounded number of events alive.
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    for (size_t i = 0; i < s->pending_events.size();) {
+        auto& pe = s->pending_events[i];
+        float ms = 0;
+        if (cudaEventQuery(pe.second) == cudaSuccess && cudaEventElapsedTime(&ms, pe.first, pe.second) == cudaSuccess) {
+            s->stats.elapsed_secs += double(ms) * 1e-3;
+            if (!e0) { e0 = pe.first; e1 = pe.second; }
+            else { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+            s->pending_events.erase(s->pending_events.begin() + i);
+        } else {
+            (void)cudaGetLastError();
+            i++;
+        }
+    }
+    if (!e0) {
+        YB_CUDA(cudaEventCreate(&e0));
+        if (cudaEventCreate(&e1) != cudaSuccess) { cudaEventDestroy(e0); return set_error(YB_ECUDA, "cudaEventCreate failed"); }
+    }
+    s->pending_events.emplace_back(e0, e1);     // owned by the solution from here on (drained by get_stats / the next run)
     YB_CUDA(cudaEventRecord(e0, st));
+    YB_CUDA(cudaEventRecord(e1, st));           // placeholder so that the pair is always complete; re-recorded below
     Box whole;
     for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = d < s->ndd ? s->rank_size[d] : 1; }
     int64_t pts = whole.points();
@@ -700,8 +738,8 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
         }
         s->stats.num_steps_done++;
     }
+    if (s->halo && rc >= 0) rc = halo_finish(*s, st);   // the last exchange completes inside the run (and its timing)
     YB_CUDA(cudaEventRecord(e1, st));
-    s->pending_events.emplace_back(e0, e1);
     return rc < 0 ? rc : 0;
 }
 

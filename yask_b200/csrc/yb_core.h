@@ -130,6 +130,10 @@ struct Engine {
     // `stream`, keep the fastest, describe the trials in `report`.  Var contents are not preserved.  Default: nothing to tune.
     virtual int auto_tune(Solution&, cudaStream_t, std::string& report) { report = "nothing to tune"; return 0; }
     virtual bool get_option(const Solution&, const std::string&, std::string&) const { return false; }
+    // May stage `stage` be evaluated as several sub-box launches (exterior slabs first, interior last)?  False when the
+    // result of a launch depends on what an earlier launch of the same stage wrote (scratch vars computed from vars the
+    // stage updates in place).
+    virtual bool can_split(const Solution&, int /*stage*/) const { return true; }
 };
 
 struct HaloState;  // yb_halo.cu
@@ -170,7 +174,14 @@ struct Solution {
     // Fused halo stores (set by the halo layer before a stage launch, consumed by an engine that can store its
     // boundary planes straight into the x neighbours' halo cells): element (0,0,0)-relative base pointers of the
     // OUTPUT var's step slot in the lower / upper x neighbour, or null.  The engine sets `used` if it honoured them.
-    struct FusedX { void* lo = nullptr; void* hi = nullptr; int var = -1; bool used = false; } fused_x;
+    // In-kernel completion signal: when `counter` is set the engine may ALSO publish `epoch` into the x neighbours'
+    // flag words itself, as soon as its boundary planes are stored (it then sets `signalled`), so that the exchange
+    // overlaps the interior of the same launch.
+    struct FusedX {
+        void* lo = nullptr; void* hi = nullptr; int var = -1; bool used = false;
+        unsigned long long* flag_lo = nullptr; unsigned long long* flag_hi = nullptr;
+        unsigned long long epoch = 0; unsigned int* counter = nullptr; bool signalled = false;
+    } fused_x;
     int multi_rank() const { return int(num_ranks[0] * num_ranks[1] * num_ranks[2]) > 1; }
     ~Solution();
 };

@@ -45,6 +45,7 @@ struct BlobVar {
 struct Blob {
     uint32_t magic, version;
     int64_t pid;
+    uint64_t nonce;       // identifies the exporting PROCESS (pids repeat across pid namespaces that share an IPC namespace)
     int32_t device;
     int32_t num_vars;
     int64_t rank_index[3];
@@ -53,6 +54,18 @@ struct Blob {
     uint64_t flags_raw;
     BlobVar vars[MAX_VARS];
 };
+
+// One random word per process, drawn at first use: raw device pointers of a blob are honoured only when the blob was
+// exported by this very process (same nonce); everything else goes through the IPC handles.
+uint64_t process_nonce() {
+    static uint64_t n = 0;
+    if (!n) {
+        FILE* f = fopen("/dev/urandom", "rb");
+        if (f) { if (fread(&n, sizeof n, 1, f) != 1) n = 0; fclose(f); }
+        if (!n) n = (uint64_t(getpid()) << 32) ^ uint64_t(reinterpret_cast<uintptr_t>(&n)) ^ 0x9e3779b97f4a7c15ull;
+    }
+    return n;
+}
 
 inline int dir_index(const int d[3]) { return (d[0] + 1) * 9 + (d[1] + 1) * 3 + (d[2] + 1); }
 
@@ -127,6 +140,9 @@ struct HaloState {
     std::vector<std::vector<char>> dirty;   // [var][slot]
     bool finalized = false;
     int device = -1;
+    bool wait_pending = false;              // the neighbours' epoch `epoch` has not been waited for yet
+    unsigned int wait_mask = 0;
+    unsigned int* sig_counter = nullptr;    // device word: arrivals of the in-kernel boundary signal (yb_iso3dfd.cuh)
 };
 
 void halo_free(HaloState* h) {
@@ -135,6 +151,7 @@ void halo_free(HaloState* h) {
         if (!nb.same_process)
             for (void* p : nb.opened) cudaIpcCloseMemHandle(p);
     if (h->flags) cudaFree(h->flags);
+    if (h->sig_counter) cudaFree(h->sig_counter);
     delete h;
 }
 
@@ -153,6 +170,8 @@ int halo_prepare(Solution& s) {
     preload_kernel((const void*)halo_wait_kernel);
     YB_CUDA(cudaMalloc(&h->flags, NDIRS * sizeof(unsigned long long)));
     YB_CUDA(cudaMemset(h->flags, 0, NDIRS * sizeof(unsigned long long)));
+    YB_CUDA(cudaMalloc(&h->sig_counter, 256));
+    YB_CUDA(cudaMemset(h->sig_counter, 0, 256));
     h->dirty.resize(s.vars.size());
     for (size_t i = 0; i < s.vars.size(); i++) h->dirty[i].assign(s.vars[i].step_alloc(), 1);  // everything starts dirty (context.hpp:545-549)
     int d[3];
@@ -260,20 +279,37 @@ static int push_var_slot(Solution& s, const Neighbor& nb, int vi, int slot, cuda
     return launched;
 }
 
-// skip_var/skip_x: the stage kernel already stored this var's x-face halos into the peers (fused path).
-static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var) {
+// Enqueue the wait for the exchange that is still in flight (if any): the neighbours' epoch `h->epoch` must have
+// arrived before (a) anything of this rank reads its halo cells again and (b) this rank overwrites the neighbours'
+// halo cells again (WAR: a neighbour publishes its epoch only after the launches that read those cells).
+static int halo_flush_wait(Solution& s, cudaStream_t st) {
+    HaloState* h = s.halo;
+    if (!h || !h->wait_pending) return 0;
+    halo_wait_kernel<<<1, 1, 0, st>>>(h->flags, h->wait_mask, h->epoch);
+    YB_CUDA(cudaGetLastError());
+    h->wait_pending = false;
+    return 0;
+}
+
+// Push every dirty var/slot to the neighbours that need it and publish the next epoch.  The matching wait is left
+// pending (halo_flush_wait) so that whatever the caller enqueues next overlaps the transfer.
+//   skip_var:  the stage kernel already stored this var's x-face halos into the peers (fused path)
+//   signalled: ... and already published the epoch to the pure x neighbours itself
+static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var, bool signalled) {
     HaloState* h = s.halo;
     if (!h) return 0;
     if (!h->finalized) return set_error(YB_ESTATE, "multi-rank solution: halo peers were not connected (yb_halo_import/finalize)");
+    if (int rc = halo_flush_wait(s, st)) return rc;
     // Always a full handshake (even with nothing dirty): exchanges are collective, and every rank must
     // advance its epoch in lock-step with its neighbours.
     h->epoch++;
     unsigned int mask = 0;
     int launched = 0;
     for (auto& nb : h->nbrs) {
+        const bool pure_x = nb.dir[0] != 0 && nb.dir[1] == 0 && nb.dir[2] == 0;
         for (size_t vi = 0; vi < s.vars.size(); vi++) {
             if (!var_talks_to(s.vars[vi], nb.dir)) continue;
-            if (int(vi) == skip_var && nb.dir[0] != 0 && nb.dir[1] == 0 && nb.dir[2] == 0) continue;   // done by the kernel
+            if (int(vi) == skip_var && pure_x) continue;   // done by the kernel
             for (int slot = 0; slot < s.vars[vi].step_alloc(); slot++) {
                 if (!h->dirty[vi][slot]) continue;
                 int rc = push_var_slot(s, nb, int(vi), slot, st);
@@ -283,38 +319,64 @@ static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var) {
         }
         int opp[3] = {-nb.dir[0], -nb.dir[1], -nb.dir[2]};
         // I am the peer's neighbour in direction `opp`; the peer waits on flags[dir_index(opp)]
-        halo_signal_kernel<<<1, 1, 0, st>>>(nb.peer_flags + dir_index(opp), h->epoch);
+        if (!(signalled && pure_x)) halo_signal_kernel<<<1, 1, 0, st>>>(nb.peer_flags + dir_index(opp), h->epoch);
         mask |= 1u << dir_index(nb.dir);
     }
-    halo_wait_kernel<<<1, 1, 0, st>>>(h->flags, mask, h->epoch);
     YB_CUDA(cudaGetLastError());
+    h->wait_pending = true;
+    h->wait_mask = mask;
     for (auto& dv : h->dirty)
         for (auto& f : dv) f = 0;
     s.stats.kernel_launches += launched;
     return 0;
 }
 
-int halo_exchange_all(Solution& s, cudaStream_t st) { return halo_exchange_impl(s, st, -1); }
+// Explicit exchange (yk_solution::exchange_halos, the start and the end of run_solution): complete on return of the stream.
+int halo_exchange_all(Solution& s, cudaStream_t st) {
+    if (int rc = halo_exchange_impl(s, st, -1, false)) return rc;
+    return halo_flush_wait(s, st);
+}
 
-// One stage of one step on a multi-rank solution.  Round 1: whole-domain compute, then push + wait
-// (the face transfer is ~1-2 % of a step at 1024^3 per GPU; the boundary-first overlap of
-// context.cpp:378-475 is replaced in a later step by a kernel that stores to the peers directly).
+int halo_finish(Solution& s, cudaStream_t st) { return halo_flush_wait(s, st); }
+
+// Is anything but `var`'s slot `slot` waiting to be pushed?  (The in-kernel signal may only be used when the kernel's
+// own stores are the whole exchange.)
+static bool other_dirty(const HaloState* h, int var, int slot) {
+    for (size_t vi = 0; vi < h->dirty.size(); vi++)
+        for (size_t sl = 0; sl < h->dirty[vi].size(); sl++)
+            if (h->dirty[vi][sl] && !(int(vi) == var && int(sl) == slot)) return true;
+    return false;
+}
+
+// One stage of one step on a multi-rank solution, ordered as the reference orders it
+// (/root/reference/src/kernel/lib/context.cpp:378-475, halo.cpp:494-574): wait for the previous exchange, evaluate the
+// EXTERIOR (the slabs the neighbours need) first, start the exchange, evaluate the interior while the halos travel.
+// The wait for this exchange is enqueued in front of the next stage.  Three forms:
+//   * fused (iso3dfd sweep kernel, x neighbours only): ONE launch whose first work units are the boundary planes; it
+//     stores them into the neighbours' HBM as it computes them and publishes the epoch itself (IsoParams::sig_*);
+//   * split: one launch per exterior slab, push kernels + epoch publication, then the interior launch;
+//   * whole (domain too thin to split, stages with scratch vars, option overlap_comms=0): whole box, then push.
 int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
     Box whole;
     for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = d < s.ndd ? s.rank_size[d] : 1; }
     HaloState* h = s.halo;
     if (!h->finalized) return set_error(YB_ESTATE, "multi-rank solution: halo peers were not connected (yb_halo_import/finalize)");
-    // Fused path: if the stage writes exactly one var, hand the engine the x neighbours' halo cells of that
-    // var's output slot; an engine that can (the iso3dfd sweep kernel) stores its first/last planes there while it
-    // computes them, so that transfer rides on the sweep instead of following it.
+    if (int rc = halo_flush_wait(s, st)) return rc;
+    const StageSpec& sp = s.spec.stages[stage];
+    auto mark_outputs_dirty = [&]() {
+        for (int vi : sp.outputs) h->dirty[vi][s.vars[vi].slot_of(t + sp.out_step_off)] = 1;
+    };
+    auto opt_off = [&](const char* key) { auto it = s.options.find(key); return it != s.options.end() && it->second == "0"; };
+    const bool overlap = !opt_off("overlap_comms");
+
+    // ---- fused path -----------------------------------------------------------------------------------------
     s.fused_x = Solution::FusedX();
-    const auto& outs = s.spec.stages[stage].outputs;
-    auto fo = s.options.find("fused_halo");
-    const bool want_fused = fo == s.options.end() || fo->second != "0";
-    if (outs.size() == 1 && want_fused) {
-        const int vi = outs[0];
+    bool only_x = !h->nbrs.empty();
+    for (auto& nb : h->nbrs) only_x = only_x && nb.dir[1] == 0 && nb.dir[2] == 0;
+    if (sp.outputs.size() == 1 && !opt_off("fused_halo")) {
+        const int vi = sp.outputs[0];
         const Var& v = s.vars[vi];
-        const int slot = v.slot_of(t + s.spec.stages[stage].out_step_off);
+        const int slot = v.slot_of(t + sp.out_step_off);
         const Dim* dx = v.domain_dim(0);
         for (auto& nb : h->nbrs) {
             if (nb.dir[1] != 0 || nb.dir[2] != 0 || nb.dir[0] == 0 || !dx) continue;
@@ -324,21 +386,73 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
             if (!same) continue;
             char* base = nb.var_base[vi] + size_t(slot) * pg.slot_elems * v.elem_bytes;
             long long origin = pg.pad_l[0] * pg.stride[0] + pg.pad_l[1] * pg.stride[1] + pg.pad_l[2] * pg.stride[2];
-            if (nb.dir[0] < 0) s.fused_x.lo = base + (origin + pg.domain[0] * pg.stride[0]) * v.elem_bytes;      // its right halo starts at its n_x
-            else s.fused_x.hi = base + (origin - dx->domain * pg.stride[0]) * v.elem_bytes;                          // my plane n_x-R.. -> its planes -R..
+            int opp[3] = {-nb.dir[0], 0, 0};
+            if (nb.dir[0] < 0) {
+                s.fused_x.lo = base + (origin + pg.domain[0] * pg.stride[0]) * v.elem_bytes;      // its right halo starts at its n_x
+                s.fused_x.flag_lo = nb.peer_flags + dir_index(opp);
+            } else {
+                s.fused_x.hi = base + (origin - dx->domain * pg.stride[0]) * v.elem_bytes;          // my plane n_x-R.. -> its planes -R..
+                s.fused_x.flag_hi = nb.peer_flags + dir_index(opp);
+            }
             s.fused_x.var = vi;
         }
+        // the kernel may publish the epoch itself when its stores are the whole exchange
+        size_t n_fused = (s.fused_x.lo ? 1 : 0) + (s.fused_x.hi ? 1 : 0);
+        if (s.fused_x.var >= 0 && only_x && n_fused == h->nbrs.size() && overlap && !other_dirty(h, vi, slot)) {
+            s.fused_x.counter = h->sig_counter;
+            s.fused_x.epoch = h->epoch + 1;
+        }
     }
-    int rc = s.engine->launch(s, stage, t, whole, st);
+    if (s.fused_x.var >= 0) {
+        int rc = s.engine->launch(s, stage, t, whole, st);
+        if (rc < 0) return rc;
+        s.stats.kernel_launches += rc;
+        mark_outputs_dirty();
+        const int skip = s.fused_x.used ? s.fused_x.var : -1;
+        const bool signalled = s.fused_x.used && s.fused_x.signalled;
+        s.fused_x = Solution::FusedX();
+        return halo_exchange_impl(s, st, skip, signalled);
+    }
+
+    // ---- split path: exterior slabs, exchange, interior --------------------------------------------------------
+    Box interior = whole;
+    bool split = overlap && s.engine->can_split(s, stage);
+    int64_t w[3] = {0, 0, 0};
+    for (int d = 0; d < s.ndd && split; d++) {
+        if (s.num_ranks[d] <= 1) continue;
+        for (auto& v : s.vars) {
+            const Dim* dd = v.domain_dim(d);
+            if (dd) w[d] = std::max<int64_t>(w[d], std::max(dd->spec.halo_l, dd->spec.halo_r));
+        }
+        if (s.rank_index[d] > 0) interior.b[d] += w[d];
+        if (s.rank_index[d] < s.num_ranks[d] - 1) interior.e[d] -= w[d];
+        if (interior.e[d] - interior.b[d] < 1) split = false;
+    }
+    if (!split) {
+        int rc = s.engine->launch(s, stage, t, whole, st);
+        if (rc < 0) return rc;
+        s.stats.kernel_launches += rc;
+        mark_outputs_dirty();
+        return halo_exchange_impl(s, st, -1, false);
+    }
+    Box cur = whole;
+    for (int d = 0; d < s.ndd; d++) {
+        for (int side = 0; side < 2; side++) {
+            Box slab = cur;
+            if (side == 0) { if (interior.b[d] == whole.b[d]) continue; slab.e[d] = interior.b[d]; }
+            else { if (interior.e[d] == whole.e[d]) continue; slab.b[d] = interior.e[d]; }
+            int rc = s.engine->launch(s, stage, t, slab, st);
+            if (rc < 0) return rc;
+            s.stats.kernel_launches += rc;
+        }
+        cur.b[d] = interior.b[d]; cur.e[d] = interior.e[d];
+    }
+    mark_outputs_dirty();
+    if (int rc = halo_exchange_impl(s, st, -1, false)) return rc;
+    int rc = s.engine->launch(s, stage, t, interior, st);
     if (rc < 0) return rc;
     s.stats.kernel_launches += rc;
-    for (int vi : s.spec.stages[stage].outputs) {
-        const Var& v = s.vars[vi];
-        h->dirty[vi][v.slot_of(t + s.spec.stages[stage].out_step_off)] = 1;
-    }
-    const int skip = s.fused_x.used ? s.fused_x.var : -1;
-    s.fused_x = Solution::FusedX();
-    return halo_exchange_impl(s, st, skip);
+    return 0;
 }
 
 }  // namespace yb
@@ -362,7 +476,7 @@ int yb_halo_export(yb_solution* s_, void* out, size_t nbytes) {
     YB_CUDA(cudaSetDevice(s->device));
     Blob b;
     memset(&b, 0, sizeof b);
-    b.magic = BLOB_MAGIC; b.version = 1; b.pid = int64_t(getpid()); b.device = s->device;
+    b.magic = BLOB_MAGIC; b.version = 2; b.pid = int64_t(getpid()); b.nonce = process_nonce(); b.device = s->device;
     b.num_vars = int(s->vars.size());
     for (int k = 0; k < 3; k++) { b.rank_index[k] = s->rank_index[k]; b.rank_size[k] = s->rank_size[k]; }
     YB_CUDA(cudaIpcGetMemHandle(&b.flags_handle, s->halo->flags));
@@ -400,7 +514,7 @@ int yb_halo_import(yb_solution* s_, int64_t peer_rank_linear, const void* blob, 
         if (nb.peer_linear != peer_rank_linear) continue;
         for (int k = 0; k < 3; k++)
             if (b.rank_index[k] != s->rank_index[k] + nb.dir[k]) return set_error(YB_EINVAL, "blob of rank %lld has unexpected rank index", (long long)peer_rank_linear);
-        nb.same_process = (b.pid == int64_t(getpid()));
+        nb.same_process = (b.nonce == process_nonce());
         for (int i = 0; i < b.num_vars; i++) nb.var_geom[i] = b.vars[i];
         if (nb.same_process) {
             // same process (single-process multi-rank tests): plain pointers; enable peer access if on another device

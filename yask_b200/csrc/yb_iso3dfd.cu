@@ -171,45 +171,26 @@ int make_var_tensor_map(void* map_, const Var& v, int slot, int box_z, int box_y
 
 namespace {
 
-template <class T>
-TileCfg cfg_gen1(const char* name) {
-    return TileCfg{false, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
-                   {iso3dfd_tma_kernel<T, 0>, iso3dfd_tma_kernel<T, 1>, iso3dfd_tma_kernel<T, 2>, nullptr}};
-}
-template <class T>
-TileCfg cfg_gen2(const char* name) {
-    return TileCfg{true, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
-                   {iso3dfd_tma2_kernel<T, 0>, iso3dfd_tma2_kernel<T, 1>, iso3dfd_tma2_kernel<T, 2>, iso3dfd_tma2_kernel<T, 3>}};
-}
-
-template <class T>
-TileCfg cfg_gen3(const char* name) {
-    return TileCfg{false, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS, T::SMEM_BYTES,
-                   {iso3dfd_tma3_kernel<T, 0>, iso3dfd_tma3_kernel<T, 1>, iso3dfd_tma3_kernel<T, 2>, nullptr}};
-}
-
 template <class T, int PW, int U>
-TileCfg cfg_gen2x(const char* name) {
+TileCfg cfg_tile(const char* name) {
     return TileCfg{true, name, T::TY, T::TZ, T::HP, T::HROWS, T::THREADS + 128 * PW, T::SMEM_BYTES,
                    {iso3dfd_tma2_kernel<T, 0, PW, U>, iso3dfd_tma2_kernel<T, 1, PW, U>, iso3dfd_tma2_kernel<T, 2, PW, U>,
                     iso3dfd_tma2_kernel<T, 3, PW, U>}};
 }
 
-constexpr int NTILES = 12;
+// Compiled variants of the sweep kernel for radius 8 (option `tile`): tile shape x producer warpgroup x planes per trip.
+constexpr int NTILES = 8;
+constexpr int DEFAULT_TILE = 7;
 const TileCfg& tile_cfg(int i) {
     static const TileCfg cfgs[NTILES] = {
-        cfg_gen1<IsoTile<8, 32, 16, 5>>("gen1 32x64, 512 thr x 4 pts"),
-        cfg_gen1<IsoTile<8, 16, 32, 5>>("gen1 16x128, 512 thr x 4 pts"),
-        cfg_gen2<IsoTile2<8, 16, 16, 5>>("gen2 32x64, 256 thr x 8 pts (row pairs)"),
-        cfg_gen2<IsoTile2<8, 8, 32, 5>>("gen2 16x128, 256 thr x 8 pts (row pairs)"),
-        cfg_gen3<IsoTile3<8, 16, 16, 11, 3>>("gen3 32x64, row pairs, 11 resident haloed planes"),
-        cfg_gen3<IsoTile3<8, 16, 16, 12, 2>>("gen3 32x64, row pairs, 12 resident haloed planes"),
-        cfg_gen2x<IsoTile2<8, 16, 16, 5>, 1, 1>("gen2 32x64 + producer warp"),
-        cfg_gen2x<IsoTile2<8, 16, 16, 5>, 0, 2>("gen2 32x64, 2 planes per trip"),
-        cfg_gen2x<IsoTile2<8, 8, 32, 5>, 1, 1>("gen2 16x128 + producer warp"),
-        cfg_gen2x<IsoTile2<8, 8, 32, 5>, 0, 2>("gen2 16x128, 2 planes per trip"),
-        cfg_gen2x<IsoTile2<8, 16, 16, 5>, 1, 2>("gen2 32x64 + producer warp, 2 planes per trip"),
-        cfg_gen2x<IsoTile2<8, 8, 32, 5>, 1, 2>("gen2 16x128 + producer warp, 2 planes per trip"),
+        cfg_tile<IsoTile2<8, 16, 16, 5>, 0, 1>("32x64, in-loop producer"),
+        cfg_tile<IsoTile2<8, 8, 32, 5>, 0, 1>("16x128, in-loop producer"),
+        cfg_tile<IsoTile2<8, 16, 16, 5>, 1, 1>("32x64 + producer warpgroup"),
+        cfg_tile<IsoTile2<8, 16, 16, 5>, 0, 2>("32x64, 2 planes per trip"),
+        cfg_tile<IsoTile2<8, 8, 32, 5>, 1, 1>("16x128 + producer warpgroup"),
+        cfg_tile<IsoTile2<8, 8, 32, 5>, 0, 2>("16x128, 2 planes per trip"),
+        cfg_tile<IsoTile2<8, 16, 16, 5>, 1, 2>("32x64 + producer warpgroup, 2 planes per trip"),
+        cfg_tile<IsoTile2<8, 8, 32, 5>, 1, 2>("16x128 + producer warpgroup, 2 planes per trip"),
     };
     return cfgs[i];
 }
@@ -218,7 +199,7 @@ struct IsoEngine : Engine {
     int radius = 8;
     double coef[ISO_MAX_R + 1] = {0};
     std::string kernel = "auto";   // auto | tma | direct
-    int tile = 11;                 // index into tile_cfg(): gen2 16x128, producer warpgroup, 2 planes per trip
+    int tile = DEFAULT_TILE;       // index into tile_cfg(): 16x128, producer warpgroup, 2 planes per trip
     int lx = 0;                    // planes per sweep chunk (0 = choose per launch)
     int grid_override = 0;
     int num_sms = 148;
@@ -327,34 +308,58 @@ struct IsoEngine : Engine {
             if (mem_probe && c.fn[3]) mode = 3;
             // fused halo exchange: only for whole-domain launches of a kernel that implements the peer stores
             P.peer_lo = P.peer_hi = nullptr;
-            if (s.fused_x.var == 0 && c.fused_ok && mode != 3 && box.b[0] == 0 && box.e[0] == P.nx && P.nx >= 2 * radius) {
+            const bool fused = s.fused_x.var == 0 && c.fused_ok && mode != 3 && box.b[0] == 0 && box.e[0] == P.nx && P.nx >= 2 * radius;
+            if (fused) {
                 P.peer_lo = static_cast<float*>(s.fused_x.lo);
                 P.peer_hi = static_cast<float*>(s.fused_x.hi);
                 s.fused_x.used = true;
             }
             P.nty = int((box.e[1] - box.b[1] + c.ty - 1) / c.ty);
             P.ntz = int((box.e[2] - box.b[2] + c.tz - 1) / c.tz);
-            const int64_t nxb = box.e[0] - box.b[0];
+            const int64_t ntile = int64_t(P.nty) * P.ntz;
             const int gmax = grid_override > 0 ? grid_override : num_sms;
+            // x chunks.  With an in-kernel completion signal the boundary planes [0,R) / [nx-R,nx) are chunks of their
+            // own and come FIRST, so that every CTA sweeps them (and stores them into the neighbours) before any interior
+            // plane; the rest of [begin,end) is split evenly.
+            int nb = 0;
+            int64_t ib = box.b[0], ie = box.e[0];
+            const bool sig = fused && s.fused_x.counter != nullptr && P.nx >= 3 * radius;
+            if (sig) {
+                if (P.peer_lo) { P.cx0[nb] = 0; P.cx1[nb] = radius; nb++; ib = radius; }
+                if (P.peer_hi) { P.cx0[nb] = P.nx - radius; P.cx1[nb] = P.nx; nb++; ie = P.nx - radius; }
+            }
+            const int64_t nxb = ie - ib;
+            const int max_nc = ISO_MAX_CHUNKS - nb;
+            int nc_best = 1;
             if (lx > 0) {
-                P.lx = int(std::min<int64_t>(lx, nxb));
+                nc_best = int(std::min<int64_t>((nxb + lx - 1) / lx, max_nc));
             } else {
                 // Pick the chunk count that minimises (rounds of units per CTA) x (chunk length + queue
                 // warm-up): long chunks amortise the 2R warm-up planes, short ones balance the last round.
-                const int64_t ntile = int64_t(P.nty) * P.ntz;
                 double best = 1e30;
-                int best_lx = int(nxb);
-                for (int nc = 1; nc <= 64 && nc <= nxb; nc++) {
+                for (int nc = 1; nc <= max_nc && nc <= nxb; nc++) {
                     const int64_t l = (nxb + nc - 1) / nc;
                     const int64_t rounds = (ntile * nc + gmax - 1) / gmax;
                     const double cost = double(rounds) * (double(l) + 2 * radius * 0.4);
-                    if (cost < best * 0.999) { best = cost; best_lx = int(l); }
+                    if (cost < best * 0.999) { best = cost; nc_best = nc; }
                 }
-                P.lx = best_lx;
             }
-            P.nchunks = int((nxb + P.lx - 1) / P.lx);
+            if (nxb > 0) {
+                const int64_t l = (nxb + nc_best - 1) / nc_best;
+                for (int64_t x = ib; x < ie; x += l) { P.cx0[nb] = int(x); P.cx1[nb] = int(std::min(x + l, ie)); nb++; }
+            }
+            P.nchunks = nb;
+            P.sig_units = 0; P.sig_total = 0; P.sig_counter = nullptr; P.sig_flag_lo = P.sig_flag_hi = nullptr; P.sig_epoch = 0;
             const int64_t nunits = int64_t(P.nty) * P.ntz * P.nchunks;
             int grid = int(std::min<int64_t>(nunits, gmax));
+            if (sig) {
+                P.sig_units = int(ntile) * ((P.peer_lo ? 1 : 0) + (P.peer_hi ? 1 : 0));
+                P.sig_total = unsigned(grid) * unsigned(c.ty * c.tz / 8 / 32);     // consumer warps: 8 points per thread
+                P.sig_counter = s.fused_x.counter;
+                P.sig_flag_lo = s.fused_x.flag_lo; P.sig_flag_hi = s.fused_x.flag_hi;
+                P.sig_epoch = s.fused_x.epoch;
+                s.fused_x.signalled = true;
+            }
             if (!attr_set[ti][mode]) {
                 YB_CUDA(cudaFuncSetAttribute(c.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
                 attr_set[ti][mode] = true;
@@ -383,8 +388,8 @@ struct IsoEngine : Engine {
         for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = s.rank_size[d]; }
         if (whole.e[1] < 8 || whole.e[2] < 16) { report = "iso3dfd: domain too thin for the tiled kernel"; return 0; }
         const int64_t t0 = s.vars[0].last_valid_step();
-        const int tiles[] = {11, 10, 9, 8, 3, 2};
-        const int lxs[] = {0, 256, 512, 1024};
+        const int tiles[] = {7, 6, 5, 4, 1, 0};
+        const int lxs[] = {0, 256, 512, 1024};   // planes per interior chunk (0 = cost model)
         const int keep_tile = tile, keep_lx = lx;
         double best = 1e30;
         int best_tile = tile, best_lx = lx;

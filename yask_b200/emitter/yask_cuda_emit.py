@@ -18,8 +18,9 @@ Outputs (committed; nothing at run time needs the reference):
   oracle/gen/<name>.gen.h             plain-C restatement of the same statements (TEST oracle)
   yask_b200/csrc/gen/<name>.json      the parsed IR (tests use it for var names / halos)
 
-Unsupported on purpose (reported, not silently dropped): sub-domain / step conditions, scratch vars,
-math functions, misc dims.
+Covered: sub-domain (IF_DOMAIN) and step (IF_STEP) conditions, scratch vars and scratch-part chains, the DSL's math
+functions, misc dims (up to two per var), 1-D/2-D/3-D solutions, reverse-time solutions.  Refused with a message (never
+silently dropped): more than three domain dims, more than two misc dims per var, non-constant misc indices.
 
 usage: python -m yask_b200.emitter.yask_cuda_emit --stencil awp_elastic --elem-bytes 4 [--radius R] [--name NAME]
 """
@@ -34,8 +35,10 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-COMPILER = os.path.join(ROOT, "oracle", "_ref", "yask", "bin", "yask_compiler.exe")
-COMPILER_LIB = os.path.join(ROOT, "oracle", "_ref", "yask", "lib")
+# The reference's stencil compiler, built out of tree from the unmodified sources by oracle/build_ref.sh into tools/_refc
+# (build container only; the emitter's outputs are committed, nothing at run time needs it).
+COMPILER = os.path.join(ROOT, "tools", "_refc", "bin", "yask_compiler.exe")
+COMPILER_LIB = os.path.join(ROOT, "tools", "_refc", "lib")
 
 
 class EmitError(RuntimeError):
