@@ -26,7 +26,6 @@ _dist = None
 def _init_dist():
     global _dist
     if WORLD > 1 and _dist is None:
-        os.environ["NCCL_DEBUG"] = os.environ.get("YB_NCCL_DEBUG", "WARN")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(LOCAL)
@@ -35,8 +34,10 @@ def _init_dist():
     return _dist
 
 
-def run(stencil, n, steps, warm, fp_mode, opts=()):
-    dist = _init_dist()
+def run(stencil, n, steps, warm, fp_mode, opts=(), dist=None):
+    """One timed run; `dist` = an already initialised torch.distributed (bench.py), else initialised here under torchrun."""
+    if dist is None:
+        dist = _init_dist()
     s = capi.Solution(stencil, elem_bytes=0)
     s.set_rank_domain_size_vec((n, n, n))
     if WORLD > 1:

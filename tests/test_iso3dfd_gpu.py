@@ -214,3 +214,24 @@ def test_tma_equals_direct_on_device_large(n, steps):
     vv = hash_field(7, var_salt("v", 0), lo, shp, 0.05, 0.3)
     ref = O.iso3dfd_run(ins0, ins1, vv, 8, steps, 2)[8:-8, 8:-8, 8:-8]
     assert np.array_equal(sub.view(np.uint32), ref[m:-m, m:-m, m:-m].view(np.uint32))
+
+
+@pytest.mark.parametrize("tag,fp_mode", [("iso3dfd.avx512", 2), ("iso3dfd-strict.avx512", 0)])
+@pytest.mark.parametrize("steps", [1, 2, 10])
+def test_config1_live_reference_128(tag, fp_mode, steps):
+    """BASELINE.json config 1 as written: iso3dfd order 16 fp32 128^3, one rank, against the UNMODIFIED reference run live
+    on this box's CPU (oracle/_ref/ship, built by oracle/build_ref.sh from /root/reference) on identical inputs, bit for bit
+    (the default build against fp_mode 2, the -ffp-contract=off build against fp_mode 0)."""
+    if not O.ref_available(tag):
+        pytest.skip(f"prebuilt reference driver {tag} not present")
+    if "avx512f" not in open("/proc/cpuinfo").read():
+        pytest.skip("host CPU lacks AVX-512")
+    n = (128, 128, 128)
+    ins = synth_inputs(n, 1234)
+    outs, after = O.ref_run(tag, n, steps, {("p", 0): ins[("p", 0)], ("p", 1): ins[("p", 1)], ("v", 0): ins[("v", 0)]})
+    tl = after["vars"]["p"]["steps"][1]
+    ref = outs[("p", tl)]
+    for kernel in ("tma", "direct"):
+        got = run_gpu(n, steps, ins, fp_mode=fp_mode, opts={"kernel": kernel})
+        assert got.shape == ref.shape
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), kernel

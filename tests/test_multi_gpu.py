@@ -61,13 +61,13 @@ def test_rank_grid_matches_single_rank(n, grid, steps):
     assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
 
 
-def _ipc_worker(rank, world, n, steps, seed, port, q):
+def _ipc_worker(rank, world, n, steps, seed, port, q, one_device_per_rank=False):
     import os
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    dev = rank % max(1, torch.cuda.device_count())
+    dev = rank if one_device_per_rank else rank % max(1, torch.cuda.device_count())
     s = capi.Solution("iso3dfd")
     s.set_overall_domain_size_vec(n)
     s.set_num_ranks_vec([world, 1, 1])
@@ -98,6 +98,37 @@ def test_two_processes_cuda_ipc():
     out = np.zeros(n, np.float32)
     for _ in range(2):
         rank, f, l, a = q.get(timeout=180)
+        out[f[1]:l[1] + 1, f[2]:l[2] + 1, f[3]:l[3] + 1] = a
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert np.array_equal(out.view(np.uint32), ref.view(np.uint32))
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("n,world,steps", [((192, 64, 256), 2, 5), ((160, 48, 128), 4, 4)])
+def test_one_physical_device_per_rank(n, world, steps):
+    """The product's launch mode on real hardware: one process per GPU, rank r on device r (never shared), CUDA-IPC peer
+    mappings, boundary planes stored into the neighbour's HBM over NVLink by the sweep kernel with the in-kernel epoch
+    signal.  Needs `world` physical devices (skipped otherwise: the one-device variants above cover the protocol, not
+    the cross-device memory ordering)."""
+    if _device_count() < world:
+        pytest.skip(f"needs {world} CUDA devices, found {_device_count()}")
+    import torch.multiprocessing as mp
+    seed = 29
+    ref = single_rank(n, steps, seed)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, n, steps, seed, 29541 + world, q, True)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    out = np.zeros(n, np.float32)
+    for _ in range(world):
+        rank, f, l, a = q.get(timeout=240)
         out[f[1]:l[1] + 1, f[2]:l[2] + 1, f[3]:l[3] + 1] = a
     for pr in procs:
         pr.join(timeout=60)
