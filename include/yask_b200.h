@@ -208,6 +208,26 @@ int yb_halo_import(yb_solution* s, int64_t peer_rank_linear, const void* blob, s
 int yb_halo_finalize(yb_solution* s);              /* after all imports: ready to run */
 int yb_exchange_halos(yb_solution* s);             /* yk_solution::exchange_halos (public API) */
 
+/* ---- job rendezvous without MPI or torch (replaces the MPI set-up of setup.cpp:169-524 and the harness's
+ *      yk_env::global_barrier / sum_over_ranks, yask_kernel_api.hpp:238-293) ---------------------------------------
+ * One process per GPU on one node; the ranks meet in a POSIX shared-memory mailbox named after `job_key` (NULL:
+ * YASK_JOB_ID, else MASTER_ADDR:MASTER_PORT + the launcher's pid).  yb_comm_env_* read the rank / world size / local
+ * rank a launcher exported (YASK_*, torchrun's RANK/WORLD_SIZE/LOCAL_RANK, Open MPI, PMI, Slurm). */
+int yb_comm_env_rank(void);
+int yb_comm_env_world(void);
+int yb_comm_env_local_rank(void);
+int yb_comm_init(int rank, int world, const char* job_key);
+int yb_comm_rank(void);
+int yb_comm_world(void);
+int yb_comm_barrier(void);
+int yb_comm_allgather(const void* mine, size_t nbytes, void* all /* world * nbytes */);
+int yb_comm_sum_i64(int64_t v, int64_t* out);
+int yb_comm_max_f64(double v, double* out);
+int yb_comm_finalize(void);
+/* export -> all-gather through the communicator -> import every neighbour -> finalize, for a prepared multi-rank solution
+ * whose rank-grid position matches this process's job rank (row-major over the domain dims, x slowest). */
+int yb_halo_connect(yb_solution* s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,7 +61,8 @@ ABI_SYMBOLS = [
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
     "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_var_fill_hash", "yb_var_fill_hash_shifted", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
-    "yb_exchange_halos",
+    "yb_exchange_halos", "yb_comm_env_rank", "yb_comm_env_world", "yb_comm_env_local_rank", "yb_comm_init", "yb_comm_rank", "yb_comm_world",
+    "yb_comm_barrier", "yb_comm_allgather", "yb_comm_sum_i64", "yb_comm_max_f64", "yb_comm_finalize", "yb_halo_connect",
 ]
 
 _lib = None
@@ -125,6 +126,11 @@ def lib() -> C.CDLL:
         L.yb_halo_import.argtypes = [p, i64, p, C.c_size_t]
         L.yb_halo_finalize.argtypes = [p]
         L.yb_exchange_halos.argtypes = [p]
+        L.yb_comm_init.argtypes = [i32, i32, C.c_char_p]
+        L.yb_comm_allgather.argtypes = [p, C.c_size_t, p]
+        L.yb_comm_sum_i64.argtypes = [i64, C.POINTER(i64)]
+        L.yb_comm_max_f64.argtypes = [C.c_double, C.POINTER(C.c_double)]
+        L.yb_halo_connect.argtypes = [p]
         _lib = L
     return _lib
 

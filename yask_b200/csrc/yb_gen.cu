@@ -67,7 +67,9 @@ struct GenEngine : Engine {
         if (const char* e = getenv("YB_GEN_SWEEP")) sweep = atoi(e) != 0;
     }
     int sweep = 0;     // option gen_sweep (env YB_GEN_SWEEP): 1 = use the TMA-staged sweep variant where a part has one (experimental)
-    int sweep_lx = 128;  // option gen_sweep_lx: x planes per sweep chunk
+    int sweep_lx = 0;    // option gen_sweep_lx: x planes per sweep chunk (0 = cost model)
+    int sweep_min_x = 12;  // shorter boxes (exterior slabs of a rank grid) take the direct kernels
+    int num_sms = 148;
     std::map<const void*, bool> sweep_attr;   // kernels whose dynamic shared-memory limit has been raised
     // tensor maps of a part's streams live in device memory, one array per combination of step slots (they depend only on
     // the vars' storage, fixed after prepare)
@@ -81,10 +83,12 @@ struct GenEngine : Engine {
         if (key == "gen_pf") { pf_dist = std::max(0, atoi(value.c_str())); return 0; }
         if (key == "gen_l2_mb") { l2_mb = std::max(0, atoi(value.c_str())); return 0; }
         if (key == "gen_sweep") { sweep = atoi(value.c_str()) != 0; return 0; }
-        if (key == "gen_sweep_lx") { sweep_lx = std::max(8, atoi(value.c_str())); return 0; }
+        if (key == "gen_sweep_lx") { sweep_lx = std::max(0, atoi(value.c_str())); return 0; }
         return YB_EINVAL;
     }
     int prepare(Solution& s) override {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, s.device) == cudaSuccess) num_sms = prop.multiProcessorCount;
         if (s.spec.elem_bytes != g.elem_bytes)
             return set_error(YB_EUNSUPPORTED, "solution '%s' was generated for %d-byte elements", g.name.c_str(), g.elem_bytes);
         for (auto& st : g.stages)
@@ -219,7 +223,9 @@ struct GenEngine : Engine {
                 }
             // Sweep variant: TMA-staged shared-memory planes (yb_gen_sweep.cuh), for whole-box launches of parts that have one.
             const int fi = g.elem_bytes == 8 ? 1 : 0, mi = s.fp_mode == 0 ? 0 : 1;
-            if (sweep && p.sweep.fn[fi][mi] && P.SX != 0 && pb.e[1] - pb.b[1] >= 1 && pb.e[2] - pb.b[2] >= 32) {
+            // (TMA boxes and the consumers' 128-bit accesses need the box to start on a 16-byte boundary in z)
+            if (sweep && p.sweep.fn[fi][mi] && P.SX != 0 && pb.e[0] - pb.b[0] >= sweep_min_x && pb.e[2] - pb.b[2] >= 32 &&
+                pb.b[2] % (16 / g.elem_bytes) == 0) {
                 GenSweepParams SP;
                 memset(&SP, 0, sizeof SP);
                 SP.g = P;
@@ -251,11 +257,26 @@ struct GenEngine : Engine {
                     it = sweep_maps.emplace(mk, dm).first;
                 }
                 SP.maps = static_cast<const CUtensorMap*>(it->second);
-                SP.lx = int(std::min<int64_t>(sweep_lx, pb.e[0] - pb.b[0]));
-                SP.nchunks = int((pb.e[0] - pb.b[0] + SP.lx - 1) / SP.lx);
-                SP.nzb = int((pb.e[2] - pb.b[2] + GEN_SW_TZ - 1) / GEN_SW_TZ);
+                SP.nzb = int((pb.e[2] - pb.b[2] + sw.tz - 1) / sw.tz);
                 SP.nyb = int((pb.e[1] - pb.b[1] + sw.ty - 1) / sw.ty);
-                SP.bar_off = sw.bar_off;
+                const int64_t nxb = pb.e[0] - pb.b[0];
+                if (sweep_lx > 0) {
+                    SP.lx = int(std::min<int64_t>(sweep_lx, nxb));
+                } else {
+                    // chunk count that minimises (waves of CTAs) x (chunk length + pipeline fill): long chunks amortise the
+                    // x reach re-read at every chunk start, short ones fill the last wave
+                    const int64_t slots = int64_t(num_sms) * sw.occ, tiles = int64_t(SP.nzb) * SP.nyb;
+                    double best = 1e30;
+                    int64_t best_l = nxb;
+                    for (int64_t nc = 1; nc <= 64 && nc <= nxb; nc++) {
+                        const int64_t l = (nxb + nc - 1) / nc;
+                        const int64_t waves = (tiles * nc + slots - 1) / slots;
+                        const double cost = double(waves) * (double(l) + 8.0);
+                        if (cost < best * 0.999) { best = cost; best_l = l; }
+                    }
+                    SP.lx = int(best_l);
+                }
+                SP.nchunks = int((nxb + SP.lx - 1) / SP.lx);
                 GenSweepFn sfn = sw.fn[fi][mi];
                 if (!sweep_attr[(const void*)sfn]) {
                     YB_CUDA(cudaFuncSetAttribute((const void*)sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, sw.smem));
@@ -263,7 +284,7 @@ struct GenEngine : Engine {
                 }
                 const int64_t nb = int64_t(SP.nzb) * SP.nyb * SP.nchunks;
                 if (nb >= (int64_t(1) << 31)) return set_error(YB_EUNSUPPORTED, "domain too large for the sweep kernels");
-                sfn<<<unsigned(nb), GEN_SW_THREADS, sw.smem, st>>>(SP);
+                sfn<<<unsigned(nb), sw.threads, sw.smem, st>>>(SP);
                 YB_CUDA(cudaGetLastError());
                 n++;
                 continue;

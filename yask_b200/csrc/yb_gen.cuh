@@ -54,8 +54,8 @@ struct GenSweepParams;
 typedef void (*GenSweepFn)(const GenSweepParams);
 struct GenSweepStream { int acc, xl, xr, yl, yr, zl, zr, rows, pz, slot_bytes, ns, off; };
 struct GenSweep {
-    GenSweepFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [fp64?][mode]
-    int ty = 0, pf = 0, smem = 0, bar_off = 0;
+    GenSweepFn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [fp64?][mode]; only the solution's element type is emitted
+    int ty = 0, tz = 0, threads = 0, occ = 1, smem = 0;               // tile rows x z points, CTA size, CTAs per SM, dynamic smem
     std::vector<GenSweepStream> streams;
 };
 

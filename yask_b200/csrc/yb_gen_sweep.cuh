@@ -1,21 +1,26 @@
-// "Sweep" variant of the emitter-generated kernels: TMA-staged shared-memory planes with the same 2.5-D march along x
-// as the hand-written iso3dfd kernel, for multi-var stencils.  EXPERIMENTAL (option gen_sweep=1, off by default).
+// "Sweep" form of the emitter-generated kernels: TMA-staged shared-memory planes with the same 2.5-D march along x as the
+// hand-written iso3dfd kernel, for multi-var stencils (awp_elastic, ssg, ...).  The kernels themselves are written by
+// yask_b200/emitter/yask_cuda_emit.py (gen/<name>.gen.cuh); this header holds what they share.
 //
-// A CTA of 256 threads (two row groups of 128) owns a (TY rows x 128 z) tile and marches over a chunk of x planes.  Every full-rank var the
-// part reads is a *stream*: its planes arrive by TMA (cp.async.bulk.tensor.3d, box = tile + the stream's y/z reach)
-// into a shared-memory ring of (x reach + PF) slots, PF planes ahead of their first use, and complete on one mbarrier
-// per sweep iteration.  The statements are the same as in the direct kernel (same order, same rounding); only the
-// full-rank reads come from shared memory.  Lower-rank vars (1-D sponge arrays, scalars) are read from global memory
-// as before; outputs are stored straight to global memory.
+// A CTA owns a (TY rows x TZ z) tile, TZ = 32 vectors of VW = 16 B / sizeof(T) elements, and marches over a chunk of x
+// planes.  Warp-specialised like the iso3dfd kernel:
+//   * a producer warpgroup (one elected lane, registers handed back with setmaxnreg.dec) streams every full-rank var the part
+//     reads: each is a TMA *stream* (cp.async.bulk.tensor.3d, box = tile + the stream's y/z reach, first element 16-byte
+//     aligned) into its own shared-memory ring of (x reach + PF) plane slots, PF planes ahead of first use.  All loads first
+//     needed at sweep iteration j complete on full[j mod (PF+1)]; the slots that iteration j + PF + 1 overwrites are released
+//     by done[j mod (PF+1)], on which every consumer warp arrives -- no __syncthreads in the loop.
+//   * a var whose x reach is long (ssg: 8 planes) and whose x neighbours are only read at the point's own (y,z) is split
+//     into two streams: the current plane with its y/z halo, and a ring of halo-less planes for the x neighbours;
+//   * NW consumer warps (setmaxnreg.inc), one warp per tile row: a thread computes VW consecutive z points of its row from
+//     128-bit shared-memory loads (z neighbours of the VW points share their vectors), evaluates the part's statement list
+//     (same order, same rounding as the direct kernel) and stores 128-bit vectors straight to HBM;
+//   * lower-rank vars (1-D sponge arrays, scalars) are read from global memory, hoisted out of the sweep where they do not
+//     depend on x.
 #pragma once
 #include "yb_gen.cuh"
 #include "yb_ptx.cuh"
 
 namespace yb { namespace gen {
-
-constexpr int GEN_SW_MAX_STREAMS = 24;
-constexpr int GEN_SW_TZ = 128;          // z extent of a tile
-constexpr int GEN_SW_THREADS = 256;     // two row groups of GEN_SW_TZ threads: thread (tz, g) computes rows g*TY/2 .. g*TY/2 + TY/2 - 1
 
 struct GenSweepParams {
     GenParams g;                               // box, pointers and strides as for the direct kernel
@@ -24,51 +29,59 @@ struct GenSweepParams {
     int px, py, pz;                            // left pads of the shared geometry (tensor coordinate of local index 0)
     int lx, nchunks;                           // planes per sweep chunk, chunks along x
     int nzb, nyb;                              // tiles along z and y
-    int bar_off;                               // byte offset of the mbarriers in dynamic shared memory
 };
 
 // (GenSweepFn, GenSweepStream and GenSweep -- the host-side description filled in by the generated describe() -- are
 // declared in yb_gen.cuh next to GenPart.)
 
-#define GEN_SW_FN(k, T, M) reinterpret_cast<yb::gen::GenSweepFn>(static_cast<void (*)(const yb::gen::GenSweepParams)>(k<T, M>))
+#define GEN_SW_FN(k, M) reinterpret_cast<yb::gen::GenSweepFn>(static_cast<void (*)(const yb::gen::GenSweepParams)>(k<M>))
 
 #ifdef __CUDACC__
-// Prologue shared by all sweep kernels: tile coordinates, barrier set-up.
-#define GEN_SWEEP_BEGIN(TY_, PF_)                                                                            \
-    extern __shared__ __align__(128) unsigned char sw_smem[];                                                \
-    const GenParams& P = SP.g;                                                                               \
-    constexpr int SW_TY = (TY_), SW_PF = (PF_), SW_NB = (PF_) + 1;                                           \
-    uint64_t* sw_bar = reinterpret_cast<uint64_t*>(sw_smem + SP.bar_off);                                    \
-    const int sw_bz = int(blockIdx.x) % SP.nzb;                                                              \
-    const int sw_by = (int(blockIdx.x) / SP.nzb) % SP.nyb;                                                   \
-    const int sw_bc = int(blockIdx.x) / (SP.nzb * SP.nyb);                                                   \
-    const int z0 = P.zb + sw_bz * GEN_SW_TZ;                                                                 \
-    const int y0_ = P.yb + sw_by * SW_TY;                                                                    \
-    const int xs = P.xb + sw_bc * SP.lx;                                                                     \
-    const int sw_len = min(SP.lx, P.xe - xs);                                                                \
-    const int tz = int(threadIdx.x) & (GEN_SW_TZ - 1);                                                       \
-    const int sw_rb = (int(threadIdx.x) / GEN_SW_TZ) * (SW_TY / 2);   /* first row of this thread's group */  \
-    const int z = z0 + tz;                                                                                   \
-    if (threadIdx.x == 0) {                                                                                  \
-        for (int b = 0; b < SW_NB; b++) mbar_init(&sw_bar[b], 1);                                            \
-        fence_barrier_init();                                                                                \
-    }                                                                                                        \
-    __syncthreads();
-
-// One stream's loads for sweep iteration j (j == 0: the whole initial x reach; j > 0: the newest plane).
-#define SW_LOAD(k, OFF, SLOT, NS, XL, XR, YL, ZL)                                                            \
-    if (j == 0) {                                                                                            \
-        for (int dx = (XL); dx <= (XR); dx++)                                                                \
-            tma_load_3d(sw_smem + (OFF) + ((dx - (XL)) % (NS)) * (SLOT), &SP.maps[k], bar, SP.pz + z0 + (ZL), \
-                        SP.py + y0_ + (YL), SP.px + xs + dx);                                                \
-    } else {                                                                                                 \
-        tma_load_3d(sw_smem + (OFF) + ((j + (XR) - (XL)) % (NS)) * (SLOT), &SP.maps[k], bar, SP.pz + z0 + (ZL), \
-                    SP.py + y0_ + (YL), SP.px + xs + j + (XR));                                              \
+// 16-byte vectors of the element type: VW elements
+template <typename T> struct SwVec;
+template <> struct SwVec<float> {
+    static constexpr int VW = 4;
+    static __device__ __forceinline__ void lds(uint32_t addr, float* o) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
     }
+    static __device__ __forceinline__ void stg(float* p, const float* v) {
+        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    }
+    static __device__ __forceinline__ void ldg(const float* p, float* o) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+};
+template <> struct SwVec<double> {
+    static constexpr int VW = 2;
+    static __device__ __forceinline__ void lds(uint32_t addr, double* o) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void stg(double* p, const double* v) {
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+    }
+    static __device__ __forceinline__ void ldg(const double* p, double* o) {
+        const double2 v = *reinterpret_cast<const double2*>(p);
+        o[0] = v.x; o[1] = v.y;
+    }
+};
 
-// Base pointer of stream k's plane x+dx for this thread: box row (YL) of the thread's first row, its z column.
-#define SW_PLANE(OFF, SLOT, NS, XL, ZL, dx, PZ)                                                              \
-    (reinterpret_cast<const T*>(sw_smem + (OFF) + ((unsigned(it) + unsigned((dx) - (XL))) % unsigned(NS)) * (SLOT)) + (tz - (ZL)) + sw_rb * (PZ))
+// slot index of the plane `ahead` places after the ring position `c` (both < ns)
+__device__ __forceinline__ uint32_t sw_wrap(uint32_t c, uint32_t ahead, uint32_t ns) {
+    const uint32_t u = c + ahead;
+    return u >= ns ? u - ns : u;
+}
+
+// Producer side: the loads of stream k first needed at sweep iteration j (j == 0: its whole x reach; j > 0: the newest plane).
+#define SW_ISSUE(k, OFF, SLOT, NS, XL, XR, YL, ZL)                                                                     \
+    if (j == 0) {                                                                                                      \
+        for (int dx = (XL); dx <= (XR); dx++)                                                                          \
+            tma_load_3d(sw_smem + (OFF) + (dx - (XL)) * (SLOT), &SP.maps[k], bar, SP.pz + z0 + (ZL), SP.py + y0_ + (YL), \
+                        SP.px + xs + dx);                                                                              \
+    } else {                                                                                                           \
+        tma_load_3d(sw_smem + (OFF) + ((j + (XR) - (XL)) % (NS)) * (SLOT), &SP.maps[k], bar, SP.pz + z0 + (ZL),         \
+                    SP.py + y0_ + (YL), SP.px + xs + j + (XR));                                                        \
+    }
 #endif
 
 } }  // namespace yb::gen

@@ -94,15 +94,22 @@ bool yk_env::is_trace_enabled() { return g_trace; }
 
 namespace {
 
-// One process = one rank of the host API; the rank GRID of a solution (set_num_ranks) is mapped onto GPUs by
-// the launcher (yask_b200/multi.py), see DESIGN.md section 6.
+// One process = one rank = one GPU.  The ranks of a job are started by any launcher that exports rank and world size
+// (torchrun, mpirun, srun, a shell loop); they meet in the library's shared-memory mailbox (yb_comm.cpp), which stands in
+// for the reference's MPI communicator (/root/reference/src/kernel/lib/setup.cpp:60-139, yask_kernel_api.hpp:238-293).
 struct B200Env : yk_env {
-    int get_num_ranks() const override { const char* w = getenv("WORLD_SIZE"); return w ? std::max(1, atoi(w)) : 1; }
-    int get_rank_index() const override { const char* r = getenv("RANK"); return r ? atoi(r) : 0; }
-    void global_barrier() const override {}
-    idx_t sum_over_ranks(idx_t v) const override { return v; }
-    void assert_equality_over_ranks(idx_t, const std::string&) const override {}
-    void finalize() override {}
+    B200Env() { chk_comm(yb_comm_init(yb_comm_env_rank(), yb_comm_env_world(), nullptr)); }
+    static void chk_comm(int rc) { if (rc < 0) fail(yb_last_error()); }
+    int get_num_ranks() const override { return yb_comm_world(); }
+    int get_rank_index() const override { return yb_comm_rank(); }
+    void global_barrier() const override { chk_comm(yb_comm_barrier()); }
+    idx_t sum_over_ranks(idx_t v) const override { int64_t s = 0; chk_comm(yb_comm_sum_i64(v, &s)); return idx_t(s); }
+    void assert_equality_over_ranks(idx_t v, const std::string& descr) const override {
+        // setup.cpp:106-121: every rank must hold the same value
+        const idx_t s = sum_over_ranks(v);
+        if (s != v * idx_t(yb_comm_world())) fail("ranks disagree on " + descr + " (this rank: " + std::to_string(v) + ")");
+    }
+    void finalize() override { yb_comm_finalize(); }
     [[noreturn]] void exit(int code) override { std::exit(code); }
 };
 
@@ -596,9 +603,31 @@ struct B200Solution : yk_solution {
     std::vector<yk_var_ptr> get_vars() override { std::vector<yk_var_ptr> v; for (int i = 0; i < yb_num_vars(h->s); i++) v.push_back(make_var(i)); return v; }
     void prepare_solution() override {
         for (auto& f : before_prepare) f(*this);
+        // Rank grid of a multi-rank job (setup.cpp:228-256): when the caller did not choose one, split the first domain dim
+        // (the outermost storage dim: its faces are contiguous planes); the position of this rank in the grid follows its
+        // job rank, row-major over the domain dims.
+        const int world = yb_comm_world(), rank = yb_comm_rank();
+        const int ndd = yb_solution_num_domain_dims(h->s);
+        int64_t grid = 1;
+        for (int d = 0; d < ndd; d++) grid *= yb_get_num_ranks(h->s, d);
+        if (world > 1) {
+            if (grid == 1) { chk(yb_set_num_ranks(h->s, 0, world)); grid = world; }
+            if (grid != world) fail("the rank grid has " + std::to_string(grid) + " ranks but the job has " + std::to_string(world));
+            bool idx_set = false;
+            for (int d = 0; d < ndd; d++) idx_set = idx_set || yb_get_rank_index(h->s, d) != 0;
+            if (!idx_set) {
+                int64_t r = rank;
+                for (int d = ndd - 1; d >= 0; d--) { const int64_t n = yb_get_num_ranks(h->s, d); chk(yb_set_rank_index(h->s, d, r % n)); r /= n; }
+            }
+        }
         int dev = device;
-        if (dev < 0) { const char* lr = getenv("LOCAL_RANK"); dev = lr ? atoi(lr) : 0; }
+        if (dev < 0) {
+            dev = yb_comm_env_local_rank();
+            const int ndev = yb_device_count();
+            if (ndev > 0) dev %= ndev;
+        }
         chk(yb_solution_prepare(h->s, dev));
+        if (grid > 1) chk(yb_halo_connect(h->s));
         for (auto& f : after_prepare) f(*this);
     }
     idx_t get_first_rank_domain_index(const std::string& dim) const override { return yb_get_first_rank_domain_index(h->s, dpos(dim, "get_first_rank_domain_index")); }

@@ -35,8 +35,10 @@ struct Trial { idx_t nsteps; double secs, pts_ps, reads_ps, writes_ps, flops; };
 void usage(const char* exe, yk_solution_ptr soln) {
     std::cout << "Usage: " << exe << " [options]\n"
               << " -h | -help              this text\n"
-              << " -trial_steps <n>        steps per performance trial (default 50)\n"
-              << " -num_trials <n>         number of trials (default 3)\n"
+              << " -trial_steps | -dt <n>  steps per performance trial (default 50)\n"
+              << " -num_trials | -t <n>    number of trials (default 3)\n"
+              << " -msg_rank <r>           rank that prints (default 0); a job of several ranks is started once per rank\n"
+              << "                         (RANK / WORLD_SIZE / LOCAL_RANK as torchrun, mpirun or srun export them)\n"
               << " -warmup_steps <n>       untimed steps before the trials (default 5)\n"
               << " -init_val <x>           value every var is initialised to (default 0.1, var k gets x*(1+k/16))\n"
               << " -validate               iso3dfd only: cross-check the tiled kernel against the direct kernel on the device\n"
@@ -50,11 +52,8 @@ int main(int argc, char** argv) {
         yk_factory kfac;
         auto env = kfac.new_env();
         auto soln = kfac.new_solution(env);
-        std::cout << "YASK-compatible kernel harness, solution '" << soln->get_name() << "', target " << soln->get_target()
-                  << ", " << soln->get_element_bytes() << "-byte elements, API version " << kfac.get_version_string() << "\n";
-
-        idx_t trial_steps = 50, num_trials = 3, warmup_steps = 5;
-        double init_val = 0.1;
+        idx_t trial_steps = 50, num_trials = 3, warmup_steps = 5, msg_rank = 0;
+        double init_val = 0.1, init_seed = 0.1;
         bool validate = false;
         // harness options first; everything else goes to the solution (as yask_main.cpp:199-259 does)
         string_vec rest;
@@ -65,14 +64,23 @@ int main(int argc, char** argv) {
                 return argv[++i];
             };
             if (a == "-h" || a == "-help" || a == "--help") { usage(argv[0], soln); return 0; }
-            else if (a == "-trial_steps" || a == "-t") trial_steps = atoll(val().c_str());
-            else if (a == "-num_trials") num_trials = atoll(val().c_str());
+            // (-t and -dt are the reference's deprecated aliases of -num_trials and -trial_steps, yask_main.cpp:107-119)
+            else if (a == "-trial_steps" || a == "-dt") trial_steps = atoll(val().c_str());
+            else if (a == "-num_trials" || a == "-t") num_trials = atoll(val().c_str());
             else if (a == "-warmup_steps") warmup_steps = atoll(val().c_str());
-            else if (a == "-init_val" || a == "-init_seed") init_val = atof(val().c_str());
+            else if (a == "-msg_rank") msg_rank = atoll(val().c_str());
+            else if (a == "-init_val") init_val = atof(val().c_str());
+            else if (a == "-init_seed") init_seed = atof(val().c_str());   // spread of the per-var values (the reference seeds its varying sequence with it)
             else if (a == "-trial_time" || a == "-sleep") val();      // reference options with no meaning here
             else if (a == "-validate" || a == "-v") validate = true;
             else rest.push_back(a);
         }
+        // only one rank of a job prints (yask_main.cpp -msg_rank)
+        const int nranks = env->get_num_ranks(), my_rank = env->get_rank_index();
+        std::ostringstream quiet;
+        std::ostream& out = my_rank == msg_rank ? std::cout : quiet;
+        out << "YASK-compatible kernel harness, solution '" << soln->get_name() << "', target " << soln->get_target()
+            << ", " << soln->get_element_bytes() << "-byte elements, API version " << kfac.get_version_string() << "\n";
         std::string unused = soln->apply_command_line_options(rest);
         if (!unused.empty()) { std::cerr << "Error: extraneous parameter(s): '" << unused << "'; run with '-help' for usage.\n"; return 1; }
         if (trial_steps < 1 || num_trials < 1) { std::cerr << "Error: -trial_steps and -num_trials must be positive.\n"; return 1; }
@@ -80,21 +88,22 @@ int main(int argc, char** argv) {
         soln->prepare_solution();
         auto dims = soln->get_domain_dim_names();
         idx_t pts = 1;
-        std::cout << DIV << "Problem:\n";
+        out << DIV << "Problem:\n";
         std::ostringstream gs, ls;
         for (auto& d : dims) {
             gs << (gs.str().empty() ? "" : " * ") << d << "=" << soln->get_overall_domain_size(d);
             ls << (ls.str().empty() ? "" : " * ") << d << "=" << soln->get_rank_domain_size(d);
             pts *= soln->get_rank_domain_size(d);
         }
-        std::cout << " global-domain-size:     " << gs.str() << "\n"
+        out << " global-domain-size:     " << gs.str() << "\n"
                   << " local-domain-size:      " << ls.str() << "\n"
                   << " num-ranks:              " << env->get_num_ranks() << "\n"
                   << " num-points-per-step:    " << num_str(double(pts)) << "\n";
 
         // data: every var constant, slightly different per var (the reference's init_same pattern)
         int k = 0;
-        for (auto& v : soln->get_vars()) v->set_all_elements_same(init_val * (1.0 + double(k++) / 16.0));
+        auto var_val = [&](int kk) { return init_val * (1.0 + double(kk) * init_seed / 1.6); };
+        for (auto& v : soln->get_vars()) v->set_all_elements_same(var_val(k++));
 
         if (validate) {
             if (soln->get_name() != "iso3dfd" || soln->get_element_bytes() != 4) {
@@ -108,13 +117,19 @@ int main(int argc, char** argv) {
             other->apply_command_line_options("-kernel direct");
             other->prepare_solution();
             k = 0;
-            for (auto& v : other->get_vars()) v->set_all_elements_same(init_val * (1.0 + double(k++) / 16.0));
+            for (auto& v : other->get_vars()) v->set_all_elements_same(var_val(k++));
             // a bump in the middle so that the field is not constant
             idx_t_vec mid;
             mid.push_back(0);
             for (auto& d : dims) mid.push_back(soln->get_overall_domain_size(d) / 2);
-            p->set_element(1.0, mid);
-            other->get_var("p")->set_element(1.0, mid);
+            bool mine = true;     // the bump belongs to the rank whose domain holds it
+            for (size_t d = 0; d < dims.size(); d++)
+                mine = mine && mid[d + 1] >= p->get_first_rank_domain_index(dims[d]) && mid[d + 1] <= p->get_last_rank_domain_index(dims[d]);
+            if (mine) {
+                p->set_element(1.0, mid);
+                other->get_var("p")->set_element(1.0, mid);
+            }
+            env->global_barrier();
             const idx_t vsteps = std::min<idx_t>(trial_steps, 4);
             soln->run_solution(0, vsteps - 1);
             other->run_solution(0, vsteps - 1);
@@ -128,10 +143,12 @@ int main(int argc, char** argv) {
             q->get_elements_in_slice(b.data(), b.size(), f, l);
             idx_t bad = 0;
             for (size_t i = 0; i < a.size(); i++) bad += a[i] != b[i];
+            bad = env->sum_over_ranks(bad);
             other->end_solution();
-            std::cout << DIV << (bad ? "TEST FAILED: " : "TEST PASSED: ") << bad << " mismatch(es) between the sweep and the direct kernel over "
+            out << DIV << (bad ? "TEST FAILED: " : "TEST PASSED: ") << bad << " mismatch(es) between the sweep and the direct kernel over "
                       << vsteps << " step(s).\n";
             soln->end_solution();
+            env->finalize();
             return bad ? 1 : 0;
         }
 
@@ -140,18 +157,20 @@ int main(int argc, char** argv) {
         std::vector<Trial> trials;
         for (idx_t tr = 0; tr < num_trials; tr++) {
             soln->clear_stats();
+            env->global_barrier();
             soln->run_solution(first_t, first_t + trial_steps - 1);
             first_t += trial_steps;
             auto st = soln->get_stats();      // waits for the device
             Trial t;
             t.nsteps = st->get_num_steps_done();
-            t.secs = st->get_elapsed_secs();
+            // the ranks advance in lock-step (halo epochs); report the mean of their device times
+            t.secs = nranks > 1 ? double(env->sum_over_ranks(idx_t(st->get_elapsed_secs() * 1e9))) * 1e-9 / nranks : st->get_elapsed_secs();
             t.pts_ps = double(st->get_num_elements()) * double(t.nsteps) / t.secs;
             t.writes_ps = double(st->get_num_writes_done()) / t.secs;
             t.reads_ps = 0.;
             t.flops = double(st->get_est_fp_ops_done()) / t.secs;
             trials.push_back(t);
-            std::cout << DIV << "Trial " << (tr + 1) << ":\n"
+            out << DIV << "Trial " << (tr + 1) << ":\n"
                       << " num-steps-done:               " << t.nsteps << "\n"
                       << " elapsed-time (sec):           " << num_str(t.secs) << "\n"
                       << " throughput (num-writes/sec):  " << num_str(t.writes_ps) << "\n"
@@ -166,7 +185,7 @@ int main(int argc, char** argv) {
         for (auto& t : trials) { sum += t.pts_ps; sum2 += t.pts_ps * t.pts_ps; }
         const double n = double(trials.size());
         const double sd = n > 2 ? std::sqrt(std::max(0., (sum2 - sum * sum / n) / (n - 1.))) : 0.;
-        std::cout << DIV << "Throughput stats across trials:\n"
+        out << DIV << "Throughput stats across trials:\n"
                   << " num-trials:                          " << trials.size() << "\n"
                   << " min-throughput (num-points/sec):     " << num_str(sorted.back().pts_ps) << "\n"
                   << " max-throughput (num-points/sec):     " << num_str(best.pts_ps) << "\n"
@@ -186,7 +205,7 @@ int main(int argc, char** argv) {
                   << " mid-throughput (num-points/sec):  " << num_str(mid.pts_ps) << "\n";
         soln->end_solution();
         env->finalize();
-        std::cout << "YASK DONE\n";
+        out << "YASK DONE\n";
         return 0;
     } catch (yask_exception& e) {
         std::cerr << "YASK kernel harness: " << e.get_message() << "\n";

@@ -583,133 +583,269 @@ def _stage_sequence(ir, st):
 
 
 # ----------------------------------------------------------------------------------------------------
-# sweep variant (TMA-staged shared-memory planes, yask_b200/csrc/yb_gen_sweep.cuh)
+# sweep kernels (TMA-staged shared-memory planes, warp-specialised; yask_b200/csrc/yb_gen_sweep.cuh)
 # ----------------------------------------------------------------------------------------------------
-SWEEP_TZ = 128
-SWEEP_SMEM_LIMIT = 200 * 1024
-SWEEP_TWO_CTA_SMEM = 113 * 1024
-SWEEP_MAX_STREAMS = 24
+SWEEP_SMEM_LIMIT = 225 * 1024          # of the 227 KB a CTA may use
+SWEEP_TWO_CTA_SMEM = 112 * 1024        # two CTAs per SM below this
+SWEEP_MAX_STREAMS = 28
 
 
 def _roundup(v, m):
     return (v + m - 1) // m * m
 
 
-def sweep_plan(ir, p, ty=None, pf=None):
-    """Shared-memory layout of part `p` for the sweep kernel, or None when the part does not qualify: 3-D solutions,
-    unconditional non-scratch parts, full-rank outputs, no misc-dim vars among the full-rank reads, and rings that
-    fit in shared memory (x reach + pf slots per stream)."""
+def _sweep_streams(ir, p, ty, pf):
+    """TMA streams of part `p` for a tile of `ty` rows x 32 vectors and `pf` planes of prefetch, or None when the part does
+    not qualify (3-D solutions, unconditional non-scratch parts, full-rank outputs, no misc-dim / scratch vars among the
+    full-rank reads).  A var whose x neighbours are only read at the point's own (y, z) may be SPLIT into the current plane
+    with its y/z halo ('H') and a ring of halo-less planes ('C'); chosen when that needs less shared memory."""
     if len(ir["domain_dims"]) != 3 or p.get("cond") or p.get("step_cond") or p.get("scratch") or p.get("children"):
         return None
-    if ty is None:
-        ty = int(os.environ.get("YB_EMIT_SWEEP_TY", "4"))      # rows per tile (even: two row groups); tuning knob
-    if pf is None and os.environ.get("YB_EMIT_SWEEP_PF"):
-        pf = int(os.environ["YB_EMIT_SWEEP_PF"])                # planes of prefetch; default: chosen below
-    if pf is None:
-        # two planes of prefetch unless one plane lets two CTAs share an SM (2 x 113 KB)
-        plan = sweep_plan(ir, p, ty, 2)
-        if plan and plan["smem"] > SWEEP_TWO_CTA_SMEM:
-            plan1 = sweep_plan(ir, p, ty, 1)
-            if plan1 and plan1["smem"] <= SWEEP_TWO_CTA_SMEM:
-                return plan1
-        return plan or sweep_plan(ir, p, ty, 1)
     masks = _masks(ir, p)
     if any(masks[o["access"]] != 7 for o in p["outputs"]):
         return None
     vmap = {v["name"]: v for v in ir["vars"]}
-    ext = {}
-    for st in p["stmts"]:
-        for a, offs in st["reads"]:
-            e = ext.setdefault(a, [[0, 0], [0, 0], [0, 0]])
-            for d in range(3):
-                e[d][0], e[d][1] = min(e[d][0], offs[d]), max(e[d][1], offs[d])
     eb = ir["elem_bytes"]
-    align = 16 // eb
-    streams, off = [], 0
-    for a in sorted(ext):
+    vw = 16 // eb
+    tz = 32 * vw
+    offs = {}
+    for st in p["stmts"]:
+        for a, o in st["reads"]:
+            offs.setdefault(a, set()).add(tuple(o))
+    streams = []
+
+    def mk(a, kind, xl, xr, pts):
+        yl = min(o[1] for o in pts); yr = max(o[1] for o in pts)
+        zl = min(o[2] for o in pts); zr = max(o[2] for o in pts)
+        # The box must START on a 16-byte boundary in global memory (pads and tile origins are multiples of 128 B, so only
+        # the z reach matters): measured on B200 -- UTMALDG raises "illegal instruction" for a start coordinate that is not
+        # a multiple of 16 B.  The vector loads of the consumers need the same alignment on both ends.
+        zl = -_roundup(-zl, vw)
+        zr = _roundup(zr, vw)
+        rows = ty + yr - yl
+        pz = tz + zr - zl
+        slot = _roundup(rows * pz * eb, 128)
+        ns = xr - xl + 1 + pf
+        return {"acc": a, "kind": kind, "xl": xl, "xr": xr, "yl": yl, "yr": yr, "zl": zl, "zr": zr, "rows": rows, "pz": pz,
+                "slot": slot, "ns": ns, "bytes": rows * pz * eb}
+
+    for a in sorted(offs):
         if masks[a] != 7:
             continue
         acc = p["accesses"][a]
         if acc.get("misc") or vmap[acc["var"]].get("scratch"):
             return None
-        (xl, xr), (yl, yr), (zl, zr) = ext[a]
-        # The box must START on a 16-byte boundary in global memory (pads and tile origins are multiples of 128 B, so
-        # only the z reach matters): measured on B200 -- UTMALDG raises "illegal instruction" for a start coordinate
-        # that is not a multiple of 16 B (z reach -1, -2, -3 with 4-byte elements), reach -4 and 0 are fine.
-        zl = -_roundup(-zl, align)
-        rows = ty + yr - yl
-        pz = _roundup(SWEEP_TZ + zr - zl, align)
-        slot = _roundup(rows * pz * eb, 128)
-        ns = xr - xl + 1 + pf
-        streams.append({"acc": a, "xl": xl, "xr": xr, "yl": yl, "yr": yr, "zl": zl, "zr": zr, "rows": rows, "pz": pz,
-                        "slot": slot, "ns": ns, "off": off})
-        off += ns * slot
+        pts = offs[a]
+        xl, xr = min(o[0] for o in pts), max(o[0] for o in pts)
+        whole = [mk(a, "W", xl, xr, pts)]
+        star = all(o[1] == 0 and o[2] == 0 for o in pts if o[0] != 0)
+        here = [o for o in pts if o[0] == 0]
+        choice = whole
+        if star and here and xr - xl + 1 >= 3 and any(o[1] or o[2] for o in here):
+            split = [mk(a, "H", 0, 0, here), mk(a, "C", xl, xr, [(0, 0, 0)])]
+            if sum(s_["ns"] * s_["slot"] for s_ in split) < sum(s_["ns"] * s_["slot"] for s_ in whole):
+                choice = split
+        streams += choice
     if not streams or len(streams) > SWEEP_MAX_STREAMS:
         return None
-    bar_off = off
-    smem = bar_off + 8 * (pf + 1)
-    if smem > SWEEP_SMEM_LIMIT:
-        return None
-    return {"ty": ty, "pf": pf, "streams": streams, "bar_off": bar_off, "smem": smem,
-            "bytes0": sum((s_["xr"] - s_["xl"] + 1) * s_["rows"] * s_["pz"] * eb for s_ in streams),
-            "bytes1": sum(s_["rows"] * s_["pz"] * eb for s_ in streams)}
+    off = 0
+    for s_ in streams:
+        s_["off"] = off
+        off += s_["ns"] * s_["slot"]
+    return streams, off
+
+
+def sweep_plan(ir, p):
+    """Tile shape, prefetch depth and shared-memory layout of part `p`'s sweep kernel, or None."""
+    cands = [(8, 8, 2), (4, 4, 2), (8, 8, 1), (4, 4, 1)]          # (tile rows, consumer warps, planes of prefetch)
+    if os.environ.get("YB_EMIT_SWEEP_TY"):                          # tuning knobs: force one candidate
+        ty = int(os.environ["YB_EMIT_SWEEP_TY"])
+        cands = [(ty, int(os.environ.get("YB_EMIT_SWEEP_NW", str(min(ty, 8)))), int(os.environ.get("YB_EMIT_SWEEP_PF", "2")))]
+    for ty, nw, pf in cands:
+        r = _sweep_streams(ir, p, ty, pf)
+        if r is None:
+            return None
+        streams, ring_bytes = r
+        bar_off = _roundup(ring_bytes, 8)
+        smem = bar_off + 16 * (pf + 1)
+        if smem > SWEEP_SMEM_LIMIT:
+            continue
+        eb = ir["elem_bytes"]
+        occ = 2 if smem <= SWEEP_TWO_CTA_SMEM else 1
+        return {"ty": ty, "nw": nw, "rpt": ty // nw, "pf": pf, "vw": 16 // eb, "tz": 32 * (16 // eb), "streams": streams, "bar_off": bar_off,
+                "smem": smem, "occ": occ, "threads": nw * 32 + 128,
+                # consumer register budget after setmaxnreg (64 K registers per SM, producer warpgroup keeps 24 each)
+                "cregs": min(232, ((65536 // occ - 128 * 24) // (nw * 32)) // 8 * 8),
+                "bytes0": sum((s_["xr"] - s_["xl"] + 1) * s_["bytes"] for s_ in streams),
+                "bytes1": sum(s_["bytes"] for s_ in streams)}
+    return None
 
 
 def emit_sweep_kernel(ir, p, plan, ident) -> list:
     masks = _masks(ir, p)
-    sidx = {s_["acc"]: k for k, s_ in enumerate(plan["streams"])}
-    L = []
-    L.append(f"// sweep variant of part '{p['name']}' (yb_gen_sweep.cuh): {len(plan['streams'])} TMA streams, {plan['ty']} rows x {SWEEP_TZ} z per CTA (256 threads), "
-             f"{plan['pf']} planes of prefetch, {plan['smem']} B of shared memory")
-    L.append("template <typename T, int MODE>")
-    L.append(f"__global__ void __launch_bounds__(GEN_SW_THREADS) {ident}_{p['name']}_sweep_kernel(const __grid_constant__ GenSweepParams SP) {{")
-    L.append(f"    GEN_SWEEP_BEGIN({plan['ty']}, {plan['pf']})")
-    L.append("    auto sw_issue = [&](int j) {     // everything first needed at sweep iteration j")
-    L.append("        uint64_t* bar = &sw_bar[j % SW_NB];")
-    L.append(f"        mbar_arrive_expect_tx(bar, j == 0 ? {plan['bytes0']}u : {plan['bytes1']}u);")
-    for k, s_ in enumerate(plan["streams"]):
-        acc = p["accesses"][s_["acc"]]
-        L.append(f"        SW_LOAD({k}, {s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['xr']}, {s_['yl']}, {s_['zl']})   // {acc['var']}"
-                 f"(t{acc['toff']:+d}): x {s_['xl']}..{s_['xr']}, y {s_['yl']}..{s_['yr']}, z {s_['zl']}..{s_['zr']}")
-    L.append("    };")
-    L.append("    if (threadIdx.x == 0)")
-    L.append("        for (int j = 0; j < SW_PF && j < sw_len; j++) sw_issue(j);")
-    L.append("    for (int it = 0; it < sw_len; it++) {")
-    L.append("        if (threadIdx.x == 0 && it + SW_PF < sw_len) sw_issue(it + SW_PF);")
-    L.append("        mbar_wait(&sw_bar[it % SW_NB], (unsigned(it) / SW_NB) & 1u);")
-    L.append("        const int x = xs + it;")
-    # plane base pointers per (stream, dx) actually read
-    used = {}
-    for st in p["stmts"]:
-        for a, offs in st["reads"]:
-            if a in sidx:
-                used.setdefault((sidx[a], offs[0]), None)
-    for (k, dx) in sorted(used):
-        s_ = plan["streams"][k]
-        nm = f"s{k}_{'m' if dx < 0 else 'p'}{abs(dx)}"
-        used[(k, dx)] = nm
-        L.append(f"        const T* {nm} = SW_PLANE({s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['zl']}, {dx}, {s_['pz']});")
-    L.append("        _Pragma(\"unroll\") for (int r = 0; r < SW_TY / 2; r++) {     // r: row within this thread's group")
-    L.append("            const int y = y0_ + sw_rb + r;")
-    L.append("            if (y < P.ye && z < P.ze) {")
+    T = "float" if ir["elem_bytes"] == 4 else "double"
+    eb, vw, nw, rpt, pf = ir["elem_bytes"], plan["vw"], plan["nw"], plan["rpt"], plan["pf"]
+    streams = plan["streams"]
+    outs = {o["access"] for o in p["outputs"]}
 
+    def stream_of(a, o):
+        """Index of the stream that serves the read of access `a` at offset o = (dx, dy, dz)."""
+        for k, s_ in enumerate(streams):
+            if s_["acc"] != a:
+                continue
+            if s_["kind"] == "W" or (s_["kind"] == "H" and o[0] == 0) or (s_["kind"] == "C" and o[0] != 0):
+                return k
+        raise EmitError("read without a stream")
+
+    # ---- classify the reads ---------------------------------------------------------------------------------
+    loads = {}        # (k, dx, row offset, vector index) -> name
+    hoist = {}        # (acc, (dx, dy, dz)) -> (where, name): lower-rank reads moved out of the point bodies
     for st in p["stmts"]:
-        def rd(i, st=st):
-            a, offs = st["reads"][i]
-            if a in sidx:
-                s_ = plan["streams"][sidx[a]]
-                return f"{used[(sidx[a], offs[0])]}[(r + {offs[1] - s_['yl']}) * {s_['pz']} + ({offs[2]})]"
-            return _rd_text(a, offs, masks)
-        if st.get("kind") == "sincos":
-            L.append(f"                T {st['sin']}, {st['cos']};")
-            L.append(f"                YF_sincos({gen_expr(st['tree'], rd, OPS)}, {st['sin']}, {st['cos']});")
-            continue
-        L.append(f"                const T {st['dst']} = {gen_expr(st['tree'], rd, OPS)};")
-    for o in p["outputs"]:
-        L.append(f"                WR({o['access']}, {masks[o['access']]}, {o['src']});")
+        for a, o in st["reads"]:
+            o = tuple(o)
+            m = masks[a]
+            if m == 7:
+                k = stream_of(a, o)
+                for i in range(vw):
+                    j = (i + o[2]) // vw
+                    loads.setdefault((k, o[0], o[1] - streams[k]["yl"], j), None)
+            elif a not in outs and m in (0, 1, 2, 4):
+                hoist.setdefault((a, o), None)
+    n_str = len({s_["acc"] for s_ in streams})
+    # Points of a vector beyond the box are computed like the others (their reads stay inside shared memory / clamped
+    # indices) and simply not stored -- unless the part has reads that go to global memory with the point's own indices.
+    guard = any(masks[a] != 7 and (a, tuple(o)) not in hoist for st in p["stmts"] for a, o in st["reads"])
+    L = []
+    L.append(f"// sweep kernel of part '{p['name']}' (yb_gen_sweep.cuh): {len(streams)} TMA streams over {n_str} vars, tile {plan['ty']} rows x {plan['tz']} z, "
+             f"{nw} consumer warps x {vw} points, {pf} planes of prefetch, {plan['smem']} B of shared memory, {plan['occ']} CTA(s) per SM")
+    L.append("template <int MODE>")
+    L.append(f"__global__ void __launch_bounds__({plan['threads']}, {plan['occ']}) {ident}_{p['name']}_sweep_kernel(const __grid_constant__ GenSweepParams SP) {{")
+    L.append(f"    typedef {T} T;")
+    L.append(f"    constexpr int VW = {vw}, NW = {nw}, RPT = {rpt}, TY = {plan['ty']}, TZ = {plan['tz']}, PF = {pf}, NB = PF + 1;")
+    L.append("    extern __shared__ __align__(128) unsigned char sw_smem[];")
+    L.append("    const GenParams& P = SP.g;")
+    L.append(f"    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sw_smem + {plan['bar_off']});")
+    L.append("    uint64_t* done_bar = full_bar + NB;")
+    L.append("    const int sw_bz = int(blockIdx.x) % SP.nzb, sw_by = (int(blockIdx.x) / SP.nzb) % SP.nyb, sw_bc = int(blockIdx.x) / (SP.nzb * SP.nyb);")
+    L.append("    const int z0 = P.zb + sw_bz * TZ, y0_ = P.yb + sw_by * TY, xs = P.xb + sw_bc * SP.lx;")
+    L.append("    const int sw_len = min(SP.lx, P.xe - xs);")
+    L.append("    if (threadIdx.x == 0) {")
+    L.append("        for (int b = 0; b < NB; b++) { mbar_init(&full_bar[b], 1); mbar_init(&done_bar[b], NW); }")
+    L.append("        fence_barrier_init();")
+    L.append("    }")
+    L.append("    __syncthreads();")
+    L.append("    if (threadIdx.x >= NW * 32) {")
+    L.append("        // ---- producer warpgroup: one lane streams every plane of this CTA, then exits ----")
+    L.append('        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");')
+    L.append("        if (threadIdx.x == NW * 32) {")
+    L.append("            int fb = 0, db = 0; unsigned dpar = 0;")
+    L.append("            for (int j = 0; j < sw_len; j++) {")
+    L.append("                if (j > PF) {       // the slots written now were last read at iteration j - 1 - PF")
+    L.append("                    mbar_wait(&done_bar[db], dpar);")
+    L.append("                    if (++db == NB) { db = 0; dpar ^= 1u; }")
+    L.append("                }")
+    L.append("                uint64_t* bar = &full_bar[fb];")
+    L.append("                if (++fb == NB) fb = 0;")
+    L.append(f"                mbar_arrive_expect_tx(bar, j == 0 ? {plan['bytes0']}u : {plan['bytes1']}u);")
+    for k, s_ in enumerate(streams):
+        acc = p["accesses"][s_["acc"]]
+        L.append(f"                SW_ISSUE({k}, {s_['off']}, {s_['slot']}, {s_['ns']}, {s_['xl']}, {s_['xr']}, {s_['yl']}, {s_['zl']})   // {acc['var']}"
+                 f"(t{acc['toff']:+d}) {s_['kind']}: x {s_['xl']}..{s_['xr']}, y {s_['yl']}..{s_['yr']}, z {s_['zl']}..{s_['zr']}")
     L.append("            }")
     L.append("        }")
-    L.append("        __syncthreads();     // every thread is done with the oldest slots before they are refilled")
+    L.append("        return;")
+    L.append("    }")
+    L.append(f'    asm volatile("setmaxnreg.inc.sync.aligned.u32 {plan["cregs"]};");')
+    L.append("    // ---- consumers: warp w owns tile rows w*RPT .. w*RPT+RPT-1, lane l the z vector l ----")
+    L.append("    const int lane = int(threadIdx.x) & 31, sw_r0 = (int(threadIdx.x) >> 5) * RPT;")
+    L.append("    const int zq = z0 + lane * VW;                                    // first z of this thread's vector")
+    L.append("    const int nzv = max(0, min(VW, P.ze - zq));                       // valid points of the vector")
+    L.append("    const uint32_t sw_base = smem_u32(sw_smem);")
+    for k, s_ in enumerate(streams):
+        L.append(f"    const uint32_t t{k} = sw_base + {s_['off']}u + uint32_t((sw_r0 * {s_['pz']} + lane * VW + {-s_['zl']}) * {eb});")
+    # hoisted lower-rank reads that do not depend on x
+    for (a, o) in sorted(hoist):
+        m = masks[a]
+        nm = f"h{a}_{'_'.join(('m' if c < 0 else 'p') + str(abs(c)) for c in o)}"
+        if m == 0:
+            hoist[(a, o)] = ("pre", nm)
+            L.append(f"    const T {nm} = static_cast<const T*>(P.ptr[{a}])[0];")
+        elif m == 2:
+            hoist[(a, o)] = ("row", nm)
+            L.append(f"    T {nm}[RPT];")
+            L.append(f"    _Pragma(\"unroll\") for (int r = 0; r < RPT; r++) {nm}[r] = static_cast<const T*>(P.ptr[{a}])[(min(y0_ + sw_r0 + r, P.ye - 1) + ({o[1]})) * P.sy[{a}]];")
+        elif m == 4:
+            hoist[(a, o)] = ("vec", nm)
+            L.append(f"    T {nm}[VW];")
+            L.append(f"    _Pragma(\"unroll\") for (int i = 0; i < VW; i++) {nm}[i] = static_cast<const T*>(P.ptr[{a}])[(min(zq + i, P.ze - 1) + ({o[2]})) * P.sz[{a}]];")
+        else:
+            hoist[(a, o)] = ("plane", nm)
+    ns_vals = sorted({s_["ns"] for s_ in streams})
+    L.append("    int fb = 0; unsigned fpar = 0;")
+    L.append("    " + " ".join(f"uint32_t c{n} = 0;" for n in ns_vals) + "      // sweep iteration modulo the ring lengths")
+    L.append("    const bool vec_ok = nzv == VW && ((reinterpret_cast<uintptr_t>(static_cast<T*>(P.ptr[%d]) + zq) & 15) == 0) && (P.SY %% VW == 0) && (P.SX %% VW == 0);" % p["outputs"][0]["access"])
+    L.append("    for (int it = 0; it < sw_len; it++) {")
+    L.append("        mbar_wait(&full_bar[fb], fpar);")
+    L.append("        const int x = xs + it;")
+    for (a, o), (where, nm) in sorted(hoist.items()):
+        if where == "plane":
+            L.append(f"        const T {nm} = static_cast<const T*>(P.ptr[{a}])[(x + ({o[0]})) * P.sx[{a}]];")
+    # plane bases per (stream, dx) actually read
+    used = sorted({(k, dx) for (k, dx, _, _) in loads})
+    for (k, dx) in used:
+        s_ = streams[k]
+        L.append(f"        const uint32_t b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} = t{k} + sw_wrap(c{s_['ns']}, {dx - s_['xl']}u, {s_['ns']}u) * {s_['slot']}u;")
+    for key in sorted(loads):
+        k, dx, ry, j = key
+        s_ = streams[k]
+        nm = f"v{k}_{'m' if dx < 0 else 'p'}{abs(dx)}_{ry}_{'m' if j < 0 else 'p'}{abs(j)}"
+        loads[key] = nm
+    L.append("        _Pragma(\"unroll\") for (int r = 0; r < RPT; r++) {")
+    L.append("            const int y = y0_ + sw_r0 + r;")
+    for key in sorted(loads):
+        k, dx, ry, j = key
+        s_ = streams[k]
+        L.append(f"            T {loads[key]}[VW]; SwVec<T>::lds(b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} + uint32_t(((r + {ry}) * {s_['pz']} + ({j * vw})) * {eb}), {loads[key]});")
+    for o in p["outputs"]:
+        L.append(f"            T o{o['access']}[VW];")
+    L.append("            if (y < P.ye) {")
+    for i in range(vw):
+        L.append((f"                if ({i} < nzv) {{" if guard else "                {") + f"        // point {i} of the vector")
+        L.append(f"                    const int z = zq + {i}; (void)z;")
+
+        def rd(ri, st=None, i=i):
+            a, o = st["reads"][ri]
+            o = tuple(o)
+            if masks[a] == 7:
+                k = stream_of(a, o)
+                j = (i + o[2]) // vw
+                c = (i + o[2]) % vw
+                return f"{loads[(k, o[0], o[1] - streams[k]['yl'], j)]}[{c}]"
+            if (a, o) in hoist:
+                where, nm = hoist[(a, o)]
+                return {"pre": nm, "plane": nm, "row": f"{nm}[r]", "vec": f"{nm}[{i}]"}[where]
+            return _rd_text(a, o, masks)
+
+        for st in p["stmts"]:
+            rdf = (lambda ri, st=st: rd(ri, st))
+            if st.get("kind") == "sincos":
+                L.append(f"                    T {st['sin']}, {st['cos']};")
+                L.append(f"                    YF_sincos({gen_expr(st['tree'], rdf, OPS)}, {st['sin']}, {st['cos']});")
+                continue
+            L.append(f"                    const T {st['dst']} = {gen_expr(st['tree'], rdf, OPS)};")
+        for o in p["outputs"]:
+            L.append(f"                    o{o['access']}[{i}] = {o['src']};")
+        L.append("                }")
+    for o in p["outputs"]:
+        a = o["access"]
+        L.append(f"                {{ T* dst = static_cast<T*>(P.ptr[{a}]) + (x * P.SX + y * P.SY + zq);")
+        L.append(f"                  if (vec_ok) SwVec<T>::stg(dst, o{a}); else for (int i = 0; i < nzv; i++) dst[i] = o{a}[i]; }}")
+    L.append("            }")
+    L.append("        }")
+    L.append("        __syncwarp();")
+    L.append("        if (lane == 0) mbar_arrive(&done_bar[fb]);      // this warp is done with the oldest slots")
+    L.append("        if (++fb == NB) { fb = 0; fpar ^= 1u; }")
+    L.append("        " + " ".join(f"if (++c{n} == {n}u) c{n} = 0;" for n in ns_vals))
     L.append("    }")
     L.append("}")
     return L
@@ -805,11 +941,11 @@ def emit_cuda(ir: dict) -> str:
             plan = plans.get(p["name"])
             if plan:
                 ks = f"{ident}_{p['name']}_sweep_kernel"
+                fi = 0 if ir["elem_bytes"] == 4 else 1
                 L.append("    {")
                 L.append("        GenSweep& sw = g.stages.back().parts.back().sweep;")
-                L.append(f"        sw.fn[0][0] = GEN_SW_FN({ks}, float, 0); sw.fn[0][1] = GEN_SW_FN({ks}, float, 1);")
-                L.append(f"        sw.fn[1][0] = GEN_SW_FN({ks}, double, 0); sw.fn[1][1] = GEN_SW_FN({ks}, double, 1);")
-                L.append(f"        sw.ty = {plan['ty']}; sw.pf = {plan['pf']}; sw.smem = {plan['smem']}; sw.bar_off = {plan['bar_off']};")
+                L.append(f"        sw.fn[{fi}][0] = GEN_SW_FN({ks}, 0); sw.fn[{fi}][1] = GEN_SW_FN({ks}, 1);")
+                L.append(f"        sw.ty = {plan['ty']}; sw.tz = {plan['tz']}; sw.threads = {plan['threads']}; sw.occ = {plan['occ']}; sw.smem = {plan['smem']};")
                 for s_ in plan["streams"]:
                     L.append("        sw.streams.push_back(GenSweepStream{%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d});" % (
                         s_["acc"], s_["xl"], s_["xr"], s_["yl"], s_["yr"], s_["zl"], s_["zr"], s_["rows"], s_["pz"], s_["slot"], s_["ns"], s_["off"]))

@@ -66,3 +66,12 @@ def connect_local(solns) -> None:
             if q != r:
                 s.halo_import(q, b)
         s.halo_finalize()
+
+
+def connect_shm(soln, rank: int, world: int, job_key: str | None = None) -> None:
+    """Same wiring WITHOUT torch or MPI: the library's own shared-memory rendezvous (yask_b200/csrc/yb_comm.cpp), the path
+    the C++ yk_solution::prepare_solution() takes when the job has more than one rank."""
+    from . import capi
+    L = capi.lib()
+    capi._chk(L.yb_comm_init(rank, world, job_key.encode() if job_key else None))
+    capi._chk(L.yb_halo_connect(soln._h))
