@@ -150,6 +150,10 @@ int yb_var_info_get(const yb_solution* s, int var, yb_var_info* out);
  * dim: steps / domain points / misc extent).  Returns the new var's index (>= 0) or a negative error. */
 int yb_var_create(yb_solution* s, const char* name, int ndims, const char* const* dim_names, const int64_t* sizes);
 
+/* yk_var::fuse_vars (aux/yk_var_api.hpp:1370-1397; /root/reference/src/kernel/lib/yk_var_apis.cpp:334-360): `var` of `s`
+ * becomes another reference to the device storage of `src_var` of `src` (the same or another solution of this process);
+ * layouts must be identical; storage `var` had is released when its last user lets go. */
+int yb_var_fuse(yb_solution* s, int var, yb_solution* src, int src_var);
 /* Set per-var geometry before prepare (set_halo_size / set_min_pad_size, yk_var_api.hpp:1180-1290). */
 int yb_var_set_min_pad(yb_solution* s, int var, int dim, int64_t left, int64_t right);
 

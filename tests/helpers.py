@@ -77,3 +77,14 @@ def ulp_diff_f32(a, b):
     ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
     bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
     return np.abs(ai - bi)
+
+
+def elem_ulps(got, ref):
+    """Element-wise distance in units in the last place (ordered-integer distance of the bit patterns), float32 or float64."""
+    if got.dtype == np.float32:
+        return ulp_diff_f32(got, ref).astype(np.float64)
+    ai, bi = got.view(np.int64).astype(object), ref.view(np.int64).astype(object)     # exact arithmetic on 64-bit patterns
+    sign = 0x7FFFFFFFFFFFFFFF
+    ai = np.where(ai < 0, -(ai & sign), ai)
+    bi = np.where(bi < 0, -(bi & sign), bi)
+    return np.abs(ai - bi).astype(np.float64)

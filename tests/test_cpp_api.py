@@ -129,3 +129,38 @@ def test_harness_prints_the_reference_report_keys(stencil, args):
 def test_harness_validate_iso3dfd():
     r = subprocess.run([_exe("iso3dfd"), "-g", "96", "-validate"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "TEST PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def _run_ranks(exe, args, world, port):
+    """Start the harness once per rank the way mpirun/torchrun would (RANK / WORLD_SIZE / LOCAL_RANK in the environment);
+    the ranks meet in the library's shared-memory mailbox.  Ranks share the box's devices round-robin."""
+    import torch
+    ndev = max(1, torch.cuda.device_count())
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r % ndev), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   YASK_JOB_ID=f"pytest_{os.getpid()}_{port}")
+        procs.append(subprocess.Popen([exe] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = []
+    for p in procs:
+        o, e = p.communicate(timeout=300)
+        outs.append((p.returncode, o, e))
+    return outs
+
+
+@pytest.mark.gpu
+def test_harness_two_ranks_validate_and_report():
+    """The reference's multi-rank command line (`-nrx 2`, one process per rank) through the C++ API only: prepare_solution()
+    wires the ranks (yb_comm + CUDA IPC), -validate compares the sweep kernel with the direct kernel across the rank
+    boundary, the timing run reports from rank 0 with the global point count."""
+    outs = _run_ranks(_exe("iso3dfd"), ["-g", "96", "-nrx", "2", "-validate"], 2, 29561)
+    for rc, o, e in outs:
+        assert rc == 0, o + e
+    assert "TEST PASSED" in outs[0][1] and "num-ranks:              2" in outs[0][1]
+    assert "TEST PASSED" not in outs[1][1]          # only rank 0 prints
+    outs = _run_ranks(_exe("awp_elastic"), ["-g", "64", "-trial_steps", "3", "-num_trials", "2"], 2, 29562)   # rank grid chosen by the library
+    for rc, o, e in outs:
+        assert rc == 0, o + e
+    assert "YASK DONE" in outs[0][1] and "num-ranks:              2" in outs[0][1]
+    line = [l for l in outs[0][1].splitlines() if "global-domain-size" in l][0]
+    assert "x=64" in line

@@ -235,3 +235,37 @@ def test_config1_live_reference_128(tag, fp_mode, steps):
         got = run_gpu(n, steps, ins, fp_mode=fp_mode, opts={"kernel": kernel})
         assert got.shape == ref.shape
         assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), kernel
+
+
+def test_fuse_vars_shares_storage_between_solutions():
+    """yk_var::fuse_vars / yk_solution::fuse_vars (aux/yk_var_api.hpp:1370-1397): after fusing, both vars address ONE device
+    allocation -- a second solution steps the first one's data in place; incompatible layouts are refused."""
+    n, seed = (40, 24, 64), 5
+    ins = synth_inputs(n, seed)
+    ref = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], 8, 2, 2)[8:-8, 8:-8, 8:-8]
+    _, a = run_gpu(n, 0, ins, ret_soln=True)          # holds the inputs, never runs
+    b = capi.Solution("iso3dfd")
+    b.set_overall_domain_size_vec(n)
+    b.prepare_solution(0)
+    for name in ("p", "v"):
+        b.get_var(name).fuse_vars(a.get_var(name))
+    assert b.get_var("p").device_ptr(0) == a.get_var("p").device_ptr(0)
+    b.run_solution(0, 1)
+    b.sync()
+    pa = a.get_var("p")
+    # `a` never ran: read its storage through b's step window (the data is shared, the bookkeeping is per solution)
+    pb = b.get_var("p")
+    tl = pb.get_last_valid_step_index()
+    got = pb.get_elements_in_slice(*pb.domain_box(tl))
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    raw_a = pa.get_elements_in_slice(*pa.domain_box(tl % 2))     # same slot of the shared allocation
+    assert np.array_equal(raw_a.view(np.uint32), ref.view(np.uint32))
+    c = capi.Solution("iso3dfd")
+    c.set_overall_domain_size_vec((n[0] + 8, n[1], n[2]))
+    c.prepare_solution(0)
+    with pytest.raises(capi.YaskError):
+        c.get_var("p").fuse_vars(a.get_var("p"))
+    b.close()                                         # the allocation lives on while `a` references it
+    assert np.array_equal(pa.get_elements_in_slice(*pa.domain_box(tl % 2)).view(np.uint32), ref.view(np.uint32))
+    a.close()
+    c.close()

@@ -82,3 +82,44 @@ def test_gloo_world2_rendezvous_and_geometry():
         assert got[0][1] == [0, 0, 0] and got[0][2] == [50, 32, 32]
         assert got[1][1] == [50, 0, 0] and got[1][2] == [50, 32, 32]
         assert err is not None and "not prepared" in err
+
+
+def _comm_worker(rank, world, key, q):
+    import ctypes as C
+    import numpy as np
+    L = capi.lib()
+    capi._chk(L.yb_comm_init(rank, world, key.encode()))
+    assert L.yb_comm_rank() == rank and L.yb_comm_world() == world
+    # all-gather larger than one mailbox slot (64 KiB): exercises the chunked path
+    n = 100_000
+    mine = (np.arange(n, dtype=np.int32) * (rank + 1)).astype(np.int32)
+    allv = np.zeros(world * n, np.int32)
+    capi._chk(L.yb_comm_allgather(mine.ctypes.data_as(C.c_void_p), mine.nbytes, allv.ctypes.data_as(C.c_void_p)))
+    ok = all(np.array_equal(allv[r * n:(r + 1) * n], np.arange(n, dtype=np.int32) * (r + 1)) for r in range(world))
+    s = C.c_int64(0)
+    capi._chk(L.yb_comm_sum_i64(10 + rank, C.byref(s)))
+    m = C.c_double(0)
+    capi._chk(L.yb_comm_max_f64(1.5 * rank, C.byref(m)))
+    for _ in range(50):
+        capi._chk(L.yb_comm_barrier())
+    L.yb_comm_finalize()
+    q.put((rank, ok, s.value, m.value))
+
+
+def test_shared_memory_rendezvous_three_processes():
+    """The library's own communicator (yb_comm.cpp: /dev/shm mailbox, no MPI, no torch): all-gather, integer sum, max and
+    barriers between three processes -- what yk_env::global_barrier / sum_over_ranks and the halo-blob exchange of
+    prepare_solution() run on."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    key = f"pytest_{os.getpid()}"
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, key, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for r, (rank, ok, s, m) in enumerate(res):
+        assert rank == r and ok and s == sum(10 + i for i in range(world)) and m == 1.5 * (world - 1)

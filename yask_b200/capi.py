@@ -57,7 +57,7 @@ ABI_SYMBOLS = [
     "yb_set_rank_domain_size", "yb_set_overall_domain_size", "yb_set_num_ranks", "yb_set_rank_index", "yb_set_min_pad_size",
     "yb_get_rank_domain_size", "yb_get_overall_domain_size", "yb_get_num_ranks", "yb_get_rank_index",
     "yb_get_first_rank_domain_index", "yb_get_last_rank_domain_index", "yb_set_option", "yb_get_option", "yb_set_stream",
-    "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_create", "yb_var_set_min_pad",
+    "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_create", "yb_var_fuse", "yb_var_set_min_pad",
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
     "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_var_fill_hash", "yb_var_fill_hash_shifted", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
         L.yb_var_info_get.argtypes = [p, i32, C.POINTER(VarInfo)]
         L.yb_var_create.argtypes = [p, C.c_char_p, i32, C.POINTER(C.c_char_p), C.POINTER(i64)]
         L.yb_var_set_min_pad.argtypes = [p, i32, i32, i64, i64]
+        L.yb_var_fuse.argtypes = [p, i32, p, i32]
         for nm in ("yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device"):
             getattr(L, nm).argtypes = [p, i32, p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         L.yb_var_set_all_same.argtypes = [p, i32, C.c_double]
@@ -239,6 +240,10 @@ class Var:
         else:
             _chk(lib().yb_var_fill_hash_shifted(self.soln._h, self.index, int(step), seed & 0xFFFFFFFF, salt & 0xFFFFFFFF, lo, hi,
                                                 _arr(list(shift) + [0] * (3 - len(shift)))))
+
+    def fuse_vars(self, source: "Var"):
+        """yk_var::fuse_vars: this var becomes another reference to `source`'s device storage."""
+        _chk(lib().yb_var_fuse(self.soln._h, self.index, source.soln._h, source.index))
 
     def checksum(self, step: int) -> int:
         out = C.c_uint64(0)

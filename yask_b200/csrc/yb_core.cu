@@ -28,8 +28,11 @@ Solution::~Solution() {
     if (device >= 0) {
         cudaSetDevice(device);
         halo_free(halo); halo = nullptr;
-        for (auto& v : vars)
-            if (v.dev) cudaFree(v.dev);
+        for (auto& v : vars) {
+            if (v.store) v.store.reset();          // frees when this was the last var sharing the allocation
+            else if (v.dev) cudaFree(v.dev);
+            v.dev = nullptr;
+        }
         for (auto& pe : pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
         if (stage_dev) cudaFree(stage_dev);
         if (stage_host) cudaFreeHost(stage_host);
@@ -124,6 +127,16 @@ void compute_var_geometry(Solution& s, Var& v) {
     int64_t a256 = 256 / v.elem_bytes;
     v.slot_elems = (v.slot_elems + a256 - 1) / a256 * a256;
     v.first_valid_step = 0;
+}
+
+// device storage of a var, owned through Var::store
+static cudaError_t alloc_var_storage(Var& v) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(v.bytes(), 256));
+    if (e != cudaSuccess) return e;
+    v.store = std::shared_ptr<void>(p, [](void* q) { cudaFree(q); });
+    v.dev = p;
+    return cudaSuccess;
 }
 
 static int ensure_stage(Solution& s, size_t bytes) {
@@ -415,8 +428,16 @@ int yb_solution_prepare(yb_solution* s_, int device) {
     if (!s->own_stream) YB_CUDA(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     if (!s->comm_stream) YB_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
     for (auto& v : s->vars) {
+        const int64_t fvs = v.first_valid_step;
+        const size_t had = v.dev ? v.bytes() : 0;
         compute_var_geometry(*s, v);
-        YB_CUDA(cudaMalloc(&v.dev, v.bytes()));
+        if (v.dev) {
+            // storage came from fuse_vars before prepare: it must fit the geometry this solution needs
+            if (v.bytes() != had) return set_error(YB_EINVAL, "var '%s' was fused with storage of %zu bytes but this solution needs %zu", v.spec.name.c_str(), had, v.bytes());
+            v.first_valid_step = fvs;
+            continue;
+        }
+        YB_CUDA(alloc_var_storage(v));
         // the reference zero-initialises storage (alloc.cpp); halo cells outside the global domain
         // keep whatever the user wrote there.
         YB_CUDA(cudaMemsetAsync(v.dev, 0, v.bytes(), s->stream()));
@@ -511,12 +532,68 @@ int yb_var_create(yb_solution* s_, const char* name, int ndims, const char* cons
     if (s->prepared) {
         YB_CUDA(cudaSetDevice(s->device));
         compute_var_geometry(*s, v);
-        YB_CUDA(cudaMalloc(&v.dev, v.bytes()));
+        YB_CUDA(alloc_var_storage(v));
         YB_CUDA(cudaMemsetAsync(v.dev, 0, v.bytes(), s->stream()));
         if (s->halo) return set_error(YB_EUNSUPPORTED, "vars cannot be added to a prepared multi-rank solution");
     }
     s->vars.push_back(std::move(v));
     return int(s->vars.size()) - 1;
+}
+
+// yk_var::fuse_vars (/root/reference/src/kernel/lib/yk_var_apis.cpp:302-360): `var` of `s` becomes another reference to the
+// storage of `src_var` of `src` (which may be the same solution).  Both must agree on element size, dims and allocation
+// (is_storage_layout_identical); any storage `var` had is released; the valid-step window is taken from the source.
+int yb_var_fuse(yb_solution* s_, int var, yb_solution* src_, int src_var) {
+    Solution* s = SOL(s_);
+    Solution* src = SOL(src_);
+    if (int rc = check_var(s, var)) return rc;
+    if (int rc = check_var(src, src_var)) return rc;
+    Var& d = s->vars[var];
+    Var& o = src->vars[src_var];
+    if (&d == &o) return 0;
+    if (s->halo || src->halo) return set_error(YB_EUNSUPPORTED, "fuse_vars: vars of a prepared multi-rank solution are mapped by their neighbours and cannot change storage");
+    if (d.elem_bytes != o.elem_bytes || d.dims.size() != o.dims.size())
+        return set_error(YB_EINVAL, "fuse_vars(): '%s' and '%s' differ in element size or number of dims", d.spec.name.c_str(), o.spec.name.c_str());
+    for (size_t i = 0; i < d.dims.size(); i++)
+        if (d.dims[i].spec.name != o.dims[i].spec.name || d.dims[i].spec.kind != o.dims[i].spec.kind)
+            return set_error(YB_EINVAL, "fuse_vars(): dim %zu of '%s' is '%s' but '%s' in '%s'", i, d.spec.name.c_str(), d.dims[i].spec.name.c_str(),
+                             o.dims[i].spec.name.c_str(), o.spec.name.c_str());
+    if (!o.dev) {
+        // source not allocated: this var becomes unallocated too (yk_var_api.hpp:1378-1383)
+        if (s->prepared) return set_error(YB_ESTATE, "fuse_vars(): source var '%s' has no storage but '%s' belongs to a prepared solution", o.spec.name.c_str(), d.spec.name.c_str());
+        d.store.reset(); d.dev = nullptr;
+        return 0;
+    }
+    if (s->prepared || d.dev) {
+        // geometry of `var` is known: it must match the source's allocation exactly
+        bool same = d.step_alloc() == o.step_alloc() && d.slot_elems == o.slot_elems;
+        for (size_t i = 0; i < d.dims.size() && same; i++)
+            same = d.dims[i].alloc == o.dims[i].alloc && d.dims[i].pad_l == o.dims[i].pad_l && d.dims[i].stride == o.dims[i].stride &&
+                   d.dims[i].domain == o.dims[i].domain;
+        if (!same) return set_error(YB_EINVAL, "fuse_vars(): attempt to replace the storage of '%s' with the incompatible layout of '%s'", d.spec.name.c_str(), o.spec.name.c_str());
+    } else {
+        // not prepared yet: adopt the source's geometry now; prepare() checks that it is what the solution needs
+        d.spec.step_alloc = o.spec.step_alloc;
+        for (size_t i = 0; i < d.dims.size(); i++) {
+            const DimSpec keep = d.dims[i].spec;
+            d.dims[i] = o.dims[i];
+            d.dims[i].spec = keep;
+            d.dims[i].spec.halo_l = std::max(keep.halo_l, int64_t(0)); d.dims[i].spec.halo_r = std::max(keep.halo_r, int64_t(0));
+        }
+        d.slot_elems = o.slot_elems;
+    }
+    if (src->prepared) { cudaSetDevice(src->device); cudaStreamSynchronize(src->stream()); }
+    if (!o.store) return set_error(YB_ESTATE, "fuse_vars(): storage of '%s' is not shareable", o.spec.name.c_str());
+    d.store = o.store;
+    d.dev = o.dev;
+    d.first_valid_step = o.first_valid_step;
+    if (s->prepared) {
+        // tensor maps and cached pointers of the engine refer to the old storage
+        YB_CUDA(cudaSetDevice(s->device));
+        YB_CUDA(cudaStreamSynchronize(s->stream()));
+        if (int rc = s->engine->prepare(*s)) return rc;
+    }
+    return 0;
 }
 
 int yb_var_set_min_pad(yb_solution* s_, int var, int dim, int64_t left, int64_t right) {

@@ -77,6 +77,9 @@ struct Var {
     int64_t slot_elems = 0;
     int64_t first_valid_step = 0;  // local offset of the step dim
     void* dev = nullptr;           // step_alloc * slot_elems elements
+    // Solution vars own their storage through `store` (cudaFree on the last release): yk_var::fuse_vars makes two vars --
+    // possibly of two solutions -- share one allocation (/root/reference/src/kernel/lib/yk_var_apis.cpp:334-360).
+    std::shared_ptr<void> store;
     bool has_step() const { return !dims.empty() && dims[0].spec.kind == DIM_STEP; }
     int step_alloc() const { return has_step() ? spec.step_alloc : 1; }
     int64_t last_valid_step() const { return first_valid_step + step_alloc() - 1; }

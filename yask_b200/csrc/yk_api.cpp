@@ -418,7 +418,11 @@ struct B200Var : yk_var {
         if (!other) return false;
         return get_dim_names() == other->get_dim_names() && get_alloc_size_vec() == other->get_alloc_size_vec();
     }
-    void fuse_vars(yk_var_ptr) override { fail("fuse_vars is not supported by the B200 engine"); }
+    void fuse_vars(yk_var_ptr source) override {
+        auto src = std::dynamic_pointer_cast<B200Var>(source);
+        if (!src) fail("fuse_vars(): the source var does not belong to the B200 engine");
+        chk(yb_var_fuse(h->s, vi, src->h->s, src->vi));
+    }
     // Storage lives in HBM: hand out a HOST snapshot (refreshed on every call).  The reference documents no
     // layout guarantees for this buffer (aux/yk_var_api.hpp:1399-1437); writes to it are not propagated.
     void* get_raw_storage_buffer() override {
@@ -684,7 +688,12 @@ struct B200Solution : yk_solution {
     void call_after_prepare_solution(hook_fn_t f) override { after_prepare.push_back(f); }
     void call_before_run_solution(hook_fn_2idx_t f) override { before_run.push_back(f); }
     void call_after_run_solution(hook_fn_2idx_t f) override { after_run.push_back(f); }
-    void fuse_vars(yk_solution_ptr) override { fail("fuse_vars is not supported by the B200 engine"); }
+    void fuse_vars(yk_solution_ptr source) override {
+        // every pair of vars with the same name (soln_apis.cpp:271-283)
+        if (!source) fail("fuse_vars(): null source solution");
+        for (auto& sv : source->get_vars())
+            if (yb_var_index(h->s, sv->get_name().c_str()) >= 0) get_var(sv->get_name())->fuse_vars(sv);
+    }
     void set_step_wrap(bool w) override { step_wrap = w; }
     bool get_step_wrap() const override { return step_wrap; }
     void set_debug_output(yask_output_ptr debug) override { yk_env::set_debug_output(debug); }
