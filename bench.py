@@ -410,7 +410,14 @@ def main_b200(args):
     t1 = time.time()
     st = s.get_stats()
     clk = clocks.window(t0, t1)
-    dev_s, wall_s = max_over_ranks(st.elapsed_secs, t1 - t0)     # CUDA events on the launching stream, max over ranks
+    own_dev_s = st.elapsed_secs
+    dev_s, wall_s = max_over_ranks(own_dev_s, t1 - t0)           # CUDA events on the launching stream, max over ranks
+    per_rank_ms = None
+    if dist:
+        tt = torch.zeros(world, dtype=torch.float64, device="cuda")
+        tt[rank] = own_dev_s / K * 1e3
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        per_rank_ms = [round(x, 4) for x in tt.tolist()]
     launches = st.kernel_launches
     pts_per_gpu = N ** 3
     value = pts_per_gpu * world * K / dev_s / 1e9
@@ -542,6 +549,8 @@ def main_b200(args):
                                              "published in-kernel, interior swept meanwhile; wait kernel in front of the next step")},
                 "hbm_gbs_algorithmic": round(value * BYTES_PER_POINT, 1), "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clk}
+        if per_rank_ms is not None:
+            line["per_rank_ms_per_step"] = per_rank_ms
         if hc is not None:
             line["halo_check"] = hc["result"]
             line["halo_check_detail"] = hc

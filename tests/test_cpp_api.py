@@ -164,3 +164,16 @@ def test_harness_two_ranks_validate_and_report():
     assert "YASK DONE" in outs[0][1] and "num-ranks:              2" in outs[0][1]
     line = [l for l in outs[0][1].splitlines() if "global-domain-size" in l][0]
     assert "x=64" in line
+
+
+@pytest.mark.gpu
+def test_yask_sh_launcher_two_ranks(tmp_path):
+    """The yask.sh-style launcher (yask_b200/scripts/yask.sh): reference option names, log file, closing checks; -ranks 2 starts
+    one process per rank without mpirun."""
+    sh = os.path.join(ROOT, "yask_b200", "scripts", "yask.sh")
+    _exe("iso3dfd")
+    r = subprocess.run([sh, "-stencil", "iso3dfd", "-ranks", "2", "-log_dir", str(tmp_path), "-v", "-g", "96"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "YASK passed internal validation test." in r.stdout and "YASK ran successfully." in r.stdout
+    logs = [f for f in os.listdir(tmp_path) if f.endswith(".log")]
+    assert len(logs) == 1 and logs[0].startswith("yask.iso3dfd.b200.") and ".r2." in logs[0]

@@ -37,32 +37,38 @@ struct GenSweepParams {
 #define GEN_SW_FN(k, M) reinterpret_cast<yb::gen::GenSweepFn>(static_cast<void (*)(const yb::gen::GenSweepParams)>(k<M>))
 
 #ifdef __CUDACC__
-// 16-byte vectors of the element type: VW elements
-template <typename T> struct SwVec;
-template <> struct SwVec<float> {
-    static constexpr int VW = 4;
+// The VW consecutive points of a thread: a 16-byte vector (float x 4, double x 2) or half of one (float x 2, double x 1).
+template <typename T, int VW> struct SwVec;
+template <> struct SwVec<float, 4> {
     static __device__ __forceinline__ void lds(uint32_t addr, float* o) {
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
     }
     static __device__ __forceinline__ void stg(float* p, const float* v) {
         asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     }
-    static __device__ __forceinline__ void ldg(const float* p, float* o) {
-        const float4 v = *reinterpret_cast<const float4*>(p);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+};
+template <> struct SwVec<float, 2> {
+    static __device__ __forceinline__ void lds(uint32_t addr, float* o) {
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void stg(float* p, const float* v) {
+        asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
     }
 };
-template <> struct SwVec<double> {
-    static constexpr int VW = 2;
+template <> struct SwVec<double, 2> {
     static __device__ __forceinline__ void lds(uint32_t addr, double* o) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
     }
     static __device__ __forceinline__ void stg(double* p, const double* v) {
         asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
     }
-    static __device__ __forceinline__ void ldg(const double* p, double* o) {
-        const double2 v = *reinterpret_cast<const double2*>(p);
-        o[0] = v.x; o[1] = v.y;
+};
+template <> struct SwVec<double, 1> {
+    static __device__ __forceinline__ void lds(uint32_t addr, double* o) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o[0]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void stg(double* p, const double* v) {
+        asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v[0]) : "memory");
     }
 };
 

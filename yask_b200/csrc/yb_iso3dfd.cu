@@ -2,6 +2,9 @@
 // /root/reference/src/stencils/Iso3dfdStencil.cpp), FD coefficients,
 // TMA tensor maps and kernel launch logic.
 #include <math.h>
+
+#include <algorithm>
+#include <vector>
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -318,42 +321,50 @@ struct IsoEngine : Engine {
             P.ntz = int((box.e[2] - box.b[2] + c.tz - 1) / c.tz);
             const int64_t ntile = int64_t(P.nty) * P.ntz;
             const int gmax = grid_override > 0 ? grid_override : num_sms;
-            // x chunks.  With an in-kernel completion signal the boundary planes [0,R) / [nx-R,nx) are chunks of their
-            // own and come FIRST, so that every CTA sweeps them (and stores them into the neighbours) before any interior
-            // plane; the rest of [begin,end) is split evenly.
-            int nb = 0;
-            int64_t ib = box.b[0], ie = box.e[0];
-            const bool sig = fused && s.fused_x.counter != nullptr && P.nx >= 3 * radius;
-            if (sig) {
-                if (P.peer_lo) { P.cx0[nb] = 0; P.cx1[nb] = radius; nb++; ib = radius; }
-                if (P.peer_hi) { P.cx0[nb] = P.nx - radius; P.cx1[nb] = P.nx; nb++; ie = P.nx - radius; }
-            }
+            // x chunks of equal length.  With an in-kernel completion signal the chunk that starts at plane 0 and the chunk
+            // that ends at plane nx-1 (swept downwards) are numbered first, so that every CTA computes -- and stores into the
+            // neighbours -- the boundary planes at the very start of its first sweeps.
+            const bool sig = fused && s.fused_x.counter != nullptr && P.nx >= 4 * radius;
+            const int64_t ib = box.b[0], ie = box.e[0];
             const int64_t nxb = ie - ib;
-            const int max_nc = ISO_MAX_CHUNKS - nb;
-            int nc_best = 1;
+            const int min_nc = (sig && P.peer_lo && P.peer_hi) ? 2 : 1;
+            const int64_t max_nc = std::min<int64_t>(ISO_MAX_CHUNKS, sig ? nxb / radius : nxb);
+            int nc_best = min_nc;
             if (lx > 0) {
-                nc_best = int(std::min<int64_t>((nxb + lx - 1) / lx, max_nc));
+                nc_best = int(std::max<int64_t>(min_nc, std::min<int64_t>((nxb + lx - 1) / lx, max_nc)));
             } else {
                 // Pick the chunk count that minimises (rounds of units per CTA) x (chunk length + queue
                 // warm-up): long chunks amortise the 2R warm-up planes, short ones balance the last round.
                 double best = 1e30;
-                for (int nc = 1; nc <= max_nc && nc <= nxb; nc++) {
+                for (int64_t nc = min_nc; nc <= max_nc; nc++) {
                     const int64_t l = (nxb + nc - 1) / nc;
                     const int64_t rounds = (ntile * nc + gmax - 1) / gmax;
                     const double cost = double(rounds) * (double(l) + 2 * radius * 0.4);
-                    if (cost < best * 0.999) { best = cost; nc_best = nc; }
+                    if (cost < best * 0.999) { best = cost; nc_best = int(nc); }
                 }
             }
-            if (nxb > 0) {
-                const int64_t l = (nxb + nc_best - 1) / nc_best;
-                for (int64_t x = ib; x < ie; x += l) { P.cx0[nb] = int(x); P.cx1[nb] = int(std::min(x + l, ie)); nb++; }
+            int nb = 0, nsig = 0;
+            {
+                const int nc = nc_best;      // balanced partition: chunk lengths differ by at most one plane (all >= R when signalling)
+                std::vector<int> order;
+                if (sig && P.peer_lo) order.push_back(0);
+                if (sig && P.peer_hi && !(nc == 1 && P.peer_lo)) order.push_back(nc - 1);
+                nsig = int(order.size());
+                for (int c = 0; c < nc; c++)
+                    if (std::find(order.begin(), order.end(), c) == order.end()) order.push_back(c);
+                for (int c : order) {
+                    const int64_t x0 = ib + nxb * c / nc, x1 = ib + nxb * (c + 1) / nc;
+                    const bool down = sig && P.peer_hi && c == nc - 1 && !(nc == 1 && P.peer_lo);
+                    P.cx0[nb] = int(down ? x1 - 1 : x0); P.clen[nb] = int(x1 - x0); P.cdir[nb] = down ? -1 : 1;
+                    nb++;
+                }
             }
             P.nchunks = nb;
             P.sig_units = 0; P.sig_total = 0; P.sig_counter = nullptr; P.sig_flag_lo = P.sig_flag_hi = nullptr; P.sig_epoch = 0;
             const int64_t nunits = int64_t(P.nty) * P.ntz * P.nchunks;
             int grid = int(std::min<int64_t>(nunits, gmax));
             if (sig) {
-                P.sig_units = int(ntile) * ((P.peer_lo ? 1 : 0) + (P.peer_hi ? 1 : 0));
+                P.sig_units = int(ntile) * nsig;
                 P.sig_total = unsigned(grid) * unsigned(c.ty * c.tz / 8 / 32);     // consumer warps: 8 points per thread
                 P.sig_counter = s.fused_x.counter;
                 P.sig_flag_lo = s.fused_x.flag_lo; P.sig_flag_hi = s.fused_x.flag_hi;

@@ -34,21 +34,25 @@ struct IsoParams {
     int pad_x, pad_y, pad_z;    // p arrays: alloc index of domain origin (TMA coordinates)
     int vpad_x, vpad_y, vpad_z; // v array: same
     int nty, ntz, nchunks;      // tiling of [begin,end): tiles in y,z; chunks along x
-    // x range of every chunk.  Work units are numbered chunk-major, so the chunks listed first are swept first by
-    // every CTA: a multi-rank launch lists its two BOUNDARY chunks [0,R) and [nx-R,nx) before the interior ones.
-    int cx0[ISO_MAX_CHUNKS], cx1[ISO_MAX_CHUNKS];
+    // Every chunk: first plane computed, number of planes, sweep direction (+1 / -1).  Work units are numbered chunk-major,
+    // so the chunks listed first are swept first by every CTA.  A multi-rank launch lists the chunk that starts at plane 0
+    // (swept upwards) and the chunk that ends at plane nx-1 (swept DOWNWARDS) first: the planes the x neighbours need are
+    // then the first R planes of those sweeps.  (A downward sweep gives the same bits: the x neighbours enter the sum as
+    // p[x-r] + p[x+r], and IEEE addition commutes.)
+    int cx0[ISO_MAX_CHUNKS], clen[ISO_MAX_CHUNKS], cdir[ISO_MAX_CHUNKS];
     int pol_c, pol_h, pol_pv;   // L2 eviction policy of the TMA streams: 0 normal, 1 evict_first, 2 evict_last
     int st_cs;                  // 1: results leave with streaming (evict-first) stores
     // Fused halo exchange: when non-null, the first / last R computed x planes are ALSO stored into the lower /
     // upper x neighbour's halo cells (peer HBM over NVLink), indexed exactly like `out`.
     float* peer_lo;
     float* peer_hi;
-    // In-kernel completion signal of the boundary chunks (replaces the push + signal kernels that used to follow the
-    // sweep): units [0, sig_units) are the boundary units.  Every consumer warp of the grid arrives once on
-    // *sig_counter after its last boundary unit (system-scope fence first); the arrival that completes the count
-    // (sig_total) publishes sig_epoch into the neighbours' flag words with release semantics and resets the counter.
-    // The neighbours' next step, which needs exactly these planes, therefore has them one whole interior sweep early
-    // (the overlap of /root/reference/src/kernel/lib/context.cpp:378-475: exterior first, exchange during the interior).
+    // In-kernel completion signal of the boundary planes (replaces the push + signal kernels that used to follow the
+    // sweep): units [0, sig_units) are the units whose sweeps START with boundary planes.  Every consumer warp of the
+    // grid arrives once on *sig_counter, right after the R-th plane of its last such unit (system-scope fence first);
+    // the arrival that completes the count (sig_total) publishes sig_epoch into the neighbours' flag words with release
+    // semantics and resets the counter.  The neighbours' next step, which needs exactly these planes, therefore has them
+    // while this rank is still sweeping the rest (the overlap of /root/reference/src/kernel/lib/context.cpp:378-475:
+    // exterior first, exchange during the interior) -- and no plane is swept twice or warmed up twice for it.
     int sig_units;
     unsigned int sig_total;
     unsigned int* sig_counter;
@@ -141,7 +145,8 @@ struct IsoCursor {
     int unit;      // current work unit
     int it;        // iteration within unit: 0 .. n_it-1
     int n_it;      // lx_unit + 2R
-    int x0, y0, z0;  // unit origin (domain coordinates)
+    int x0, y0, z0;  // unit origin (domain coordinates); x0 = first plane computed
+    int dir;         // sweep direction along x
     int stage;
     uint32_t phase;
 };
@@ -154,7 +159,8 @@ __device__ __forceinline__ void iso_unit_setup(IsoCursor& cu, const IsoParams& P
     cu.z0 = P.z_begin + tz * T::TZ;
     cu.y0 = P.y_begin + ty * T::TY;
     cu.x0 = P.cx0[u];
-    cu.n_it = P.cx1[u] - P.cx0[u] + 2 * T::R;
+    cu.dir = P.cdir[u];
+    cu.n_it = P.clen[u] + 2 * T::R;
     cu.it = 0;
 }
 
@@ -196,7 +202,7 @@ struct IsoTile2 {
 };
 
 // Boundary-phase completion (see IsoParams::sig_*): called once per consumer warp, by all of its lanes.
-__device__ __forceinline__ void iso_boundary_arrive(const IsoParams& P, int lane) {
+static __device__ __noinline__ void iso_boundary_arrive(const IsoParams& P, int lane) {
     __threadfence_system();          // this lane's peer stores are ordered before what follows, at system scope
     __syncwarp();
     if (lane == 0) {
@@ -241,7 +247,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
 
     // ---- producer -----------------------------------------------------------------------------------
     IsoCursor pr;
-    pr.unit = blockIdx.x; pr.stage = 0; pr.phase = 0; pr.it = 0; pr.n_it = 0; pr.x0 = pr.y0 = pr.z0 = 0;
+    pr.unit = blockIdx.x; pr.stage = 0; pr.phase = 0; pr.it = 0; pr.n_it = 0; pr.x0 = pr.y0 = pr.z0 = 0; pr.dir = 1;
     const uint64_t pol_pv = l2_policy(P.pol_pv), pol_c = l2_policy(P.pol_c), pol_h = l2_policy(P.pol_h);
     bool pr_live = (tid == prod_tid) && (pr.unit < nunits);
     if (pr_live) iso_unit_setup<T>(pr, P);
@@ -253,9 +259,9 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
         const bool compute = pr.it >= 2 * R;
         mbar_arrive_expect_tx(fb, compute ? (T::H_BYTES + 3 * T::C_BYTES) : T::C_BYTES);
         const int cz = P.pad_z + pr.z0, cy = P.pad_y + pr.y0;
-        tma_load_3d_hint(st + T::C_OFF, &M.c, fb, cz, cy, P.pad_x + pr.x0 - R + pr.it, pol_c);
+        tma_load_3d_hint(st + T::C_OFF, &M.c, fb, cz, cy, P.pad_x + pr.x0 + pr.dir * (pr.it - R), pol_c);
         if (compute) {
-            const int xo = pr.x0 + pr.it - 2 * R;
+            const int xo = pr.x0 + pr.dir * (pr.it - 2 * R);
             tma_load_3d_hint(st + T::H_OFF, &M.h, fb, cz - T::HZ, cy - R, P.pad_x + xo, pol_h);
             tma_load_3d_hint(st + T::P_OFF, &M.p, fb, cz, cy, P.pad_x + xo, pol_pv);
             tma_load_3d_hint(st + T::V_OFF, &M.v, fb, P.vpad_z + pr.z0, P.vpad_y + pr.y0, P.vpad_x + xo, pol_pv);
@@ -293,15 +299,18 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
 
     bool sig_pending = P.sig_counter != nullptr;
     for (cu.unit = blockIdx.x; cu.unit < nunits; cu.unit += gridDim.x) {
-        if (sig_pending && cu.unit >= P.sig_units) { iso_boundary_arrive(P, lane); sig_pending = false; }
+        if (sig_pending && cu.unit >= P.sig_units) { iso_boundary_arrive(P, lane); sig_pending = false; }   // (a CTA without boundary-first units)
         iso_unit_setup<T>(cu, P);
         const int ya = cu.y0 + 2 * rp;
         const int zq = cu.z0 + 4 * quad;
         const int nz_ok = max(0, min(4, P.z_end - zq));
         const int nva = (ya < P.y_end) ? nz_ok : 0;
         const int nvb = (ya + 1 < P.y_end) ? nz_ok : 0;
-        float* out_a = P.out + (long long)ya * P.out_sy + zq + (long long)(cu.x0 - 2 * R) * P.out_sx;
+        float* out_a = P.out + (long long)ya * P.out_sy + zq + (long long)cu.x0 * P.out_sx;       // plane x0; step s -> + dir*s planes
+        const long long out_step = (long long)cu.dir * P.out_sx;
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_a) & 15) == 0);
+        // this warp's boundary planes are complete after plane R-1 of its last boundary-first unit
+        const bool sig_here = sig_pending && cu.unit < P.sig_units && cu.unit + int(gridDim.x) >= P.sig_units;
 
         // One sweep step.  B = index of the oldest live queue entry after the push (window = q[B .. B+2R]).
         auto step = [&](auto Bc, const int it) {
@@ -329,7 +338,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
                     const float4 ha = *reinterpret_cast<const float4*>(st + T::H_OFF + h_own);
                     float4 ra = make_float4(pva.x + vva.x * qa[B + R].x, pva.y + vva.y * ha.y, pva.z + vva.z, pva.w + vva.w);
                     float4 rb = make_float4(pvb.x + vvb.x * qb[B + R].x, pvb.y + vvb.y, pvb.z + vvb.z, pvb.w + vvb.w);
-                    float* oa = out_a + (long long)it * P.out_sx;
+                    float* oa = out_a + (long long)(it - 2 * R) * out_step;
                     if (vec_ok && nva == 4) stg128(oa, ra);
                     if (vec_ok && nvb == 4) stg128(oa + P.out_sy, rb);
                 }
@@ -378,14 +387,14 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
                 ra.z = iso_final<MODE>(acca[2], pa[2], pva.z, vva.z); ra.w = iso_final<MODE>(acca[3], pa[3], pva.w, vva.w);
                 rb.x = iso_final<MODE>(accb[0], pb[0], pvb.x, vvb.x); rb.y = iso_final<MODE>(accb[1], pb[1], pvb.y, vvb.y);
                 rb.z = iso_final<MODE>(accb[2], pb[2], pvb.z, vvb.z); rb.w = iso_final<MODE>(accb[3], pb[3], pvb.w, vvb.w);
-                float* oa = out_a + (long long)it * P.out_sx;
+                float* oa = out_a + (long long)(it - 2 * R) * out_step;
                 float* ob = oa + P.out_sy;
                 if (vec_ok && nva == 4) { if (P.st_cs) stg128_cs(oa, ra); else stg128(oa, ra); }
                 else if (nva > 0) { oa[0] = ra.x; if (nva > 1) oa[1] = ra.y; if (nva > 2) oa[2] = ra.z; if (nva > 3) oa[3] = ra.w; }
                 if (vec_ok && nvb == 4) { if (P.st_cs) stg128_cs(ob, rb); else stg128(ob, rb); }
                 else if (nvb > 0) { ob[0] = rb.x; if (nvb > 1) ob[1] = rb.y; if (nvb > 2) ob[2] = rb.z; if (nvb > 3) ob[3] = rb.w; }
                 // fused halo exchange: boundary planes also go straight into the x neighbours' halo cells
-                const int xo = cu.x0 + it - 2 * R;
+                const int xo = cu.x0 + cu.dir * (it - 2 * R);
                 float* peer = (P.peer_lo != nullptr && xo < R) ? P.peer_lo : ((P.peer_hi != nullptr && xo >= P.nx - R) ? P.peer_hi : nullptr);
                 if (peer != nullptr) {
                     float* qa_ = peer + (oa - P.out);
@@ -399,6 +408,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[cu.stage]);
             if (++cu.stage == T::STAGES) { cu.stage = 0; cu.phase ^= 1u; }
+            if (sig_here && it == 3 * R - 1) { iso_boundary_arrive(P, lane); sig_pending = false; }
         };
 
         if (U == 1) {

@@ -149,6 +149,7 @@ int main(int argc, char** argv) {
                       << vsteps << " step(s).\n";
             soln->end_solution();
             env->finalize();
+            if (!bad) out << "YASK DONE\n";
             return bad ? 1 : 0;
         }
 

@@ -656,11 +656,13 @@ def _sweep_streams(ir, p, ty, pf):
 
 
 def sweep_plan(ir, p):
-    """Tile shape, prefetch depth and shared-memory layout of part `p`'s sweep kernel, or None."""
-    cands = [(8, 8, 2), (4, 4, 2), (8, 8, 1), (4, 4, 1)]          # (tile rows, consumer warps, planes of prefetch)
+    """Tile shape, prefetch depth and shared-memory layout of part `p`'s sweep kernel, or None.  Always 8 consumer warps:
+    a tile of 8 rows gives every thread one 16-byte vector of points, a tile of 4 rows (rings of 8 rows do not fit) half
+    a vector -- two warps then share a tile row."""
+    cands = [(8, 8, 2), (4, 8, 2), (8, 8, 1), (4, 8, 1)]          # (tile rows, consumer warps, planes of prefetch)
     if os.environ.get("YB_EMIT_SWEEP_TY"):                          # tuning knobs: force one candidate
         ty = int(os.environ["YB_EMIT_SWEEP_TY"])
-        cands = [(ty, int(os.environ.get("YB_EMIT_SWEEP_NW", str(min(ty, 8)))), int(os.environ.get("YB_EMIT_SWEEP_PF", "2")))]
+        cands = [(ty, int(os.environ.get("YB_EMIT_SWEEP_NW", "8")), int(os.environ.get("YB_EMIT_SWEEP_PF", "2")))]
     for ty, nw, pf in cands:
         r = _sweep_streams(ir, p, ty, pf)
         if r is None:
@@ -671,9 +673,19 @@ def sweep_plan(ir, p):
         if smem > SWEEP_SMEM_LIMIT:
             continue
         eb = ir["elem_bytes"]
-        occ = 2 if smem <= SWEEP_TWO_CTA_SMEM else 1
-        return {"ty": ty, "nw": nw, "rpt": ty // nw, "pf": pf, "vw": 16 // eb, "tz": 32 * (16 // eb), "streams": streams, "bar_off": bar_off,
-                "smem": smem, "occ": occ, "threads": nw * 32 + 128,
+        vw = 16 // eb
+        tz = 32 * vw
+        nwz = max(1, nw // ty)                     # warps per tile row
+        tv = vw // nwz                             # points per thread (a 16-byte vector, or a part of one)
+        if tv < 1 or ty * nwz != nw:
+            continue
+        # One CTA per SM (8 + 4 warps, up to 168 registers per thread at launch): launch with enough dynamic shared memory
+        # that a second CTA never fits -- the consumers' setmaxnreg.inc below is sized for one resident CTA and would wait
+        # forever for registers next to a second one.
+        occ = 1
+        smem_launch = max(smem, 117 * 1024)
+        return {"ty": ty, "nw": nw, "nwz": nwz, "tv": tv, "rpt": 1, "pf": pf, "vw": vw, "tz": tz, "streams": streams, "bar_off": bar_off,
+                "smem": smem, "smem_launch": smem_launch, "occ": occ, "threads": nw * 32 + 128,
                 # consumer register budget after setmaxnreg (64 K registers per SM, producer warpgroup keeps 24 each)
                 "cregs": min(232, ((65536 // occ - 128 * 24) // (nw * 32)) // 8 * 8),
                 "bytes0": sum((s_["xr"] - s_["xl"] + 1) * s_["bytes"] for s_ in streams),
@@ -684,7 +696,7 @@ def sweep_plan(ir, p):
 def emit_sweep_kernel(ir, p, plan, ident) -> list:
     masks = _masks(ir, p)
     T = "float" if ir["elem_bytes"] == 4 else "double"
-    eb, vw, nw, rpt, pf = ir["elem_bytes"], plan["vw"], plan["nw"], plan["rpt"], plan["pf"]
+    eb, vw, nw, rpt, pf = ir["elem_bytes"], plan["tv"], plan["nw"], plan["rpt"], plan["pf"]      # vw: points per THREAD from here on
     streams = plan["streams"]
     outs = {o["access"] for o in p["outputs"]}
 
@@ -717,11 +729,11 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     guard = any(masks[a] != 7 and (a, tuple(o)) not in hoist for st in p["stmts"] for a, o in st["reads"])
     L = []
     L.append(f"// sweep kernel of part '{p['name']}' (yb_gen_sweep.cuh): {len(streams)} TMA streams over {n_str} vars, tile {plan['ty']} rows x {plan['tz']} z, "
-             f"{nw} consumer warps x {vw} points, {pf} planes of prefetch, {plan['smem']} B of shared memory, {plan['occ']} CTA(s) per SM")
+             f"{nw} consumer warps x {vw} point(s) per thread, {pf} planes of prefetch, {plan['smem']} B of shared memory, {plan['occ']} CTA(s) per SM")
     L.append("template <int MODE>")
     L.append(f"__global__ void __launch_bounds__({plan['threads']}, {plan['occ']}) {ident}_{p['name']}_sweep_kernel(const __grid_constant__ GenSweepParams SP) {{")
     L.append(f"    typedef {T} T;")
-    L.append(f"    constexpr int VW = {vw}, NW = {nw}, RPT = {rpt}, TY = {plan['ty']}, TZ = {plan['tz']}, PF = {pf}, NB = PF + 1;")
+    L.append(f"    constexpr int VW = {vw}, NW = {nw}, NWZ = {plan['nwz']}, RPT = {rpt}, TY = {plan['ty']}, TZ = {plan['tz']}, PF = {pf}, NB = PF + 1;")
     L.append("    extern __shared__ __align__(128) unsigned char sw_smem[];")
     L.append("    const GenParams& P = SP.g;")
     L.append(f"    uint64_t* full_bar = reinterpret_cast<uint64_t*>(sw_smem + {plan['bar_off']});")
@@ -756,13 +768,14 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     L.append("        return;")
     L.append("    }")
     L.append(f'    asm volatile("setmaxnreg.inc.sync.aligned.u32 {plan["cregs"]};");')
-    L.append("    // ---- consumers: warp w owns tile rows w*RPT .. w*RPT+RPT-1, lane l the z vector l ----")
-    L.append("    const int lane = int(threadIdx.x) & 31, sw_r0 = (int(threadIdx.x) >> 5) * RPT;")
-    L.append("    const int zq = z0 + lane * VW;                                    // first z of this thread's vector")
+    L.append("    // ---- consumers: NWZ warps per tile row; a thread owns VW consecutive z points of its row ----")
+    L.append("    const int lane = int(threadIdx.x) & 31, sw_w = int(threadIdx.x) >> 5, sw_r0 = (sw_w / NWZ) * RPT;")
+    L.append("    const int zt = ((sw_w % NWZ) * 32 + lane) * VW;                   // z offset of this thread's points within the tile")
+    L.append("    const int zq = z0 + zt;                                           // first z of this thread's points")
     L.append("    const int nzv = max(0, min(VW, P.ze - zq));                       // valid points of the vector")
     L.append("    const uint32_t sw_base = smem_u32(sw_smem);")
     for k, s_ in enumerate(streams):
-        L.append(f"    const uint32_t t{k} = sw_base + {s_['off']}u + uint32_t((sw_r0 * {s_['pz']} + lane * VW + {-s_['zl']}) * {eb});")
+        L.append(f"    const uint32_t t{k} = sw_base + {s_['off']}u + uint32_t((sw_r0 * {s_['pz']} + zt + {-s_['zl']}) * {eb});")
     # hoisted lower-rank reads that do not depend on x
     for (a, o) in sorted(hoist):
         m = masks[a]
@@ -783,7 +796,7 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     ns_vals = sorted({s_["ns"] for s_ in streams})
     L.append("    int fb = 0; unsigned fpar = 0;")
     L.append("    " + " ".join(f"uint32_t c{n} = 0;" for n in ns_vals) + "      // sweep iteration modulo the ring lengths")
-    L.append("    const bool vec_ok = nzv == VW && ((reinterpret_cast<uintptr_t>(static_cast<T*>(P.ptr[%d]) + zq) & 15) == 0) && (P.SY %% VW == 0) && (P.SX %% VW == 0);" % p["outputs"][0]["access"])
+    L.append("    const bool vec_ok = nzv == VW && ((reinterpret_cast<uintptr_t>(static_cast<T*>(P.ptr[%d]) + zq) & (VW * sizeof(T) - 1)) == 0) && (P.SY %% VW == 0) && (P.SX %% VW == 0);" % p["outputs"][0]["access"])
     L.append("    for (int it = 0; it < sw_len; it++) {")
     L.append("        mbar_wait(&full_bar[fb], fpar);")
     L.append("        const int x = xs + it;")
@@ -805,7 +818,7 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     for key in sorted(loads):
         k, dx, ry, j = key
         s_ = streams[k]
-        L.append(f"            T {loads[key]}[VW]; SwVec<T>::lds(b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} + uint32_t(((r + {ry}) * {s_['pz']} + ({j * vw})) * {eb}), {loads[key]});")
+        L.append(f"            T {loads[key]}[VW]; SwVec<T, VW>::lds(b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} + uint32_t(((r + {ry}) * {s_['pz']} + ({j * vw})) * {eb}), {loads[key]});")
     for o in p["outputs"]:
         L.append(f"            T o{o['access']}[VW];")
     L.append("            if (y < P.ye) {")
@@ -839,7 +852,7 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     for o in p["outputs"]:
         a = o["access"]
         L.append(f"                {{ T* dst = static_cast<T*>(P.ptr[{a}]) + (x * P.SX + y * P.SY + zq);")
-        L.append(f"                  if (vec_ok) SwVec<T>::stg(dst, o{a}); else for (int i = 0; i < nzv; i++) dst[i] = o{a}[i]; }}")
+        L.append(f"                  if (vec_ok) SwVec<T, VW>::stg(dst, o{a}); else for (int i = 0; i < nzv; i++) dst[i] = o{a}[i]; }}")
     L.append("            }")
     L.append("        }")
     L.append("        __syncwarp();")
@@ -945,7 +958,7 @@ def emit_cuda(ir: dict) -> str:
                 L.append("    {")
                 L.append("        GenSweep& sw = g.stages.back().parts.back().sweep;")
                 L.append(f"        sw.fn[{fi}][0] = GEN_SW_FN({ks}, 0); sw.fn[{fi}][1] = GEN_SW_FN({ks}, 1);")
-                L.append(f"        sw.ty = {plan['ty']}; sw.tz = {plan['tz']}; sw.threads = {plan['threads']}; sw.occ = {plan['occ']}; sw.smem = {plan['smem']};")
+                L.append(f"        sw.ty = {plan['ty']}; sw.tz = {plan['tz']}; sw.threads = {plan['threads']}; sw.occ = {plan['occ']}; sw.smem = {plan['smem_launch']};")
                 for s_ in plan["streams"]:
                     L.append("        sw.streams.push_back(GenSweepStream{%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d});" % (
                         s_["acc"], s_["xl"], s_["xr"], s_["yl"], s_["yr"], s_["zl"], s_["zr"], s_["rows"], s_["pz"], s_["slot"], s_["ns"], s_["off"]))
