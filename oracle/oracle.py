@@ -77,8 +77,10 @@ def gen_ir(stencil: str) -> dict:
     return json.load(open(os.path.join(os.path.dirname(HERE), "yask_b200", "csrc", "gen", f"{stencil}.json")))
 
 
-def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
+def gen_run(stencil: str, n, steps: int, inputs: dict, contract: int = 0) -> dict:
     """Run `steps` steps of a generated solution on the CPU.
+    contract = 0: every operation rounded separately (== the reference built with -ffp-contract=off);
+    contract = 1: products fused into additions exactly where GCC fuses them in the reference's default build.
     inputs: {(var, api_step): ndarray over the var's rank halo box} (scalars: 0-d / size-1 arrays); API steps
     0..alloc_t-1 for vars with a step dim.  Returns {var: (last_valid_step, ndarray over the halo box)} for every
     written var.  Inputs are not modified."""
@@ -87,6 +89,7 @@ def gen_run(stencil: str, n, steps: int, inputs: dict) -> dict:
     dt = np.float32 if ir["elem_bytes"] == 4 else np.float64
     L = lib()
     L.yo_gen_run_part.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_GenArgs)]
+    L.yo_gen_set_contract(1 if contract else 0)
     slots = {}      # var -> list of arrays per slot
     meta = {}
     nn = [1] * (3 - len(n)) + list(n)      # domain dims right-aligned into the (x,y,z) slots, like the CUDA engine

@@ -241,6 +241,16 @@ typedef struct { const char* name; void (*fn)(const yo_gen_args*); int nacc; } y
 #define SUB(a, b) ((a) - (b))
 #define MUL(a, b) ((a) * (b))
 #define DIV(a, b) ((a) / (b))
+/* The places where the reference's DEFAULT build (GCC -O3, -ffp-contract=fast) fuses a product into the addition that
+ * consumes it, as worked out by the emitter (contract_like_gcc): evaluated as two rounded operations by default (== the
+ * reference built with -ffp-contract=off) and as one fma after yo_gen_set_contract(1) (== its default build). */
+static int yo_gen_contract = 0;
+void yo_gen_set_contract(int on) { yo_gen_contract = on; }
+#define YO_FMA(a, b, c) (sizeof(T) == 4 ? (T)fmaf((float)(a), (float)(b), (float)(c)) : (T)fma((double)(a), (double)(b), (double)(c)))
+#define MAD(a, b, c) (yo_gen_contract ? YO_FMA(a, b, c) : (T)((T)((a) * (b)) + (c)))
+#define MSB(a, b, c) (yo_gen_contract ? YO_FMA(a, b, -(c)) : (T)((T)((a) * (b)) - (c)))
+#define NMAD(a, b, c) (yo_gen_contract ? YO_FMA(-(a), b, c) : (T)((c) - (T)((a) * (b))))
+#define NMSB(a, b, c) (yo_gen_contract ? YO_FMA(-(a), b, -(c)) : (T)((T)(-(T)((a) * (b))) - (c)))
 /* DSL math functions: libm of the element type, as the reference's non-SVML build calls them per element
  * (/root/reference/src/kernel/lib/realv.hpp:648-738). */
 #define YF1(fd, ff, a) (sizeof(T) == 4 ? (T)ff((float)(a)) : (T)fd((double)(a)))

@@ -50,20 +50,27 @@ def _domain(ir, name, arr):
 from tests.helpers import generated_golden_cases  # noqa: E402
 
 
+# Solutions whose default-build contraction is not reproduced element for element (the reference's vector code orders a few
+# products differently from its scalar listing, which the emitter reads): held to 4 field-ulps instead.
+NOT_BITEXACT_DEFAULT = {"tti", "wave2d"}
+
+
 @pytest.mark.parametrize("path", generated_golden_cases())
 def test_generated_oracle_vs_reference(path):
-    """Strict reference build: bit-exact.  Default (GCC-contracted) build: within 4 field-ulps -- GCC's FMA
-    choices for these expression trees are not restated, see DESIGN.md section 4."""
+    """Strict reference build (-ffp-contract=off): bit-exact.  Default build (GCC -O3, -ffp-contract=fast): bit-exact as
+    well, with the products fused exactly where GCC fuses them (emitter: contract_like_gcc; oracle contract=1) -- for 43 of
+    the 45 solutions; the two in NOT_BITEXACT_DEFAULT within 4 field-ulps."""
     meta, arrays = load_golden(path)
     ins = regen_inputs(meta)
-    out = O.gen_run(meta["stencil"], meta["n"], meta["steps"], ins)
+    strict = "strict" in meta["ref_tag"]
+    out = O.gen_run(meta["stencil"], meta["n"], meta["steps"], ins, contract=0 if strict else 1)
     ir = O.gen_ir(meta["stencil"])
     assert len(out) == sum(1 for v in ir["vars"] if v["is_output"])
     for name, (tl, arr) in out.items():
         ref = arrays[f"{name}.t{tl}"]
         got = _domain(ir, name, arr)
         assert got.shape == ref.shape and got.dtype == ref.dtype
-        if "strict" in meta["ref_tag"]:
+        if strict or meta["stencil"] not in NOT_BITEXACT_DEFAULT:
             it = np.uint32 if got.dtype == np.float32 else np.uint64
             assert np.array_equal(got.view(it), ref.view(it)), name
         else:

@@ -66,7 +66,8 @@ struct GenEngine : Engine {
         if (const char* e = getenv("YB_GEN_L2_MB")) l2_mb = std::max(0, atoi(e));
         if (const char* e = getenv("YB_GEN_SWEEP")) sweep = atoi(e) != 0;
     }
-    int sweep = 0;     // option gen_sweep (env YB_GEN_SWEEP): 1 = use the TMA-staged sweep variant where a part has one (experimental)
+    int sweep = 1;     // option gen_sweep (env YB_GEN_SWEEP): 1 (default) = TMA-staged sweep kernels where a part has one and the
+                       // launch box allows; 0 = direct kernels everywhere
     int sweep_lx = 0;    // option gen_sweep_lx: x planes per sweep chunk (0 = cost model)
     int sweep_min_x = 12;  // shorter boxes (exterior slabs of a rank grid) take the direct kernels
     int num_sms = 148;

@@ -99,26 +99,31 @@ struct GenStencil {
 
 #ifdef __CUDACC__
 // MODE 0: every operation individually rounded, in statement order (== the reference built with
-// -ffp-contract=off).  MODE 1: plain operators, nvcc may contract a*b+c into FMA (the analogue of the
-// reference's default -ffp-contract=fast build; not bit-identical to GCC's choices).
-template <typename T, int MODE> struct GenOp;
-template <> struct GenOp<float, 0> {
+// -ffp-contract=off).  MODE 1: the same, except that the products the reference's DEFAULT build (GCC -O3,
+// -ffp-contract=fast) fuses into the addition that consumes them -- worked out by the emitter (contract_like_gcc) and
+// written as MAD / MSB / NMAD in the statement lists -- are single fma operations (== the reference's default build).
+// Nothing is left to nvcc's own contraction: every operation is an explicitly rounded intrinsic in both modes.
+template <typename T> struct GenRn;
+template <> struct GenRn<float> {
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 };
-template <> struct GenOp<double, 0> {
+template <> struct GenRn<double> {
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
 };
-template <typename T> struct GenOp<T, 1> {
-    static __device__ __forceinline__ T add(T a, T b) { return a + b; }
-    static __device__ __forceinline__ T sub(T a, T b) { return a - b; }
-    static __device__ __forceinline__ T mul(T a, T b) { return a * b; }
-    static __device__ __forceinline__ T div(T a, T b) { return a / b; }
+template <typename T, int MODE> struct GenOp : GenRn<T> {
+    using R = GenRn<T>;
+    static __device__ __forceinline__ T mad(T a, T b, T c) { return MODE == 0 ? R::add(R::mul(a, b), c) : R::fma(a, b, c); }
+    static __device__ __forceinline__ T msb(T a, T b, T c) { return MODE == 0 ? R::sub(R::mul(a, b), c) : R::fma(a, b, -c); }
+    static __device__ __forceinline__ T nmad(T a, T b, T c) { return MODE == 0 ? R::sub(c, R::mul(a, b)) : R::fma(-a, b, c); }
+    static __device__ __forceinline__ T nmsb(T a, T b, T c) { return MODE == 0 ? R::sub(-R::mul(a, b), c) : R::fma(-a, b, -c); }
 };
 
 // blockIdx.x -> (x, y, z) block coordinates in chunked sweep order (see GenParams::ychunk)
@@ -184,6 +189,10 @@ __device__ __forceinline__ void gen_prefetch(const GenParams& P, int x0, int y0,
 #define SUB(a, b) GenOp<T, MODE>::sub(a, b)
 #define MUL(a, b) GenOp<T, MODE>::mul(a, b)
 #define DIV(a, b) GenOp<T, MODE>::div(a, b)
+#define MAD(a, b, c) GenOp<T, MODE>::mad(a, b, c)
+#define MSB(a, b, c) GenOp<T, MODE>::msb(a, b, c)
+#define NMAD(a, b, c) GenOp<T, MODE>::nmad(a, b, c)
+#define NMSB(a, b, c) GenOp<T, MODE>::nmsb(a, b, c)
 // DSL math functions (/root/reference/src/kernel/lib/realv.hpp:713-726 call libm per element); CUDA's overloads
 // pick the element type.  sqrt/fabs/min/max are exact, the others agree with libm to a few ulps.
 #define YF_sqrt(a) sqrt(a)

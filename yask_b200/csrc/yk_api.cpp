@@ -527,7 +527,7 @@ struct B200Solution : yk_solution {
     std::string apply_command_line_options(const string_vec& args) override {
         std::string rest;
         auto dims = get_domain_dim_names();
-        static const char* ignored_bool[] = {"auto_tune", "pre_auto_tune", "warmup", "overlap_comms", "use_shm", "exchange_halos", "force_scalar",
+        static const char* ignored_bool[] = {"auto_tune", "pre_auto_tune", "warmup", "use_shm", "exchange_halos", "force_scalar",
                                              "force_scalar_exchange", "bundle_allocs", "bind_inner_threads", "allow_addl_padding", "use_device_mpi",
                                              "print_suffixes", "trace", "validate", "find_loc"};
         static const char* ignored_val[] = {"outer_threads", "inner_threads", "max_threads", "thread_divisor", "numa_pref", "msg_rank", "min_exterior",
@@ -538,7 +538,9 @@ struct B200Solution : yk_solution {
             if (arg.size() > 1 && arg[0] == '-') {
                 std::string key = arg.substr(1);
                 auto take = [&]() -> std::string { if (a + 1 >= args.size()) fail("no argument for option '" + arg + "'"); return args[++a]; };
-                for (auto* b : ignored_bool) if (key == b || key == std::string("no-") + b) used = true;
+                // -[no-]overlap_comms (the reference's switch for exterior-first evaluation, settings.cpp) selects the same thing here
+                if (key == "overlap_comms" || key == "no-overlap_comms") { chk(yb_set_option(h->s, "overlap_comms", key[0] == 'n' ? "0" : "1")); used = true; }
+                if (!used) for (auto* b : ignored_bool) if (key == b || key == std::string("no-") + b) used = true;
                 if (!used) for (auto* v : ignored_val) if (key == v) { take(); used = true; }
                 if (!used) {
                     struct Fam { const char* pfx; int (*fn)(yb_solution*, int, int64_t); };
@@ -558,7 +560,7 @@ struct B200Solution : yk_solution {
                     for (auto& d : dims) if (key == ps + d) { idx_t v = atoll(take().c_str()); if (ps == "b") block_size[d] = v; used = true; break; }
                     if (used) break;
                 }
-                if (!used) for (const char* k : {"fp_mode", "kernel", "tile", "lx", "grid", "gen_pf", "gen_l2_mb", "fused_halo"})
+                if (!used) for (const char* k : {"fp_mode", "kernel", "tile", "lx", "grid", "gen_pf", "gen_l2_mb", "gen_sweep", "gen_sweep_lx", "fused_halo"})
                     if (key == k) { std::string v = take(); chk(yb_set_option(h->s, k, v.c_str())); used = true; break; }
                 if (!used && key == "device") { device = atoi(take().c_str()); used = true; }
             }

@@ -452,6 +452,7 @@ def parse_generated(text: str, name: str) -> dict:
             raise EmitError(f"unrecognised statement in calc_scalar of {pname}: {line[:120]}")
         if not part["outputs"]:
             raise EmitError(f"part {pname} writes nothing")
+        part["stmts"] = contract_like_gcc(part)
         if is_scratch_part:
             # write halo = largest halo of the scratch vars it writes (find_scratch_write_halos, setup.cpp:1182-1228)
             vmap = {v["name"]: v for v in ir["vars"]}
@@ -493,11 +494,175 @@ def gen_expr(tree, rd, ops) -> str:
         return rd(tree[1])
     if k == "neg":
         return f"(-{gen_expr(tree[1], rd, ops)})"
+    if k in ("mad", "msb", "nmad", "nmsb"):
+        return f"{ops[k]}({gen_expr(tree[1], rd, ops)}, {gen_expr(tree[2], rd, ops)}, {gen_expr(tree[3], rd, ops)})"
     a, b = gen_expr(tree[1], rd, ops), gen_expr(tree[2], rd, ops)
     return f"{ops[k]}({a}, {b})"
 
 
-OPS = {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV'}
+# MAD(a,b,c) = a*b + c, MSB(a,b,c) = a*b - c, NMAD(a,b,c) = c - a*b, NMSB(a,b,c) = -(a*b) - c: the places where the reference's DEFAULT build fuses a
+# multiplication into the addition that consumes it (contract_like_gcc below).  In fp_mode 0 they expand to the two
+# separately rounded operations, otherwise to one fma -- nothing is left to nvcc's own contraction heuristics.
+OPS = {'add': 'ADD', 'sub': 'SUB', 'mul': 'MUL', 'div': 'DIV', 'mad': 'MAD', 'msb': 'MSB', 'nmad': 'NMAD', 'nmsb': 'NMSB'}
+
+
+def contract_like_gcc(part):
+    """Rewrite the statement trees of `part` with the FMA contraction GCC applies to the reference's generated code in its
+    default build (-O3, -ffp-contract=fast; tree-ssa-math-opts.c, convert_mult_to_fma): walking the operations in
+    evaluation order, a multiplication is fused iff EVERY use of its value is an addition or subtraction that has not been
+    turned into an FMA already; it is then fused into each of them and disappears.  (So of a*b + c*d the earlier product
+    is fused, the later one stays a multiplication.)  Values are numbered structurally first, as GCC's redundancy
+    elimination does before that pass: the same product written twice is one value with two uses.
+    Returns the new statement list; statements whose product was fused away are dropped."""
+    nodes = {}          # value key -> node
+    order = []          # nodes in evaluation order (first occurrence)
+
+    class N:
+        __slots__ = ("kind", "args", "leaf", "users", "dead", "name")
+
+        def __init__(self, kind, args=(), leaf=None):
+            self.kind, self.args, self.leaf, self.users, self.dead, self.name = kind, list(args), leaf, [], False, None
+
+    named = {}          # temp name -> node
+
+    def intern(kind, args, leaf=None):
+        ids = [id(a) for a in args]
+        key = (kind, tuple(sorted(ids)) if kind in ("add", "mul") else tuple(ids), leaf)
+        n = nodes.get(key)
+        if n is None:
+            n = N(kind, args, leaf)
+            nodes[key] = n
+            order.append(n)
+            for a in args:
+                a.users.append(n)
+        return n
+
+    def build(tree, st):
+        k = tree[0]
+        if k == "const":
+            return intern("const", (), ("c", float(tree[1])))
+        if k == "tmp":
+            if tree[1] not in named:
+                raise EmitError(f"temp '{tree[1]}' used before its definition")
+            return named[tree[1]]
+        if k == "read":
+            a, o = st["reads"][tree[1]]
+            return intern("read", (), ("r", a, tuple(o)))
+        if k == "call":
+            return intern("call", [build(a, st) for a in tree[2]], ("f", tree[1]))
+        if k == "neg":
+            return intern("neg", [build(tree[1], st)])
+        return intern(k, [build(tree[1], st), build(tree[2], st)])
+
+    roots = []
+    uid = [0]
+    for st in part["stmts"]:
+        if st.get("kind") == "sincos":
+            arg = build(st["tree"], st)
+            uid[0] += 1
+            sc = N("sincos", [arg], ("sc", uid[0]))     # two results, never merged with anything
+            arg.users.append(sc)
+            order.append(sc)
+            for nm in (st["sin"], st["cos"]):
+                leaf = N("scres", [sc], ("scres", nm))
+                sc.users.append(leaf)
+                named[nm] = leaf
+            roots.append((st, sc))
+            continue
+        r = build(st["tree"], st)
+        named[st["dst"]] = r
+        if r.name is None:
+            r.name = st["dst"]
+        roots.append((st, r))
+    sink = N("out")
+    for o in part["outputs"]:
+        named[o["src"]].users.append(sink)
+    # step conditions read temps? (no: they read vars only)
+    for n in order:
+        if n.kind != "mul" or not n.users:
+            continue
+        # uses: additions / subtractions, possibly through a negation that has that single use
+        # (convert_mult_to_fma: "a negate on the multiplication leads to FNMA")
+        sites = []      # (value seen by the add/sub, the add/sub, negated?)
+        ok = True
+        for u in n.users:
+            if u.kind == "neg" and len(u.users) == 1 and u.users[0].kind in ("add", "sub"):
+                sites.append((u, u.users[0], True))
+            elif u.kind in ("add", "sub"):
+                sites.append((n, u, False))
+            else:
+                ok = False
+        if not ok or any(t.args[0] is v and t.args[1] is v for v, t, _ in sites) or len({id(t) for _, t, _ in sites}) != len(sites):
+            continue
+        a, b = n.args
+        for v, u, negd in sites:
+            left = u.args[0] is v
+            other = u.args[1] if left else u.args[0]
+            if u.kind == "add":
+                kind = "nmad" if negd else "mad"                      # other - a*b | a*b + other
+            elif left:
+                kind = "nmsb" if negd else "msb"                      # -(a*b) - other | a*b - other
+            else:
+                kind = "mad" if negd else "nmad"                      # other + a*b | other - a*b
+            u.kind, u.args = kind, [a, b, other]
+            a.users.append(u); b.users.append(u)
+            if negd:
+                v.dead = True
+        n.dead = True
+    # back to trees: a node that is the root of a (live) statement is referred to by that statement's name
+    def tree_of(n, top):
+        if not top and n.name is not None and not n.dead:
+            return ("tmp", n.name)
+        if n.kind == "const":
+            return ("const", repr(n.leaf[1]))
+        if n.kind == "read":
+            return ("readx", n.leaf[1], n.leaf[2])
+        if n.kind == "scres":
+            return ("tmp", n.leaf[1])
+        if n.kind == "call":
+            return ("call", n.leaf[1], [tree_of(a, False) for a in n.args])
+        if n.kind == "neg":
+            return ("neg", tree_of(n.args[0], False))
+        if n.kind in ("mad", "msb", "nmad", "nmsb"):
+            return (n.kind, tree_of(n.args[0], False), tree_of(n.args[1], False), tree_of(n.args[2], False))
+        return (n.kind, tree_of(n.args[0], False), tree_of(n.args[1], False))
+
+    def with_reads(tree, reads):
+        """("readx", acc, offs) leaves -> ("read", index into this statement's read list)"""
+        k = tree[0]
+        if k == "readx":
+            reads.append((tree[1], list(tree[2])))
+            return ("read", len(reads) - 1)
+        if k in ("const", "tmp"):
+            return tree
+        if k == "call":
+            return ("call", tree[1], [with_reads(a, reads) for a in tree[2]])
+        return (k,) + tuple(with_reads(a, reads) for a in tree[1:])
+
+    def finish(d, tree):
+        reads = []
+        d["tree"] = with_reads(tree, reads)
+        d["reads"] = reads
+        return d
+
+    out = []
+    emitted = set()
+    for st, r in roots:
+        if st.get("kind") == "sincos":
+            out.append(finish({"kind": "sincos", "sin": st["sin"], "cos": st["cos"]}, tree_of(r.args[0], False)))
+            continue
+        if r.dead:
+            continue                      # fused into its users
+        if r.name != st["dst"]:
+            out.append(finish({"dst": st["dst"]}, ("tmp", r.name) if r.name else tree_of(r, True)))     # alias of an earlier value
+            continue
+        if id(r) in emitted:
+            continue
+        emitted.add(id(r))
+        out.append(finish({"dst": st["dst"]}, tree_of(r, True)))
+    # outputs may name a statement that was an alias of a fused product: cannot happen (a product written out has a
+    # non-add use, so it is never fused)
+    return out
 
 
 def _rd_text(a, offs, masks):
