@@ -269,3 +269,48 @@ def test_fuse_vars_shares_storage_between_solutions():
     assert np.array_equal(pa.get_elements_in_slice(*pa.domain_box(tl % 2)).view(np.uint32), ref.view(np.uint32))
     a.close()
     c.close()
+
+
+def test_var_checks_of_the_reference_var_test():
+    """What the reference's src/kernel/tests/var_test.cpp checks, through the public API (that file itself includes the
+    reference's internal headers and cannot be built against any public API): two scalar vars hold the same value after
+    set_element; two padded 3-D vars exchange a sequence of values element by element and by slice
+    (host buffer), over the whole allocation including the pads, and read back identically."""
+    import ctypes as C
+    L = capi.lib()
+    s = capi.Solution("iso3dfd")
+    s.set_rank_domain_size_vec((3, 5, 7))                    # var_test.cpp: 3 + 2*i points per dim
+    a0, a1 = s.new_var("var1", []), s.new_var("var2", [])
+    a3, b3 = s.new_var("var3", ["x", "y", "z"]), s.new_var("var4", ["x", "y", "z"])
+    for d in range(3):                                       # min pad 1, 2, 3 as in var_test.cpp (the engine rounds z up to a 128-B line)
+        for v in (a3, b3):
+            capi._chk(L.yb_var_set_min_pad(s._h, v.index, d, 1 + d, 1 + d))
+    s.prepare_solution(0)
+    # 0-D
+    for v in (a0, a1):
+        v.set_elements_in_slice(np.array([3.14], np.float32), [], [])
+    assert a0.get_elements_in_slice([], []).ravel()[0] == a1.get_elements_in_slice([], []).ravel()[0] == np.float32(3.14)
+    # 3-D: a sequence of values over the first var's whole allocation
+    ia, ib = a3.info, b3.info
+    first = [ia.dims[k].rank_offset - ia.dims[k].left_pad for k in range(3)]
+    last = [ia.dims[k].rank_offset + ia.dims[k].domain_size + ia.dims[k].right_pad - 1 for k in range(3)]
+    shape = [l - f + 1 for f, l in zip(first, last)]
+    seq = (1.0 + np.arange(int(np.prod(shape)), dtype=np.float32)).reshape(shape)
+    a3.set_elements_in_slice(seq, first, last)
+    # the box both vars hold: the second var's allocation is at least its pads 1,2,3 around the domain
+    f2 = [max(first[k], ib.dims[k].rank_offset - ib.dims[k].left_pad) for k in range(3)]
+    l2 = [min(last[k], ib.dims[k].rank_offset + ib.dims[k].domain_size + ib.dims[k].right_pad - 1) for k in range(3)]
+    assert all(f2[k] <= -1 - k and l2[k] >= ib.dims[k].domain_size + k for k in range(3))
+    # by slice
+    b3.set_all_elements_same(-1.0)
+    buf = a3.get_elements_in_slice(f2, l2)
+    b3.set_elements_in_slice(buf, f2, l2)
+    assert np.array_equal(b3.get_elements_in_slice(f2, l2), seq[tuple(slice(f2[k] - first[k], l2[k] - first[k] + 1) for k in range(3))])
+    # element by element (a diagonal of points incl. pad cells)
+    b3.set_all_elements_same(-1.0)
+    for i in range(-1, 3):
+        pt = [i, i, i]
+        val = a3.get_elements_in_slice(pt, pt)
+        b3.set_elements_in_slice(val, pt, pt)
+        assert b3.get_elements_in_slice(pt, pt).ravel()[0] == seq[tuple(pt[k] - first[k] for k in range(3))]
+    s.close()
