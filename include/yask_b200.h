@@ -170,6 +170,13 @@ int yb_var_get_slice_device(yb_solution* s, int var, void* dev_buf, const int64_
  * domain right now (no halo exchange; var contents are NOT preserved), keeps the fastest for later run_solution()
  * calls, clears the stats.  `report` (may be NULL) receives one line per trial. */
 int yb_solution_auto_tune(yb_solution* s, char* report, size_t report_len);
+/* In-run tuner (yk_solution::reset_auto_tuner, is_auto_tuner_enabled, option -auto_tune; aux/yk_solution_api.hpp:820-856):
+ * while enabled, every run_solution() step executes with the next untried launch variant and is timed; when all variants
+ * have their samples the fastest stays selected and the tuner switches itself off.  Variants compute identical bits, so the
+ * steps taken while tuning are real steps. */
+int yb_solution_reset_auto_tuner(yb_solution* s, int enable);
+int yb_solution_is_auto_tuner_enabled(const yb_solution* s);
+int yb_solution_auto_tuner_report(const yb_solution* s, char* report, size_t report_len);
 /* Reductions over a slice, on the device, accumulated in double in a fixed order: yk_var::reduce_elements_in_slice
  * (aux/yk_var_api.hpp:984-1110; /root/reference/src/kernel/lib/yk_var.hpp:1367-1450).
  * out = {sum, sum of squares, product, max, min}; *n_done = number of elements reduced (may be NULL). */

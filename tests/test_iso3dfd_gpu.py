@@ -314,3 +314,25 @@ def test_var_checks_of_the_reference_var_test():
         b3.set_elements_in_slice(val, pt, pt)
         assert b3.get_elements_in_slice(pt, pt).ravel()[0] == seq[tuple(pt[k] - first[k] for k in range(3))]
     s.close()
+
+
+def test_in_run_auto_tuner_keeps_results_exact():
+    """yk_solution::reset_auto_tuner(true) / -auto_tune: while enabled every run_solution() step runs with the next launch
+    variant and is timed; the steps are REAL steps (all variants compute the same bits), so a run that tunes on the way is
+    still bit-exact vs the oracle; afterwards the tuner is off and a variant is selected."""
+    n, seed = (64, 48, 160), 3
+    ins = synth_inputs(n, seed)
+    _, s = run_gpu(n, 0, ins, ret_soln=True)
+    s.reset_auto_tuner(True)
+    assert s.is_auto_tuner_enabled()
+    steps = 18 * 3 + 4          # 18 variants x (1 cold + 2 timed) samples, then a few steps with the winner
+    s.run_solution(0, steps - 1)
+    assert not s.is_auto_tuner_enabled()
+    rep = s.auto_tuner_report()
+    assert rep.count("ms/step") == 18 and "<- best" in rep, rep
+    p = s.get_var("p")
+    tl = p.get_last_valid_step_index()
+    got = p.get_elements_in_slice(*p.domain_box(tl))
+    s.close()
+    ref = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], 8, steps, 2)[8:-8, 8:-8, 8:-8]
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))

@@ -59,7 +59,7 @@ ABI_SYMBOLS = [
     "yb_get_first_rank_domain_index", "yb_get_last_rank_domain_index", "yb_set_option", "yb_get_option", "yb_set_stream",
     "yb_solution_plan_geometry", "yb_solution_prepare", "yb_solution_is_prepared", "yb_num_vars", "yb_var_index", "yb_var_info_get", "yb_var_create", "yb_var_fuse", "yb_var_set_min_pad",
     "yb_var_set_slice", "yb_var_get_slice", "yb_var_set_slice_device", "yb_var_get_slice_device", "yb_var_set_all_same",
-    "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_var_fill_hash", "yb_var_fill_hash_shifted", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
+    "yb_var_set_slice_same", "yb_var_reduce_slice", "yb_solution_auto_tune", "yb_solution_reset_auto_tuner", "yb_solution_is_auto_tuner_enabled", "yb_solution_auto_tuner_report", "yb_var_fill_hash", "yb_var_fill_hash_shifted", "yb_var_checksum", "yb_var_device_ptr", "yb_copy_to_host", "yb_solution_run", "yb_solution_sync",
     "yb_get_stats", "yb_clear_stats", "yb_halo_export_size", "yb_halo_export", "yb_halo_import", "yb_halo_finalize",
     "yb_exchange_halos", "yb_comm_env_rank", "yb_comm_env_world", "yb_comm_env_local_rank", "yb_comm_init", "yb_comm_rank", "yb_comm_world",
     "yb_comm_barrier", "yb_comm_allgather", "yb_comm_sum_i64", "yb_comm_max_f64", "yb_comm_finalize", "yb_halo_connect",
@@ -99,6 +99,9 @@ def lib() -> C.CDLL:
         L.yb_set_option.argtypes = [p, C.c_char_p, C.c_char_p]
         L.yb_get_option.argtypes = [p, C.c_char_p, C.c_char_p, C.c_size_t]
         L.yb_solution_auto_tune.argtypes = [p, C.c_char_p, C.c_size_t]
+        L.yb_solution_reset_auto_tuner.argtypes = [p, i32]
+        L.yb_solution_is_auto_tuner_enabled.argtypes = [p]
+        L.yb_solution_auto_tuner_report.argtypes = [p, C.c_char_p, C.c_size_t]
         L.yb_set_stream.argtypes = [p, p]
         L.yb_solution_plan_geometry.argtypes = [p]
         L.yb_solution_prepare.argtypes = [p, i32]
@@ -333,6 +336,17 @@ class Solution:
         """Offline auto-tuner: times the engine's launch variants, keeps the fastest; var contents are not preserved."""
         buf = C.create_string_buffer(8192)
         _chk(lib().yb_solution_auto_tune(self._h, buf, 8192))
+        return buf.value.decode()
+
+    def reset_auto_tuner(self, enable: bool = True):
+        _chk(lib().yb_solution_reset_auto_tuner(self._h, 1 if enable else 0))
+
+    def is_auto_tuner_enabled(self) -> bool:
+        return bool(lib().yb_solution_is_auto_tuner_enabled(self._h))
+
+    def auto_tuner_report(self) -> str:
+        buf = C.create_string_buffer(8192)
+        _chk(lib().yb_solution_auto_tuner_report(self._h, buf, 8192))
         return buf.value.decode()
 
     def get_option(self, key: str) -> str:

@@ -377,6 +377,9 @@ int yb_set_option(yb_solution* s_, const char* key, const char* value) {
         int m = atoi(value);
         if (m < 0 || m > 2) return set_error(YB_EINVAL, "fp_mode must be 0, 1 or 2");
         s->fp_mode = m;
+    } else if (k == "auto_tune") {
+        s->tuner = Solution::InRunTuner();
+        s->tuner.enabled = atoi(value) != 0;
     } else if (k == "overlap_comms" || k == "min_exterior" || k == "fused_halo") {
         // consumed by the halo engine at run time
     } else if (s->engine->set_option(*s, k, v) != 0) {
@@ -800,6 +803,20 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
     // direction from the order of the arguments, as the reference does (context.cpp:237-246)
     const int64_t step_dir = last_step >= first_step ? 1 : -1;
     for (int64_t t = first_step; t != last_step + step_dir && rc >= 0; t += step_dir) {
+        // in-run auto-tuner (/root/reference/src/kernel/lib/auto_tuner.cpp, context.cpp:592-600): this step runs with the next
+        // untried launch variant and is timed on its own; once every variant has its samples the fastest stays selected
+        cudaEvent_t te0 = nullptr, te1 = nullptr;
+        int tv = -1;
+        if (s->tuner.enabled) {
+            const int nv = s->engine->tune_variants(*s);
+            if (nv <= 1) s->tuner.enabled = false;
+            else {
+                if (int(s->tuner.ms.size()) != nv) { s->tuner.ms.assign(nv, 1e30); s->tuner.tries.assign(nv, 0); s->tuner.next = 0; s->tuner.report.clear(); }
+                tv = s->tuner.next;
+                s->engine->tune_select(*s, tv);
+                if (cudaEventCreate(&te0) == cudaSuccess && cudaEventCreate(&te1) == cudaSuccess) cudaEventRecord(te0, st);
+            }
+        }
         for (size_t sg = 0; sg < s->spec.stages.size() && rc >= 0; sg++) {
             if (s->halo) {
                 rc = halo_run_stage(*s, int(sg), t, st);
@@ -814,6 +831,28 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
             for (int vi : sp.outputs) s->vars[vi].update_valid_step(t + sp.out_step_off);
         }
         s->stats.num_steps_done++;
+        if (tv >= 0 && te0 && te1) {
+            cudaEventRecord(te1, st);
+            float ms = 0;
+            if (cudaEventSynchronize(te1) == cudaSuccess && cudaEventElapsedTime(&ms, te0, te1) == cudaSuccess) {
+                auto& tu = s->tuner;
+                tu.ms[tv] = std::min(tu.ms[tv], double(ms));
+                if (++tu.tries[tv] >= tu.reps + 1) tu.next++;        // the first sample of a variant includes its cold start
+                if (tu.next >= int(tu.ms.size())) {
+                    int best = 0;
+                    for (size_t i = 1; i < tu.ms.size(); i++) if (tu.ms[i] < tu.ms[best]) best = int(i);
+                    char line[200];
+                    for (size_t i = 0; i < tu.ms.size(); i++) {
+                        snprintf(line, sizeof line, " %s: %.4f ms/step%s\n", s->engine->tune_describe(*s, int(i)).c_str(), tu.ms[i], int(i) == best ? "  <- best" : "");
+                        tu.report += line;
+                    }
+                    s->engine->tune_select(*s, best);
+                    tu.enabled = false;
+                }
+            }
+        }
+        if (te0) cudaEventDestroy(te0);
+        if (te1) cudaEventDestroy(te1);
     }
     if (s->halo && rc >= 0) rc = halo_finish(*s, st);   // the last exchange completes inside the run (and its timing)
     YB_CUDA(cudaEventRecord(e1, st));
@@ -864,6 +903,22 @@ int yb_solution_auto_tune(yb_solution* s_, char* report, size_t n) {
     YB_CUDA(cudaStreamSynchronize(s->stream()));
     if (report && n) snprintf(report, n, "%s", rep.c_str());
     return yb_clear_stats(s_);      // the reference clears the stats when the tuner is done (yk_solution_api.hpp:872)
+}
+
+// yk_solution::reset_auto_tuner / is_auto_tuner_enabled (aux/yk_solution_api.hpp:820-856): (re)start or stop the in-run tuner
+int yb_solution_reset_auto_tuner(yb_solution* s_, int enable) {
+    Solution* s = SOL(s_);
+    if (!s) return set_error(YB_EINVAL, "null solution");
+    s->tuner = Solution::InRunTuner();
+    s->tuner.enabled = enable != 0;
+    return 0;
+}
+int yb_solution_is_auto_tuner_enabled(const yb_solution* s) { return s && CSOL(s)->tuner.enabled; }
+int yb_solution_auto_tuner_report(const yb_solution* s_, char* report, size_t n) {
+    const Solution* s = CSOL(s_);
+    if (!s || !report || !n) return set_error(YB_EINVAL, "null argument");
+    snprintf(report, n, "%s", s->tuner.report.c_str());
+    return 0;
 }
 
 int yb_clear_stats(yb_solution* s_) {

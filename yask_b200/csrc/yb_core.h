@@ -133,6 +133,11 @@ struct Engine {
     // `stream`, keep the fastest, describe the trials in `report`.  Var contents are not preserved.  Default: nothing to tune.
     virtual int auto_tune(Solution&, cudaStream_t, std::string& report) { report = "nothing to tune"; return 0; }
     virtual bool get_option(const Solution&, const std::string&, std::string&) const { return false; }
+    // In-run auto-tuner (yk_solution::reset_auto_tuner / -auto_tune): the launch variants the run loop may cycle through
+    // while it executes REAL steps -- every variant computes identical bits, so tuning on live data is safe.
+    virtual int tune_variants(const Solution&) const { return 0; }
+    virtual void tune_select(Solution&, int /*variant*/) {}
+    virtual std::string tune_describe(const Solution&, int /*variant*/) const { return ""; }
     // May stage `stage` be evaluated as several sub-box launches (exterior slabs first, interior last)?  False when the
     // result of a launch depends on what an earlier launch of the same stage wrote (scratch vars computed from vars the
     // stage updates in place).
@@ -164,6 +169,14 @@ struct Solution {
     cudaStream_t own_stream = nullptr, user_stream = nullptr, comm_stream = nullptr;
     bool use_user_stream = false;
     cudaStream_t stream() const { return use_user_stream ? user_stream : own_stream; }
+    // in-run auto-tuner: steps cycle through the engine's variants (reps timed steps each), the fastest is kept
+    struct InRunTuner {
+        bool enabled = false;
+        int next = 0, reps = 2;
+        std::vector<double> ms;        // best time seen per variant
+        std::vector<int> tries;
+        std::string report;
+    } tuner;
     // stats
     yb_stats stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;  // per run() call

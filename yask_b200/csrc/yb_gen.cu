@@ -118,6 +118,19 @@ struct GenEngine : Engine {
         }
         return 0;
     }
+    // In-run tuner: sweep kernels with the cost-model chunking or fixed chunk lengths, and the direct kernels.
+    int tune_variants(const Solution&) const override { return 4; }
+    void tune_select(Solution& s, int v) override {
+        sweep = v < 3 ? 1 : 0;
+        sweep_lx = v == 1 ? 64 : (v == 2 ? 128 : 0);
+        s.options["gen_sweep"] = std::to_string(sweep);
+        s.options["gen_sweep_lx"] = std::to_string(sweep_lx);
+    }
+    std::string tune_describe(const Solution&, int v) const override {
+        static const char* d[4] = {"gen_sweep=1 gen_sweep_lx=0 (cost model)", "gen_sweep=1 gen_sweep_lx=64", "gen_sweep=1 gen_sweep_lx=128", "gen_sweep=0 (direct kernels)"};
+        return d[v];
+    }
+
     // Offline tuner: L2 prefetch distance x sweep-chunk budget, timed over one full step of the rank box.
     int auto_tune(Solution& s, cudaStream_t st, std::string& report) override {
         Box whole;

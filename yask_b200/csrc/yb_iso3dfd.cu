@@ -393,6 +393,22 @@ struct IsoEngine : Engine {
         return 1;
     }
 
+    // In-run tuner: the same variants as the offline tuner, one per step of a live run.
+    static constexpr int TUNE_TILES[6] = {7, 6, 5, 4, 1, 0};
+    static constexpr int TUNE_LXS[3] = {0, 256, 512};
+    int tune_variants(const Solution&) const override { return (maps_ok && radius == 8 && kernel != "direct") ? 18 : 0; }
+    void tune_select(Solution& s, int v) override {
+        tile = TUNE_TILES[v / 3]; lx = TUNE_LXS[v % 3];
+        s.options["tile"] = std::to_string(tile);
+        s.options["lx"] = std::to_string(lx);
+        preload_kernel((const void*)tile_cfg(tile).fn[s.fp_mode]);
+    }
+    std::string tune_describe(const Solution&, int v) const override {
+        char b[160];
+        snprintf(b, sizeof b, "tile=%d (%s) lx=%d", TUNE_TILES[v / 3], tile_cfg(TUNE_TILES[v / 3]).name, TUNE_LXS[v % 3]);
+        return b;
+    }
+
     // Offline tuner: the compiled sweep variants (tile shape, producer warpgroup, planes per trip) x sweep chunk
     // lengths, timed over the whole rank box; the analogue of the reference's block-size search
     // (/root/reference/src/kernel/lib/auto_tuner.cpp) for the knobs this engine has.

@@ -527,7 +527,7 @@ struct B200Solution : yk_solution {
     std::string apply_command_line_options(const string_vec& args) override {
         std::string rest;
         auto dims = get_domain_dim_names();
-        static const char* ignored_bool[] = {"auto_tune", "pre_auto_tune", "warmup", "use_shm", "exchange_halos", "force_scalar",
+        static const char* ignored_bool[] = {"pre_auto_tune", "warmup", "use_shm", "exchange_halos", "force_scalar",
                                              "force_scalar_exchange", "bundle_allocs", "bind_inner_threads", "allow_addl_padding", "use_device_mpi",
                                              "print_suffixes", "trace", "validate", "find_loc"};
         static const char* ignored_val[] = {"outer_threads", "inner_threads", "max_threads", "thread_divisor", "numa_pref", "msg_rank", "min_exterior",
@@ -539,6 +539,7 @@ struct B200Solution : yk_solution {
                 std::string key = arg.substr(1);
                 auto take = [&]() -> std::string { if (a + 1 >= args.size()) fail("no argument for option '" + arg + "'"); return args[++a]; };
                 // -[no-]overlap_comms (the reference's switch for exterior-first evaluation, settings.cpp) selects the same thing here
+                if (key == "auto_tune" || key == "no-auto_tune") { chk(yb_solution_reset_auto_tuner(h->s, key[0] == 'n' ? 0 : 1)); used = true; }
                 if (key == "overlap_comms" || key == "no-overlap_comms") { chk(yb_set_option(h->s, "overlap_comms", key[0] == 'n' ? "0" : "1")); used = true; }
                 if (!used) for (auto* b : ignored_bool) if (key == b || key == std::string("no-") + b) used = true;
                 if (!used) for (auto* v : ignored_val) if (key == v) { take(); used = true; }
@@ -657,8 +658,9 @@ struct B200Solution : yk_solution {
         return st;
     }
     void clear_stats() override { chk(yb_clear_stats(h->s)); }
-    void reset_auto_tuner(bool, bool) override {}    // no CPU block sizes to tune
-    bool is_auto_tuner_enabled() const override { return false; }
+    // in-run tuner over the engine's launch variants (the reference tunes CPU block sizes the same way, auto_tuner.cpp)
+    void reset_auto_tuner(bool enable, bool) override { chk(yb_solution_reset_auto_tuner(h->s, enable ? 1 : 0)); }
+    bool is_auto_tuner_enabled() const override { return yb_solution_is_auto_tuner_enabled(h->s) != 0; }
     void run_auto_tuner_now(bool verbose) override {
         // auto_tuner.cpp raises when called before prepare_solution().  What is tuned here are the engine's launch
         // variants (sweep tile / chunk length, prefetch distance, L2 chunking), not CPU block sizes.
