@@ -212,6 +212,7 @@ struct IsoEngine : Engine {
     // (streamed once), results leave with streaming stores: -0.4 GB of DRAM reads per 1024^3 launch, +0.7 % (same-box A/B)
     int pol_c = 2, pol_h = 2, pol_pv = 1, st_cs = 1;
     bool mem_probe = false;      // debug: fp_mode=3 style memory-only kernel
+    int peer_probe = 0;          // debug: see IsoParams::peer_probe
     IsoMaps maps[NTILES][2];       // [tile][cur slot]
     bool maps_ok = false;
 
@@ -227,6 +228,7 @@ struct IsoEngine : Engine {
         else if (k == "lx") { lx = std::max(0, atoi(v.c_str())); }
         else if (k == "grid") { grid_override = std::max(0, atoi(v.c_str())); }
         else if (k == "mem_probe") { mem_probe = atoi(v.c_str()) != 0; }
+        else if (k == "peer_probe") { peer_probe = atoi(v.c_str()); }
         else if (k == "pol_c") { pol_c = atoi(v.c_str()); }
         else if (k == "pol_h") { pol_h = atoi(v.c_str()); }
         else if (k == "pol_pv") { pol_pv = atoi(v.c_str()); }
@@ -291,7 +293,7 @@ struct IsoEngine : Engine {
         P.z_begin = int(box.b[2]); P.z_end = int(box.e[2]);
         P.pad_x = int(px->pad_l); P.pad_y = int(py->pad_l); P.pad_z = int(pz->pad_l);
         P.vpad_x = int(vx->pad_l); P.vpad_y = int(vy->pad_l); P.vpad_z = int(vz->pad_l);
-        P.pol_c = pol_c; P.pol_h = pol_h; P.pol_pv = pol_pv; P.st_cs = st_cs;
+        P.pol_c = pol_c; P.pol_h = pol_h; P.pol_pv = pol_pv; P.st_cs = st_cs; P.peer_probe = peer_probe;
         for (int r = 0; r <= ISO_MAX_R; r++) P.c[r] = r <= radius ? float(coef[r]) : 0.f;
     }
 

@@ -42,6 +42,8 @@ struct IsoParams {
     int cx0[ISO_MAX_CHUNKS], clen[ISO_MAX_CHUNKS], cdir[ISO_MAX_CHUNKS];
     int pol_c, pol_h, pol_pv;   // L2 eviction policy of the TMA streams: 0 normal, 1 evict_first, 2 evict_last
     int st_cs;                  // 1: results leave with streaming (evict-first) stores
+    int peer_probe;             // DEBUG (option peer_probe): 1 = skip the peer stores (timing probe only: halos are NOT exchanged),
+                                // 2 = CTAs start a few microseconds apart so that their boundary phases do not coincide
     // Fused halo exchange: when non-null, the first / last R computed x planes are ALSO stored into the lower /
     // upper x neighbour's halo cells (peer HBM over NVLink), indexed exactly like `out`.
     float* peer_lo;
@@ -285,6 +287,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
         for (int k = 0; k < T::STAGES - 1 && pr_live; k++) produce_one();
     }
 
+    if (P.peer_probe == 2) __nanosleep((blockIdx.x & 7u) * 2000u);
     // ---- consumer ------------------------------------------------------------------------------------
     const int rp = tid / T::TZQ;           // row pair 0..TYP-1  (rows 2rp, 2rp+1)
     const int quad = tid % T::TZQ;
@@ -396,7 +399,7 @@ iso3dfd_tma2_kernel(const __grid_constant__ IsoMaps M, const __grid_constant__ I
                 // fused halo exchange: boundary planes also go straight into the x neighbours' halo cells
                 const int xo = cu.x0 + cu.dir * (it - 2 * R);
                 float* peer = (P.peer_lo != nullptr && xo < R) ? P.peer_lo : ((P.peer_hi != nullptr && xo >= P.nx - R) ? P.peer_hi : nullptr);
-                if (peer != nullptr) {
+                if (peer != nullptr && P.peer_probe != 1) {
                     float* qa_ = peer + (oa - P.out);
                     float* qb_ = qa_ + P.out_sy;
                     if (vec_ok && nva == 4) stg128(qa_, ra);
