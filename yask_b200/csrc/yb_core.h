@@ -197,6 +197,10 @@ struct Solution {
         void* lo = nullptr; void* hi = nullptr; int var = -1; bool used = false;
         unsigned long long* flag_lo = nullptr; unsigned long long* flag_hi = nullptr;
         unsigned long long epoch = 0; unsigned int* counter = nullptr; bool signalled = false;
+        // dma: the engine only ORDERS its work (boundary planes first) and publishes `epoch` into flag_lo -- a word in LOCAL
+        // memory -- when they are stored; the halo layer's side stream waits on that word and moves the planes with the copy
+        // engines (yb_halo.cu).  lo / hi then merely say on which sides there is a neighbour.
+        bool dma = false;
     } fused_x;
     int multi_rank() const { return int(num_ranks[0] * num_ranks[1] * num_ranks[2]) > 1; }
     ~Solution();

@@ -21,6 +21,8 @@
 
 #include <algorithm>
 
+#include <cuda.h>
+
 #include "yb_halo.h"
 
 namespace yb {
@@ -120,6 +122,23 @@ __global__ void halo_wait_kernel(const unsigned long long* flags, unsigned int d
     }
 }
 
+// cuStreamWaitValue64 (stream memory operation): lets the side stream wait for a word the sweep kernel writes while it is
+// still running.  Fetched from the driver at run time, like cuTensorMapEncodeTiled.
+typedef CUresult (*StreamWaitValue64Fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+StreamWaitValue64Fn stream_wait_value64() {
+    static StreamWaitValue64Fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<StreamWaitValue64Fn>(p);
+        (void)cudaGetLastError();
+    }
+    return fn;
+}
+
 struct Neighbor {
     int dir[3];
     int64_t peer_linear = -1;
@@ -143,6 +162,9 @@ struct HaloState {
     bool wait_pending = false;              // the neighbours' epoch `epoch` has not been waited for yet
     unsigned int wait_mask = 0;
     unsigned int* sig_counter = nullptr;    // device word: arrivals of the in-kernel boundary signal (yb_iso3dfd.cuh)
+    unsigned long long* local_done = nullptr;   // device word: epoch whose boundary planes are stored (copy-engine path)
+    cudaEvent_t comm_ev = nullptr;          // last work enqueued on the side stream
+    bool comm_pending = false;
 };
 
 void halo_free(HaloState* h) {
@@ -152,6 +174,7 @@ void halo_free(HaloState* h) {
             for (void* p : nb.opened) cudaIpcCloseMemHandle(p);
     if (h->flags) cudaFree(h->flags);
     if (h->sig_counter) cudaFree(h->sig_counter);
+    if (h->comm_ev) cudaEventDestroy(h->comm_ev);
     delete h;
 }
 
@@ -172,6 +195,8 @@ int halo_prepare(Solution& s) {
     YB_CUDA(cudaMemset(h->flags, 0, NDIRS * sizeof(unsigned long long)));
     YB_CUDA(cudaMalloc(&h->sig_counter, 256));
     YB_CUDA(cudaMemset(h->sig_counter, 0, 256));
+    h->local_done = reinterpret_cast<unsigned long long*>(h->sig_counter) + 8;      // same allocation, its own 64-byte line
+    YB_CUDA(cudaEventCreateWithFlags(&h->comm_ev, cudaEventDisableTiming));
     h->dirty.resize(s.vars.size());
     for (size_t i = 0; i < s.vars.size(); i++) h->dirty[i].assign(s.vars[i].step_alloc(), 1);  // everything starts dirty (context.hpp:545-549)
     int d[3];
@@ -284,7 +309,12 @@ static int push_var_slot(Solution& s, const Neighbor& nb, int vi, int slot, cuda
 // halo cells again (WAR: a neighbour publishes its epoch only after the launches that read those cells).
 static int halo_flush_wait(Solution& s, cudaStream_t st) {
     HaloState* h = s.halo;
-    if (!h || !h->wait_pending) return 0;
+    if (!h) return 0;
+    if (h->comm_pending) {      // the side stream's copies read planes the next launch may overwrite
+        YB_CUDA(cudaStreamWaitEvent(st, h->comm_ev, 0));
+        h->comm_pending = false;
+    }
+    if (!h->wait_pending) return 0;
     halo_wait_kernel<<<1, 1, 0, st>>>(h->flags, h->wait_mask, h->epoch);
     YB_CUDA(cudaGetLastError());
     h->wait_pending = false;
@@ -371,6 +401,7 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
 
     // ---- fused path -----------------------------------------------------------------------------------------
     s.fused_x = Solution::FusedX();
+    unsigned long long *fx_flag_lo = nullptr, *fx_flag_hi = nullptr;      // the neighbours' flag words (copy-engine path)
     bool only_x = !h->nbrs.empty();
     for (auto& nb : h->nbrs) only_x = only_x && nb.dir[1] == 0 && nb.dir[2] == 0;
     if (sp.outputs.size() == 1 && !opt_off("fused_halo")) {
@@ -382,7 +413,8 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
             if (nb.dir[1] != 0 || nb.dir[2] != 0 || nb.dir[0] == 0 || !dx) continue;
             const BlobVar& pg = nb.var_geom[vi];
             // same y/z geometry on both sides (always true for pure x neighbours) and a 3-D var
-            bool same = pg.nd == 3 && pg.stride[0] == v.dims[1].stride && pg.stride[1] == v.dims[2].stride && pg.stride[2] == 1;
+            bool same = pg.nd == 3 && pg.stride[0] == v.dims[1].stride && pg.stride[1] == v.dims[2].stride && pg.stride[2] == 1 &&
+                        pg.pad_l[1] == v.dims[2].pad_l && pg.pad_l[2] == v.dims[3].pad_l;
             if (!same) continue;
             char* base = nb.var_base[vi] + size_t(slot) * pg.slot_elems * v.elem_bytes;
             long long origin = pg.pad_l[0] * pg.stride[0] + pg.pad_l[1] * pg.stride[1] + pg.pad_l[2] * pg.stride[2];
@@ -401,16 +433,54 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
         if (s.fused_x.var >= 0 && only_x && n_fused == h->nbrs.size() && overlap && !other_dirty(h, vi, slot)) {
             s.fused_x.counter = h->sig_counter;
             s.fused_x.epoch = h->epoch + 1;
+            // Copy-engine transfer (default; option dma_halo=0 keeps the kernel's own peer stores): the kernel publishes
+            // the epoch into a LOCAL word once its boundary planes are stored, the side stream waits on that word
+            // (cuStreamWaitValue64) and moves the planes -- contiguous slabs of R x-planes -- with cudaMemcpyAsync over
+            // NVLink, then publishes the epoch to the neighbour.  The SMs never wait for NVLink: with the stores issued by
+            // the sweep itself a 4-GPU step was 3.3 % longer (67-134 MB per step drain at the link's pace while the
+            // consumer warps sit behind them, profiles/r2_scaling.md).
+            if (!opt_off("dma_halo") && stream_wait_value64() && s.comm_stream) {
+                s.fused_x.dma = true;
+                fx_flag_lo = s.fused_x.flag_lo; fx_flag_hi = s.fused_x.flag_hi;
+                s.fused_x.flag_lo = h->local_done; s.fused_x.flag_hi = nullptr;
+            }
         }
     }
     if (s.fused_x.var >= 0) {
+        const Solution::FusedX fx = s.fused_x;
         int rc = s.engine->launch(s, stage, t, whole, st);
         if (rc < 0) return rc;
         s.stats.kernel_launches += rc;
         mark_outputs_dirty();
         const int skip = s.fused_x.used ? s.fused_x.var : -1;
         const bool signalled = s.fused_x.used && s.fused_x.signalled;
+        const bool dma = signalled && fx.dma;
         s.fused_x = Solution::FusedX();
+        if (dma) {
+            const Var& v = s.vars[fx.var];
+            const Dim* dx = v.domain_dim(0);
+            const int64_t R = std::max(dx->spec.halo_l, dx->spec.halo_r);
+            const size_t bytes = size_t(R) * size_t(dx->stride) * v.elem_bytes;
+            const char* mine = v.slot_ptr(v.slot_of(t + sp.out_step_off)) + size_t(dx->pad_l) * dx->stride * v.elem_bytes;   // plane x = 0
+            CUresult cr = stream_wait_value64()(reinterpret_cast<CUstream>(s.comm_stream), reinterpret_cast<CUdeviceptr>(h->local_done), fx.epoch,
+                                                CU_STREAM_WAIT_VALUE_GEQ);
+            if (cr != CUDA_SUCCESS) return set_error(YB_ECUDA, "cuStreamWaitValue64 failed with code %d", int(cr));
+            // fx.lo / fx.hi are the peers' element (0,0,0)-relative bases as the kernel would index them (like `out`): plane x
+            // of this rank lands at base + (x * stride) there; whole planes, pads included, are contiguous on both sides
+            const size_t origin_off = size_t(v.origin_offset() - dx->pad_l * dx->stride) * v.elem_bytes;   // y/z pads inside a plane
+            if (fx.lo) {
+                YB_CUDA(cudaMemcpyAsync(static_cast<char*>(fx.lo) - origin_off, mine, bytes, cudaMemcpyDefault, s.comm_stream));
+                halo_signal_kernel<<<1, 1, 0, s.comm_stream>>>(fx_flag_lo, fx.epoch);
+            }
+            if (fx.hi) {
+                const size_t last = size_t(dx->domain - R) * dx->stride * v.elem_bytes;
+                YB_CUDA(cudaMemcpyAsync(static_cast<char*>(fx.hi) + last - origin_off, mine + last, bytes, cudaMemcpyDefault, s.comm_stream));
+                halo_signal_kernel<<<1, 1, 0, s.comm_stream>>>(fx_flag_hi, fx.epoch);
+            }
+            YB_CUDA(cudaGetLastError());
+            YB_CUDA(cudaEventRecord(h->comm_ev, s.comm_stream));
+            h->comm_pending = true;
+        }
         return halo_exchange_impl(s, st, skip, signalled);
     }
 

@@ -316,10 +316,16 @@ struct IsoEngine : Engine {
             if (mem_probe && c.fn[3]) mode = 3;
             // fused halo exchange: only for whole-domain launches of a kernel that implements the peer stores
             P.peer_lo = P.peer_hi = nullptr;
-            const bool fused = s.fused_x.var == 0 && c.fused_ok && mode != 3 && box.b[0] == 0 && box.e[0] == P.nx && P.nx >= 2 * radius;
+            bool fused = s.fused_x.var == 0 && c.fused_ok && mode != 3 && box.b[0] == 0 && box.e[0] == P.nx && P.nx >= 2 * radius;
+            // in-kernel completion signal: needs room for boundary-first chunks; the copy-engine path exists only with it
+            const bool sig = fused && s.fused_x.counter != nullptr && P.nx >= 4 * radius;
+            if (fused && s.fused_x.dma && !sig) fused = false;
+            const bool nb_lo = fused && s.fused_x.lo != nullptr, nb_hi = fused && s.fused_x.hi != nullptr;   // x neighbours
             if (fused) {
-                P.peer_lo = static_cast<float*>(s.fused_x.lo);
-                P.peer_hi = static_cast<float*>(s.fused_x.hi);
+                if (!s.fused_x.dma) {        // the kernel stores the boundary planes into the neighbours itself
+                    P.peer_lo = static_cast<float*>(s.fused_x.lo);
+                    P.peer_hi = static_cast<float*>(s.fused_x.hi);
+                }
                 s.fused_x.used = true;
             }
             P.nty = int((box.e[1] - box.b[1] + c.ty - 1) / c.ty);
@@ -329,10 +335,9 @@ struct IsoEngine : Engine {
             // x chunks of equal length.  With an in-kernel completion signal the chunk that starts at plane 0 and the chunk
             // that ends at plane nx-1 (swept downwards) are numbered first, so that every CTA computes -- and stores into the
             // neighbours -- the boundary planes at the very start of its first sweeps.
-            const bool sig = fused && s.fused_x.counter != nullptr && P.nx >= 4 * radius;
             const int64_t ib = box.b[0], ie = box.e[0];
             const int64_t nxb = ie - ib;
-            const int min_nc = (sig && P.peer_lo && P.peer_hi) ? 2 : 1;
+            const int min_nc = (sig && nb_lo && nb_hi) ? 2 : 1;
             const int64_t max_nc = std::min<int64_t>(ISO_MAX_CHUNKS, sig ? nxb / radius : nxb);
             int nc_best = min_nc;
             if (lx > 0) {
@@ -352,14 +357,14 @@ struct IsoEngine : Engine {
             {
                 const int nc = nc_best;      // balanced partition: chunk lengths differ by at most one plane (all >= R when signalling)
                 std::vector<int> order;
-                if (sig && P.peer_lo) order.push_back(0);
-                if (sig && P.peer_hi && !(nc == 1 && P.peer_lo)) order.push_back(nc - 1);
+                if (sig && nb_lo) order.push_back(0);
+                if (sig && nb_hi && !(nc == 1 && nb_lo)) order.push_back(nc - 1);
                 nsig = int(order.size());
                 for (int c = 0; c < nc; c++)
                     if (std::find(order.begin(), order.end(), c) == order.end()) order.push_back(c);
                 for (int c : order) {
                     const int64_t x0 = ib + nxb * c / nc, x1 = ib + nxb * (c + 1) / nc;
-                    const bool down = sig && P.peer_hi && c == nc - 1 && !(nc == 1 && P.peer_lo);
+                    const bool down = sig && nb_hi && c == nc - 1 && !(nc == 1 && nb_lo);
                     P.cx0[nb] = int(down ? x1 - 1 : x0); P.clen[nb] = int(x1 - x0); P.cdir[nb] = down ? -1 : 1;
                     nb++;
                 }
