@@ -380,7 +380,7 @@ int yb_set_option(yb_solution* s_, const char* key, const char* value) {
     } else if (k == "auto_tune") {
         s->tuner = Solution::InRunTuner();
         s->tuner.enabled = atoi(value) != 0;
-    } else if (k == "overlap_comms" || k == "min_exterior" || k == "fused_halo") {
+    } else if (k == "overlap_comms" || k == "min_exterior" || k == "fused_halo" || k == "dma_halo") {
         // consumed by the halo engine at run time
     } else if (s->engine->set_option(*s, k, v) != 0) {
         return set_error(YB_EINVAL, "unknown option '%s'", key);

@@ -164,6 +164,7 @@ struct HaloState {
     unsigned int* sig_counter = nullptr;    // device word: arrivals of the in-kernel boundary signal (yb_iso3dfd.cuh)
     unsigned long long* local_done = nullptr;   // device word: epoch whose boundary planes are stored (copy-engine path)
     cudaEvent_t comm_ev = nullptr;          // last work enqueued on the side stream
+    cudaEvent_t ext_ev = nullptr;           // exterior launches of the current stage (the side stream's pushes follow it)
     bool comm_pending = false;
 };
 
@@ -175,6 +176,7 @@ void halo_free(HaloState* h) {
     if (h->flags) cudaFree(h->flags);
     if (h->sig_counter) cudaFree(h->sig_counter);
     if (h->comm_ev) cudaEventDestroy(h->comm_ev);
+    if (h->ext_ev) cudaEventDestroy(h->ext_ev);
     delete h;
 }
 
@@ -197,6 +199,7 @@ int halo_prepare(Solution& s) {
     YB_CUDA(cudaMemset(h->sig_counter, 0, 256));
     h->local_done = reinterpret_cast<unsigned long long*>(h->sig_counter) + 8;      // same allocation, its own 64-byte line
     YB_CUDA(cudaEventCreateWithFlags(&h->comm_ev, cudaEventDisableTiming));
+    YB_CUDA(cudaEventCreateWithFlags(&h->ext_ev, cudaEventDisableTiming));
     h->dirty.resize(s.vars.size());
     for (size_t i = 0; i < s.vars.size(); i++) h->dirty[i].assign(s.vars[i].step_alloc(), 1);  // everything starts dirty (context.hpp:545-549)
     int d[3];
@@ -325,11 +328,19 @@ static int halo_flush_wait(Solution& s, cudaStream_t st) {
 // pending (halo_flush_wait) so that whatever the caller enqueues next overlaps the transfer.
 //   skip_var:  the stage kernel already stored this var's x-face halos into the peers (fused path)
 //   signalled: ... and already published the epoch to the pure x neighbours itself
-static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var, bool signalled) {
+//   side:      enqueue the pushes and signals on the side stream (ordered after what `st` holds now), so that the launches
+//              the caller puts on `st` next -- the interior -- run while the slabs travel
+static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var, bool signalled, bool side = false) {
     HaloState* h = s.halo;
     if (!h) return 0;
     if (!h->finalized) return set_error(YB_ESTATE, "multi-rank solution: halo peers were not connected (yb_halo_import/finalize)");
     if (int rc = halo_flush_wait(s, st)) return rc;
+    cudaStream_t ps = st;
+    if (side && s.comm_stream && h->ext_ev) {
+        YB_CUDA(cudaEventRecord(h->ext_ev, st));
+        YB_CUDA(cudaStreamWaitEvent(s.comm_stream, h->ext_ev, 0));
+        ps = s.comm_stream;
+    }
     // Always a full handshake (even with nothing dirty): exchanges are collective, and every rank must
     // advance its epoch in lock-step with its neighbours.
     h->epoch++;
@@ -342,17 +353,21 @@ static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var, bool s
             if (int(vi) == skip_var && pure_x) continue;   // done by the kernel
             for (int slot = 0; slot < s.vars[vi].step_alloc(); slot++) {
                 if (!h->dirty[vi][slot]) continue;
-                int rc = push_var_slot(s, nb, int(vi), slot, st);
+                int rc = push_var_slot(s, nb, int(vi), slot, ps);
                 if (rc < 0) return rc;
                 launched += rc;
             }
         }
         int opp[3] = {-nb.dir[0], -nb.dir[1], -nb.dir[2]};
         // I am the peer's neighbour in direction `opp`; the peer waits on flags[dir_index(opp)]
-        if (!(signalled && pure_x)) halo_signal_kernel<<<1, 1, 0, st>>>(nb.peer_flags + dir_index(opp), h->epoch);
+        if (!(signalled && pure_x)) halo_signal_kernel<<<1, 1, 0, ps>>>(nb.peer_flags + dir_index(opp), h->epoch);
         mask |= 1u << dir_index(nb.dir);
     }
     YB_CUDA(cudaGetLastError());
+    if (ps != st) {
+        YB_CUDA(cudaEventRecord(h->comm_ev, ps));
+        h->comm_pending = true;
+    }
     h->wait_pending = true;
     h->wait_mask = mask;
     for (auto& dv : h->dirty)
@@ -518,7 +533,7 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
         cur.b[d] = interior.b[d]; cur.e[d] = interior.e[d];
     }
     mark_outputs_dirty();
-    if (int rc = halo_exchange_impl(s, st, -1, false)) return rc;
+    if (int rc = halo_exchange_impl(s, st, -1, false, true)) return rc;      // pushes on the side stream, behind the exterior
     int rc = s.engine->launch(s, stage, t, interior, st);
     if (rc < 0) return rc;
     s.stats.kernel_launches += rc;
