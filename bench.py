@@ -58,6 +58,8 @@ def parse_args():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-halo-check", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="diagnostic: under torchrun every rank runs an INDEPENDENT single-rank "
+                    "solution (no halo exchange); shows what N busy GPUs of one box cost before any exchange")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value")
     return ap.parse_args()
 
@@ -367,14 +369,15 @@ def main_b200(args):
 
     s = capi.Solution("iso3dfd")
     s.set_rank_domain_size_vec([N, N, N])
-    if world > 1:
+    coupled = world > 1 and not args.replicas
+    if coupled:
         s.set_num_ranks_vec([world, 1, 1])
         s.set_rank_index_vec([rank, 0, 0])
     for kv in args.opt:
         k, v = kv.split("=", 1)
         s.set_option(k, v)
     s.prepare_solution(local)
-    if world > 1:
+    if coupled:
         from yask_b200 import multi
         multi.connect(s, dist, rank, world)
     p, v = s.get_var("p"), s.get_var("v")
@@ -517,7 +520,7 @@ def main_b200(args):
 
     # ---- halo check (N > 1): real cross-device bit-exactness at the bench geometry -------------------------
     hc = None
-    if dist and not args.no_halo_check:
+    if dist and coupled and not args.no_halo_check:
         try:
             hc = halo_check(capi, dist, rank, world, local, N, args.opt)
         except Exception as ex:
@@ -546,7 +549,7 @@ def main_b200(args):
                 "config": {"workload": f"iso3dfd radius 8 (16th order) fp32, {N}^3 points per GPU, rank grid {world}x1x1",
                            "fp_mode": "ref_gcc (bit-exact vs reference default build)", "l2": "inputs (13.5 GB/GPU) larger than L2; no flush needed",
                            "global_points": pts_per_gpu * world, "wall_ms_per_step": round(wall_s / K * 1e3, 4), "checksum": str(checksum),
-                           "halo_exchange": ("none (1 rank)" if world == 1 else
+                           "halo_exchange": ("none (1 rank)" if world == 1 else "none: independent replicas (diagnostic)" if not coupled else
                                              "boundary planes stored into the x neighbours' HBM by the sweep kernel's first work units, epoch "
                                              "published in-kernel, interior swept meanwhile; wait kernel in front of the next step")},
                 "hbm_gbs_algorithmic": round(value * BYTES_PER_POINT, 1), "roofline": roofline, "sustained": sustained, "cpu_baseline": cpu, "e2e": e2e,

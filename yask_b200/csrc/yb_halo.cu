@@ -448,13 +448,14 @@ int halo_run_stage(Solution& s, int stage, int64_t t, cudaStream_t st) {
         if (s.fused_x.var >= 0 && only_x && n_fused == h->nbrs.size() && overlap && !other_dirty(h, vi, slot)) {
             s.fused_x.counter = h->sig_counter;
             s.fused_x.epoch = h->epoch + 1;
-            // Copy-engine transfer (default; option dma_halo=0 keeps the kernel's own peer stores): the kernel publishes
-            // the epoch into a LOCAL word once its boundary planes are stored, the side stream waits on that word
-            // (cuStreamWaitValue64) and moves the planes -- contiguous slabs of R x-planes -- with cudaMemcpyAsync over
-            // NVLink, then publishes the epoch to the neighbour.  The SMs never wait for NVLink: with the stores issued by
-            // the sweep itself a 4-GPU step was 3.3 % longer (67-134 MB per step drain at the link's pace while the
-            // consumer warps sit behind them, profiles/r2_scaling.md).
-            if (!opt_off("dma_halo") && stream_wait_value64() && s.comm_stream) {
+            // Copy-engine transfer (option dma_halo=1; default: the kernel's own peer stores): the kernel publishes the epoch
+            // into a LOCAL word once its boundary planes are stored, the side stream waits on that word (cuStreamWaitValue64)
+            // and moves the planes -- contiguous slabs of R x-planes -- with cudaMemcpyAsync over NVLink, then publishes the
+            // epoch to the neighbour.  Measured at 4 GPUs, interleaved on one box (profiles/r2_scaling.md): 40-step bursts
+            // 3.77-3.83 ms/step with the copy engines, 3.69-3.78 with the kernel's stores, 3.67-3.69 with no transfer at all;
+            // sustained over 2 s all three sit at 4.14-4.17 ms -- the exchange is not what a multi-GPU step costs.
+            auto dm = s.options.find("dma_halo");
+            if (dm != s.options.end() && dm->second == "1" && stream_wait_value64() && s.comm_stream) {
                 s.fused_x.dma = true;
                 fx_flag_lo = s.fused_x.flag_lo; fx_flag_hi = s.fused_x.flag_hi;
                 s.fused_x.flag_lo = h->local_done; s.fused_x.flag_hi = nullptr;
