@@ -31,9 +31,13 @@ def single_rank(n, steps, seed):
     return out
 
 
-@pytest.mark.parametrize("n,grid,steps", [((64, 48, 96), (2, 1, 1), 3), ((48, 64, 96), (1, 2, 1), 2), ((40, 40, 128), (1, 1, 2), 2),
-                                           ((70, 50, 100), (2, 2, 1), 3), ((64, 64, 128), (2, 2, 2), 2), ((150, 40, 64), (4, 1, 1), 4)])
-def test_rank_grid_matches_single_rank(n, grid, steps):
+@pytest.mark.parametrize("n,grid,steps,opts", [((64, 48, 96), (2, 1, 1), 3, {}), ((48, 64, 96), (1, 2, 1), 2, {}), ((40, 40, 128), (1, 1, 2), 2, {}),
+                                                ((70, 50, 100), (2, 2, 1), 3, {}), ((64, 64, 128), (2, 2, 2), 2, {}), ((150, 40, 64), (4, 1, 1), 4, {}),
+                                                # the other forms of the x-face exchange: copy engines on the side stream; round-1 order;
+                                                # push kernels instead of the sweep kernel's own stores
+                                                ((150, 40, 64), (4, 1, 1), 4, {"dma_halo": 1}), ((96, 40, 64), (2, 1, 1), 5, {"dma_halo": 1}),
+                                                ((150, 40, 64), (4, 1, 1), 4, {"overlap_comms": 0}), ((150, 40, 64), (4, 1, 1), 3, {"fused_halo": 0})])
+def test_rank_grid_matches_single_rank(n, grid, steps, opts):
     seed = 17
     ref = single_rank(n, steps, seed)
     world = grid[0] * grid[1] * grid[2]
@@ -43,6 +47,8 @@ def test_rank_grid_matches_single_rank(n, grid, steps):
         s.set_overall_domain_size_vec(n)
         s.set_num_ranks_vec(grid)
         s.set_rank_index_vec(multi.grid_coords(r, grid))
+        for k, v in opts.items():
+            s.set_option(k, v)
         s.prepare_solution(0)
         solns.append(s)
     multi.connect_local(solns)
