@@ -56,3 +56,45 @@ def test_domain_condition_bounds():
     assert c["bounds"] == {"2": [["GF", 5], ["GL", -3]]} and "G(2)" in c["expr"]
     c = E.parse_domain_cond("((x < (FIRST_INDEX(x) + 20)) || (y > 3))", ["x", "y"])
     assert c["bounds"] is None
+
+
+def _part(stmts, outs):
+    """A synthetic part: statements as (dst, expression text over reads @0.. @9); read k = access k at offset 0."""
+    ps = []
+    for dst, text in stmts:
+        tree = E.Parser(text).parse()
+        ps.append({"dst": dst, "tree": tree, "reads": [(k, [0, 0, 0]) for k in range(10)]})
+    return {"stmts": ps, "outputs": [{"access": 20, "src": o} for o in outs]}
+
+
+def _text(part):
+    rd = lambda st: (lambda i: f"r{st['reads'][i][0]}")
+    return {st["dst"]: E.gen_expr(st["tree"], rd(st), E.OPS) for st in E.contract_like_gcc(part)}
+
+
+def test_contraction_follows_the_gcc_rule():
+    """contract_like_gcc: the FMA formation of GCC's convert_mult_to_fma restated on the statement lists -- the oracle built
+    from these lists matches the reference's DEFAULT build bit for bit (tests/test_oracle_golden.py), here the rule itself."""
+    # of two products feeding one addition the one evaluated earlier is fused, the other stays a multiplication:
+    # inline operands are evaluated right to left ...
+    assert _text(_part([("e1", "@0 * @1 + @2 * @3")], ["e1"])) == {"e1": "MAD(r2, r3, MUL(r0, r1))"}
+    # ... separate statements in statement order
+    t = _text(_part([("e1", "@0 * @1"), ("e2", "@2 * @3"), ("e3", "expr_temp1 + expr_temp2")], ["e3"]))
+    assert t == {"e2": "MUL(r2, r3)", "e3": "MAD(r0, r1, e2)"}
+    # a product consumed by another product is not fused; the outer product is
+    assert _text(_part([("e1", "@0 * @1 * @2 + @3")], ["e1"])) == {"e1": "MAD(MUL(r0, r1), r2, r3)"}
+    # subtraction on either side, negation with a single use
+    assert _text(_part([("e1", "@0 * @1 - @2")], ["e1"])) == {"e1": "MSB(r0, r1, r2)"}
+    assert _text(_part([("e1", "@2 - @0 * @1")], ["e1"])) == {"e1": "NMAD(r0, r1, r2)"}
+    assert _text(_part([("e1", "-(@0 * @1) + @2")], ["e1"])) == {"e1": "NMAD(r0, r1, r2)"}
+    # a named product with two additive uses is fused into both and disappears; with a non-additive use it is kept everywhere
+    t = _text(_part([("e1", "@0 * @1"), ("e2", "expr_temp1 + @2"), ("e3", "@3 - expr_temp1")], ["e2", "e3"]))
+    assert t == {"e2": "MAD(r0, r1, r2)", "e3": "NMAD(r0, r1, r3)"}
+    t = _text(_part([("e1", "@0 * @1"), ("e2", "expr_temp1 + @2"), ("e3", "expr_temp1 * @3")], ["e2", "e3"]))
+    assert t == {"e1": "MUL(r0, r1)", "e2": "ADD(e1, r2)", "e3": "MUL(e1, r3)"}
+    # the same product written twice is ONE value (redundancy elimination runs before FMA formation)
+    t = _text(_part([("e1", "@0 * @1 + @2"), ("e2", "(@1 * @0) * @3")], ["e1", "e2"]))
+    assert t["e1"] == "ADD(MUL(r0, r1), r2)" and t["e2"] == "MUL(MUL(r0, r1), r3)"
+    # a product that is written out is never fused away
+    t = _text(_part([("e1", "@0 * @1"), ("e2", "expr_temp1 + @2")], ["e1", "e2"]))
+    assert t == {"e1": "MUL(r0, r1)", "e2": "ADD(e1, r2)"}

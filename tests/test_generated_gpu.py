@@ -24,7 +24,7 @@ def json_meta(path):
 MATH_FUNC_STENCILS = {"test_func_1d"}
 MATH_ULPS = 16.0
 # default-build contraction not reproduced element for element (tests/test_oracle_golden.py): 4 field-ulps
-NOT_BITEXACT_DEFAULT = {"tti", "wave2d"}
+NOT_BITEXACT_DEFAULT = {"tti"}
 
 
 def load_inputs(s, ins):

@@ -50,16 +50,15 @@ def _domain(ir, name, arr):
 from tests.helpers import generated_golden_cases  # noqa: E402
 
 
-# Solutions whose default-build contraction is not reproduced element for element (the reference's vector code orders a few
-# products differently from its scalar listing, which the emitter reads): held to 4 field-ulps instead.
-NOT_BITEXACT_DEFAULT = {"tti", "wave2d"}
+# Solutions whose default-build contraction is not reproduced element for element: held to 4 field-ulps instead.
+NOT_BITEXACT_DEFAULT = {"tti"}
 
 
 @pytest.mark.parametrize("path", generated_golden_cases())
 def test_generated_oracle_vs_reference(path):
     """Strict reference build (-ffp-contract=off): bit-exact.  Default build (GCC -O3, -ffp-contract=fast): bit-exact as
-    well, with the products fused exactly where GCC fuses them (emitter: contract_like_gcc; oracle contract=1) -- for 43 of
-    the 45 solutions; the two in NOT_BITEXACT_DEFAULT within 4 field-ulps."""
+    well, with the products fused exactly where GCC fuses them (emitter: contract_like_gcc; oracle contract=1) -- for 44 of
+    the 45 solutions; tti (NOT_BITEXACT_DEFAULT) within 4 field-ulps."""
     meta, arrays = load_golden(path)
     ins = regen_inputs(meta)
     strict = "strict" in meta["ref_tag"]

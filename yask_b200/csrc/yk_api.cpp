@@ -254,6 +254,18 @@ struct B200Var : yk_var {
         }
         return true;
     }
+    // With set_step_wrap(true) any step index addresses the slot it wraps to (imod_flr(t, alloc_t), yk_var.hpp:131-147): reads go
+    // through the step of the valid window that lives in that slot (the C ABI checks the window on reads).
+    idx_t_vec wrapped(const yb_var_info& i, const idx_t_vec& idx) const {
+        idx_t_vec out = idx;
+        if (*step_wrap && i.has_step && !out.empty()) {
+            const idx_t a = i.step_alloc, f = i.first_valid_step;
+            idx_t d = (out[0] - f) % a;
+            if (d < 0) d += a;
+            out[0] = f + d;
+        }
+        return out;
+    }
     bool are_indices_local(const idx_t_vec& indices) const override {
         if (!prepared()) return false;
         return local(info(), indices, true);
@@ -267,8 +279,9 @@ struct B200Var : yk_var {
         auto i = info();
         if (!local(i, indices, true)) fail("get_element: indices " + format_indices(indices) + " are not valid for var '" + name + "'");
         double out = 0;
-        if (i.elem_bytes == 4) { float f = 0; chk(yb_var_get_slice(h->s, vi, &f, indices.data(), indices.data(), nullptr)); out = f; }
-        else chk(yb_var_get_slice(h->s, vi, &out, indices.data(), indices.data(), nullptr));
+        const idx_t_vec w = wrapped(i, indices);
+        if (i.elem_bytes == 4) { float f = 0; chk(yb_var_get_slice(h->s, vi, &f, w.data(), w.data(), nullptr)); out = f; }
+        else chk(yb_var_get_slice(h->s, vi, &out, w.data(), w.data(), nullptr));
         return out;
     }
     double get_element(const idx_t_init_list& indices) const override { return get_element(idx_t_vec(indices)); }
@@ -311,10 +324,12 @@ struct B200Var : yk_var {
         size_t n = slice_elems(first, last);
         if (buffer_size < n) fail("get_elements_in_slice: buffer of " + std::to_string(buffer_size) + " element(s) is too small for " + std::to_string(n));
         int64_t done = 0;
-        if (sizeof(T) == size_t(i.elem_bytes)) { chk(yb_var_get_slice(h->s, vi, buf, first.data(), last.data(), &done)); return done; }
+        idx_t_vec wf = first, wl = last;
+        if (*step_wrap && i.has_step && first[0] == last[0]) { wf = wrapped(i, first); wl[0] = wf[0]; }      // one step: wrap it into the window
+        if (sizeof(T) == size_t(i.elem_bytes)) { chk(yb_var_get_slice(h->s, vi, buf, wf.data(), wl.data(), &done)); return done; }
         // element-size conversion through a temporary
         std::vector<char> tmp(n * i.elem_bytes);
-        chk(yb_var_get_slice(h->s, vi, tmp.data(), first.data(), last.data(), &done));
+        chk(yb_var_get_slice(h->s, vi, tmp.data(), wf.data(), wl.data(), &done));
         for (size_t k = 0; k < n; k++) buf[k] = i.elem_bytes == 4 ? T(reinterpret_cast<float*>(tmp.data())[k]) : T(reinterpret_cast<double*>(tmp.data())[k]);
         return done;
     }

@@ -510,8 +510,9 @@ def contract_like_gcc(part):
     """Rewrite the statement trees of `part` with the FMA contraction GCC applies to the reference's generated code in its
     default build (-O3, -ffp-contract=fast; tree-ssa-math-opts.c, convert_mult_to_fma): walking the operations in
     evaluation order, a multiplication is fused iff EVERY use of its value is an addition or subtraction that has not been
-    turned into an FMA already; it is then fused into each of them and disappears.  (So of a*b + c*d the earlier product
-    is fused, the later one stays a multiplication.)  Values are numbered structurally first, as GCC's redundancy
+    turned into an FMA already; it is then fused into each of them and disappears.  (So of two products feeding one addition
+    the one evaluated EARLIER is fused, the other stays a multiplication: for separate statements that is statement order, for
+    a*b + c*d written inline it is c*d -- operands of the reference's overloaded operators are evaluated right to left.)  Values are numbered structurally first, as GCC's redundancy
     elimination does before that pass: the same product written twice is one value with two uses.
     Returns the new statement list; statements whose product was fused away are dropped."""
     nodes = {}          # value key -> node
@@ -552,7 +553,11 @@ def contract_like_gcc(part):
             return intern("call", [build(a, st) for a in tree[2]], ("f", tree[1]))
         if k == "neg":
             return intern("neg", [build(tree[1], st)])
-        return intern(k, [build(tree[1], st), build(tree[2], st)])
+        # operands of an operator written inline are evaluated RIGHT first (they are arguments of the reference's overloaded
+        # real_vec_t operators, which GCC evaluates right to left); pinned by wave2d's default-build fixtures
+        r_ = build(tree[2], st)
+        l_ = build(tree[1], st)
+        return intern(k, [l_, r_])
 
     roots = []
     uid = [0]
