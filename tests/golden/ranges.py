@@ -28,6 +28,11 @@ GENERATED = {"awp_elastic": "awp_elastic", "ssg": "ssg-fp64", "awp": "awp", "iso
              "test_boundary_3d": "test_boundary_3d", "test_stream_3d": "test_stream_3d"}
 GENERATED["iso3dfd_fp64"] = "iso3dfd-fp64"
 RANGES["iso3dfd_fp64"] = RANGES["iso3dfd"]
+# the reference's own validation matrix for these two (src/kernel/Makefile:1155-1156): fp64, radius 3 / radius 6
+GENERATED["iso3dfd_fp64_r3"] = "iso3dfd-fp64-r3"
+RANGES["iso3dfd_fp64_r3"] = RANGES["iso3dfd"]
+GENERATED["iso3dfd_sponge_fp64_r6"] = "iso3dfd_sponge-fp64-r6"
+RANGES["iso3dfd_sponge_fp64_r6"] = RANGES["iso3dfd_sponge"]
 GENERATED.update({"fsg": "fsg", "fsg_abc": "fsg_abc", "ssg2": "ssg2", "ssg_merged": "ssg_merged", "fsg2": "fsg2"})
 for _t in ("ssg2", "ssg_merged", "fsg2"):
     # merged-array variants: v/s hold all components along a misc dim, coef the material coefficients

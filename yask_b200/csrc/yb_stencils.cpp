@@ -29,15 +29,23 @@ int registry_create(const std::string& name, int radius, int elem_bytes, Stencil
         if (elem_bytes == 0) elem_bytes = 4;
         if (radius > 8) return set_error(YB_EUNSUPPORTED, "iso3dfd: radius %d > 8 is not supported", radius);
         if (elem_bytes == 8) {
-            // double precision: served by the emitter-generated kernel (radius 8 only); the tiled kernel is fp32
-            if (radius != 8) return set_error(YB_EUNSUPPORTED, "iso3dfd fp64 is generated for radius 8 only");
-            int rc = gen_registry_create("iso3dfd_fp64", 8, spec, eng);
-            if (rc == 0) { spec.name = "iso3dfd"; spec.radius = 8; }
+            // double precision: served by emitter-generated sweep kernels, radius 8 and radius 3 (the radius of the
+            // reference's own fp64 validation run, /root/reference/src/kernel/Makefile:1155); the hand-written kernel is fp32
+            if (radius != 8 && radius != 3) return set_error(YB_EUNSUPPORTED, "iso3dfd fp64 is generated for radius 8 and radius 3 only");
+            int rc = gen_registry_create(radius == 8 ? "iso3dfd_fp64" : "iso3dfd_fp64_r3", 8, spec, eng);
+            if (rc == 0) { spec.name = "iso3dfd"; spec.radius = radius; }
             return rc;
         }
         spec = iso3dfd_spec(radius, elem_bytes, false);
         eng = make_iso3dfd_engine();
         return 0;
+    }
+    if (name == "iso3dfd_sponge" && elem_bytes == 8) {
+        // fp64: generated for radius 6, the reference's fp64 validation run of this solution (src/kernel/Makefile:1156)
+        if (radius > 0 && radius != 6) return set_error(YB_EUNSUPPORTED, "iso3dfd_sponge fp64 is generated for radius 6 only");
+        int rc = gen_registry_create("iso3dfd_sponge_fp64_r6", 8, spec, eng);
+        if (rc == 0) { spec.name = "iso3dfd_sponge"; spec.radius = 6; }
+        return rc;
     }
     int rc = gen_registry_create(name, elem_bytes, spec, eng);
     if (rc != YB_EINVAL) return rc;
