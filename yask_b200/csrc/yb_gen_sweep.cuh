@@ -72,10 +72,10 @@ template <> struct SwVec<double, 1> {
     }
 };
 
-// slot index of the plane `ahead` places after the ring position `c` (both < ns)
-__device__ __forceinline__ uint32_t sw_wrap(uint32_t c, uint32_t ahead, uint32_t ns) {
+// position `ahead` further along a ring of `size` (c and ahead < size; all three in the same unit: slots or bytes)
+__device__ __forceinline__ uint32_t sw_wrap(uint32_t c, uint32_t ahead, uint32_t size) {
     const uint32_t u = c + ahead;
-    return u >= ns ? u - ns : u;
+    return u >= size ? u - size : u;
 }
 
 // Producer side: the loads of stream k first needed at sweep iteration j (j == 0: its whole x reach; j > 0: the newest plane).

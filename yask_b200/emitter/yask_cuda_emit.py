@@ -758,6 +758,7 @@ def _stage_sequence(ir, st):
 SWEEP_SMEM_LIMIT = 225 * 1024          # of the 227 KB a CTA may use
 SWEEP_TWO_CTA_SMEM = 112 * 1024        # two CTAs per SM below this
 SWEEP_MAX_STREAMS = 28
+SWEEP_XQUEUE = os.environ.get("YB_EMIT_SWEEP_XQ", "1") != "0"     # x neighbours of split streams in registers (tuning knob)
 
 
 def _roundup(v, m):
@@ -893,6 +894,16 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
                     loads.setdefault((k, o[0], o[1] - streams[k]["yl"], j), None)
             elif a not in outs and m in (0, 1, 2, 4):
                 hoist.setdefault((a, o), None)
+    # x neighbours in registers: a stream that is only read at the point's own (y, z) (long x reach) in a kernel whose threads own at most one 64-bit
+    # value per plane is read ONCE per plane -- the newest -- into a per-thread queue that shifts by one plane per iteration
+    # (the whole reach is read at the first iteration of a chunk, when the ring holds it).  The ring and the producer are
+    # unchanged; this trades (reach - 1) shared-memory loads and their ring addresses for register moves.
+    def own(k, ry, j):
+        return ry == -streams[k]["yl"] and j == 0
+
+    xq = {k for k, s_ in enumerate(streams)
+          if s_["kind"] in "CW" and vw * eb <= 8 and rpt == 1 and s_["xr"] - s_["xl"] + 1 >= 4 and SWEEP_XQUEUE
+          and all(own(k, ry, j) for (k2, dx, ry, j) in loads if k2 == k and dx != 0)}
     n_str = len({s_["acc"] for s_ in streams})
     # Points of a vector beyond the box are computed like the others (their reads stay inside shared memory / clamped
     # indices) and simply not stored -- unless the part has reads that go to global memory with the point's own indices.
@@ -963,10 +974,16 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
             L.append(f"    _Pragma(\"unroll\") for (int i = 0; i < VW; i++) {nm}[i] = static_cast<const T*>(P.ptr[{a}])[(min(zq + i, P.ze - 1) + ({o[2]})) * P.sz[{a}]];")
         else:
             hoist[(a, o)] = ("plane", nm)
-    ns_vals = sorted({s_["ns"] for s_ in streams})
+    # Ring positions: one byte offset per distinct (ring length, slot size) -- the offset of the slot that holds the OLDEST
+    # plane of the ring (x + XL) -- advanced by one slot per iteration with a wrap; a plane `ahead` slots further is one add
+    # and one conditional subtract away, shared by every stream with the same ring shape (no multiplications, no divisions).
+    rings = sorted({(s_["ns"], s_["slot"]) for s_ in streams})
     L.append("    int fb = 0; unsigned fpar = 0;")
-    L.append("    " + " ".join(f"uint32_t c{n} = 0;" for n in ns_vals) + "      // sweep iteration modulo the ring lengths")
+    L.append("    " + " ".join(f"uint32_t q{n}_{sl} = 0;" for n, sl in rings) + "      // byte offset of the oldest plane's slot, per ring shape")
     L.append("    const bool vec_ok = nzv == VW && ((reinterpret_cast<uintptr_t>(static_cast<T*>(P.ptr[%d]) + zq) & (VW * sizeof(T) - 1)) == 0) && (P.SY %% VW == 0) && (P.SX %% VW == 0);" % p["outputs"][0]["access"])
+    for k in sorted(xq):
+        s_ = streams[k]
+        L.append("    " + " ".join(f"T xq{k}_{d}[VW] = {{}};" for d in range(s_["xr"] - s_["xl"] + 1)) + f"      // x queue of stream {k}: planes x{s_['xl']:+d} .. x{s_['xr']:+d}")
     L.append("    for (int it = 0; it < sw_len; it++) {")
     L.append("        mbar_wait(&full_bar[fb], fpar);")
     L.append("        const int x = xs + it;")
@@ -974,20 +991,38 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
         if where == "plane":
             L.append(f"        const T {nm} = static_cast<const T*>(P.ptr[{a}])[(x + ({o[0]})) * P.sx[{a}]];")
     # plane bases per (stream, dx) actually read
-    used = sorted({(k, dx) for (k, dx, _, _) in loads})
+    used = sorted({(k, dx) for (k, dx, ry, j) in loads if k not in xq or not own(k, ry, j)} | {(k, streams[k]["xr"]) for k in xq})
+    rels = sorted({(streams[k]["ns"], streams[k]["slot"], dx - streams[k]["xl"]) for (k, dx) in used})
+    for (n, sl, ahead) in rels:
+        L.append(f"        const uint32_t r{n}_{sl}_{ahead} = " + (f"q{n}_{sl};" if ahead == 0 else f"sw_wrap(q{n}_{sl}, {ahead * sl}u, {n * sl}u);"))
     for (k, dx) in used:
         s_ = streams[k]
-        L.append(f"        const uint32_t b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} = t{k} + sw_wrap(c{s_['ns']}, {dx - s_['xl']}u, {s_['ns']}u) * {s_['slot']}u;")
+        L.append(f"        const uint32_t b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} = t{k} + r{s_['ns']}_{s_['slot']}_{dx - s_['xl']};")
     for key in sorted(loads):
         k, dx, ry, j = key
         s_ = streams[k]
         nm = f"v{k}_{'m' if dx < 0 else 'p'}{abs(dx)}_{ry}_{'m' if j < 0 else 'p'}{abs(j)}"
+        if k in xq and own(k, ry, j):
+            nm = f"xq{k}_{dx - s_['xl']}"
         loads[key] = nm
+    for k in sorted(xq):
+        s_ = streams[k]
+        nq = s_["xr"] - s_["xl"] + 1
+        thr = f"uint32_t(({-s_['yl']} * {s_['pz']}) * {eb})"
+        L.append("        if (it == 0) {")
+        for d in range(nq):
+            L.append(f"            SwVec<T, VW>::lds(t{k} + {d * s_['slot']}u + {thr}, xq{k}_{d});")
+        L.append("        } else {")
+        L.append("            _Pragma(\"unroll\") for (int i = 0; i < VW; i++) { " + " ".join(f"xq{k}_{d}[i] = xq{k}_{d + 1}[i];" for d in range(nq - 1)) + " }")
+        L.append(f"            SwVec<T, VW>::lds(b{k}_{'m' if s_['xr'] < 0 else 'p'}{abs(s_['xr'])} + {thr}, xq{k}_{nq - 1});")
+        L.append("        }")
     L.append("        _Pragma(\"unroll\") for (int r = 0; r < RPT; r++) {")
     L.append("            const int y = y0_ + sw_r0 + r;")
     for key in sorted(loads):
         k, dx, ry, j = key
         s_ = streams[k]
+        if k in xq and own(k, ry, j):
+            continue
         L.append(f"            T {loads[key]}[VW]; SwVec<T, VW>::lds(b{k}_{'m' if dx < 0 else 'p'}{abs(dx)} + uint32_t(((r + {ry}) * {s_['pz']} + ({j * vw})) * {eb}), {loads[key]});")
     for o in p["outputs"]:
         L.append(f"            T o{o['access']}[VW];")
@@ -1028,7 +1063,7 @@ def emit_sweep_kernel(ir, p, plan, ident) -> list:
     L.append("        __syncwarp();")
     L.append("        if (lane == 0) mbar_arrive(&done_bar[fb]);      // this warp is done with the oldest slots")
     L.append("        if (++fb == NB) { fb = 0; fpar ^= 1u; }")
-    L.append("        " + " ".join(f"if (++c{n} == {n}u) c{n} = 0;" for n in ns_vals))
+    L.append("        " + " ".join(f"q{n}_{sl} = sw_wrap(q{n}_{sl}, {sl}u, {n * sl}u);" for n, sl in rings))
     L.append("    }")
     L.append("}")
     return L
