@@ -830,7 +830,10 @@ def sweep_plan(ir, p):
     """Tile shape, prefetch depth and shared-memory layout of part `p`'s sweep kernel, or None.  Always 8 consumer warps:
     a tile of 8 rows gives every thread one 16-byte vector of points, a tile of 4 rows (rings of 8 rows do not fit) half
     a vector -- two warps then share a tile row."""
-    cands = [(8, 8, 2), (4, 8, 2), (8, 8, 1), (4, 8, 1)]          # (tile rows, consumer warps, planes of prefetch)
+    # (tile rows, consumer warps, planes of prefetch).  4-row tiles (one or two points per thread, two warps per scheduler) are
+    # latency-bound and take a third plane of prefetch when it fits: ssg fp64 512^3 +5.8 % on one box (profiles/r2_generated.md).
+    # A fourth plane (fits ssg's stage 1) measured no further gain.
+    cands = [(8, 8, 2), (4, 8, 3), (4, 8, 2), (8, 8, 1), (4, 8, 1)]
     if os.environ.get("YB_EMIT_SWEEP_TY"):                          # tuning knobs: force one candidate
         ty = int(os.environ["YB_EMIT_SWEEP_TY"])
         cands = [(ty, int(os.environ.get("YB_EMIT_SWEEP_NW", "8")), int(os.environ.get("YB_EMIT_SWEEP_PF", "2")))]
