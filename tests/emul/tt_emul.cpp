@@ -1,0 +1,161 @@
+// TEST INFRASTRUCTURE ONLY -- CTA emulator for the iso3dfd temporal-tile kernel (yask_b200/csrc/yb_iso3dfd_tt.cuh).
+//
+// The product header is compiled here by g++ with YB_TT_HOST_EMUL: the very same tt_sweep / tt_step1 / tt_step2 /
+// tt_loads code the GPU runs, on a back end that executes the threads of a CTA in a loop, copies TMA boxes on the host
+// (zero fill outside the array, as the hardware does) and models the full barriers (phase parity, transaction
+// completion).  It verifies index arithmetic, ring-slot reuse and barrier phases bit for bit against the oracle on a
+// machine without a GPU; it is NOT a product path (nothing under yask_b200/ links it) and it is not timed.
+//
+// Two completion models per run, chosen by `lazy`:
+//   eager: a box lands in shared memory the moment it is issued  (the earliest the hardware may write: a load that is
+//          issued while its slot is still being read corrupts the result)
+//   lazy : a box lands when its barrier is waited on              (the latest: a read that is not covered by the right
+//          wait sees poisoned shared memory)
+// Shared memory starts poisoned with NaNs.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#define YB_TT_HOST_EMUL 1
+#define YB_DEVFN static inline
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+
+#include "../../yask_b200/csrc/yb_iso3dfd_tt.cuh"
+
+using namespace yb;
+
+namespace {
+
+// a padded 3-D array as a tensor map sees it: dims (z, y, x), z unit stride
+struct Tensor {
+    const float* base;
+    long long nz, ny, nx, sy, sx;
+};
+
+struct Pending { uint32_t off; const Tensor* t; int bz, by, z, y, x; };
+
+template <class T>
+struct Emul {
+    std::vector<uint8_t> smem;
+    Tensor pin, prev, v;
+    bool lazy = false;
+    int error = 0;
+    struct Bar { unsigned phases = 0; bool armed = false; std::vector<Pending> pend; } bars[T::NS];
+    std::vector<TTVec4> vregs;
+    std::vector<TTThread<T>> ths;
+    TTThread<T>& thread(int tid) { return ths[tid]; }
+
+    Emul() : smem(T::SMEM_BYTES), vregs(size_t(T::THREADS) * T::S2_ROUNDS), ths(T::THREADS) {
+        const uint32_t nan = 0x7fc00000u;
+        for (size_t i = 0; i + 4 <= smem.size(); i += 4) memcpy(&smem[i], &nan, 4);
+    }
+    void copy_box(const Pending& p) {
+        float* dst = reinterpret_cast<float*>(smem.data() + p.off);
+        for (int y = 0; y < p.by; y++)
+            for (int z = 0; z < p.bz; z++) {
+                const long long gz = p.z + z, gy = p.y + y, gx = p.x;
+                const bool in = gz >= 0 && gz < p.t->nz && gy >= 0 && gy < p.t->ny && gx >= 0 && gx < p.t->nx;
+                dst[y * p.bz + z] = in ? p.t->base[gx * p.t->sx + gy * p.t->sy + gz] : 0.f;
+            }
+    }
+    template <class F> void threads(F f) { for (int t = 0; t < T::THREADS; t++) f(t); }
+    template <class F> void once(F f) { f(); }
+    void barrier() {}
+    TTVec4* vreg(int tid) { return &vregs[size_t(tid) * T::S2_ROUNDS]; }
+    void issue(const TTLoads& L, int b) {
+        Bar& br = bars[b];
+        if (br.armed) { error = 1; return; }          // a phase is re-armed before its previous use was waited on
+        uint32_t bytes = T::P_BYTES;
+        std::vector<Pending> ps;
+        ps.push_back(Pending{L.p_off, &pin, T::IZ, T::IY, L.pz, L.py, L.px});
+        if (L.step1) {
+            ps.push_back(Pending{L.pv_off, &prev, T::S1Z, T::S1Y, L.sz, L.sy, L.sx});
+            ps.push_back(Pending{L.v_off, &v, T::S1Z, T::S1Y, L.vz, L.vy, L.vx});
+            bytes += 2 * T::S_BYTES;
+        }
+        if (bytes != L.bytes) { error = 2; return; }   // expect_tx would never be met (hang) or be exceeded
+        for (auto& p : ps) {
+            if (p.off % 128 != 0 || (p.z * 4) % 16 != 0) { error = 3; return; }   // TMA destination / box start alignment
+            if (!lazy) copy_box(p);
+        }
+        br.armed = true;
+        if (lazy) br.pend = ps;
+    }
+    void wait_full(int b, uint32_t parity) {
+        Bar& br = bars[b];
+        if ((br.phases & 1u) == parity) {              // the phase waited for has not completed yet: it must be in flight
+            if (!br.armed) { error = 4; return; }      // nothing in flight: the GPU would hang here
+            for (auto& p : br.pend) copy_box(p);
+            br.pend.clear();
+            br.armed = false;
+            br.phases++;
+        }
+        // else: that phase completed earlier -- legal only if nothing newer is in flight on this barrier that we
+        // should have waited for; the data check catches a stale read
+    }
+};
+
+template <class T, int MODE>
+int run(const float* pprev, const float* pcur, const float* vel, float* out1, float* out2, const int* n, const int* ppad, const int* vpad,
+        const float* coef, int grid, int nchunks, int lazy) {
+    const long long pz = n[2] + 2 * ppad[2], py = n[1] + 2 * ppad[1], px = n[0] + 2 * ppad[0];
+    const long long vz = n[2] + 2 * vpad[2], vy = n[1] + 2 * vpad[1], vx = n[0] + 2 * vpad[0];
+    TTParams P{};
+    P.p_sy = pz; P.p_sx = pz * py; P.v_sy = vz; P.v_sx = vz * vy;
+    const long long porg = ppad[0] * P.p_sx + ppad[1] * P.p_sy + ppad[2];
+    P.out1 = out1 + porg; P.out2 = out2 + porg;
+    P.vel = vel + vpad[0] * P.v_sx + vpad[1] * P.v_sy + vpad[2];
+    P.nx = n[0]; P.ny = n[1]; P.nz = n[2];
+    P.pad_x = ppad[0]; P.pad_y = ppad[1]; P.pad_z = ppad[2];
+    P.vpad_x = vpad[0]; P.vpad_y = vpad[1]; P.vpad_z = vpad[2];
+    for (int r = 0; r <= T::R; r++) P.c[r] = coef[r];
+    P.nty = (P.ny + T::TY - 1) / T::TY;
+    P.ntz = (P.nz + T::TZ - 1) / T::TZ;
+    if (nchunks < 1 || nchunks > TT_MAX_CHUNKS || nchunks > P.nx) return -1;
+    P.nchunks = nchunks;
+    for (int k = 0; k < nchunks; k++) {
+        const long long x0 = (long long)P.nx * k / nchunks, x1 = (long long)P.nx * (k + 1) / nchunks;
+        P.cx0[k] = int(x0); P.clen[k] = int(x1 - x0);
+    }
+    for (int blk = 0; blk < grid; blk++) {
+        Emul<T> be;
+        be.lazy = lazy != 0;
+        be.pin = Tensor{pcur, pz, py, px, P.p_sy, P.p_sx};
+        be.prev = Tensor{pprev, pz, py, px, P.p_sy, P.p_sx};
+        be.v = Tensor{vel, vz, vy, vx, P.v_sy, P.v_sx};
+        tt_sweep<T, MODE>(be, be.smem.data(), P, blk, grid);
+        if (be.error) return be.error;
+        for (auto& b : be.bars) if (b.armed) return 5;     // loads still in flight when the CTA exits
+    }
+    return 0;
+}
+
+template <class T>
+int run_mode(int mode, const float* a, const float* b, const float* c, float* d, float* e, const int* n, const int* pp, const int* vp, const float* coef,
+             int grid, int nchunks, int lazy) {
+    switch (mode) {
+        case 0: return run<T, 0>(a, b, c, d, e, n, pp, vp, coef, grid, nchunks, lazy);
+        case 1: return run<T, 1>(a, b, c, d, e, n, pp, vp, coef, grid, nchunks, lazy);
+        default: return run<T, 2>(a, b, c, d, e, n, pp, vp, coef, grid, nchunks, lazy);
+    }
+}
+
+}  // namespace
+
+// p arrays: (nx+2*ppad[0], ny+2*ppad[1], nz+2*ppad[2]) floats, v: same with vpad.  out1 / out2 must arrive holding copies of
+// pprev / pcur (their halo cells are what the engine's begin_run() replicates); the domain parts are overwritten with
+// p(t+1) / p(t+2).  `variant`: 0 = the shipped tile of that radius, 1 = a small tile (more tiles and rounds per test).
+// Returns 0, or a protocol error code (see Emul).
+extern "C" int tt_emul_run(int radius, int variant, int mode, const float* pprev, const float* pcur, const float* vel, float* out1, float* out2,
+                           const int* n, const int* ppad, const int* vpad, const float* coef, int grid, int nchunks, int lazy) {
+    if (radius == 1 && variant == 0) return run_mode<TTile<1, 16, 128, 3, 256>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 2 && variant == 0) return run_mode<TTile<2, 16, 128, 2, 256>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 1 && variant == 1) return run_mode<TTile<1, 4, 16, 2, 32>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 2 && variant == 1) return run_mode<TTile<2, 4, 16, 1, 32>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    return -2;
+}

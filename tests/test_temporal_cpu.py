@@ -1,0 +1,101 @@
+"""iso3dfd temporal tile (two steps per sweep, yask_b200/csrc/yb_iso3dfd_tt.cuh) on the CPU: the kernel's own sweep / step /
+load-coordinate code, compiled by g++ into a CTA emulator (tests/emul/tt_emul.cpp), must reproduce two oracle steps bit for
+bit -- for both completion models of the TMA loads (eager = WAR hazards on ring slots, lazy = missing / wrong barrier waits),
+ragged domains, domains thinner than the tile halo, several chunkings and grid sizes, and every FP mode.
+
+Reference behaviour being matched: temporal blocking never changes results
+(/root/reference/src/kernel/lib/context.cpp:657-681), halo cells keep what the two-slot storage holds
+(/root/reference/src/compiler/lib/Var.cpp:435-464)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from yask_b200.synth import hash_field, var_salt
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def emul():
+    global _LIB
+    if _LIB is None:
+        subprocess.run(["make", "-s", "-C", os.path.join(HERE, "emul")], check=True)
+        _LIB = ctypes.CDLL(os.path.join(HERE, "_bin", "libtt_emul.so"))
+        _LIB.tt_emul_run.argtypes = [ctypes.c_int] * 3 + [ctypes.c_void_p] * 9 + [ctypes.c_int] * 3
+        _LIB.tt_emul_run.restype = ctypes.c_int
+    return _LIB
+
+
+def _coef32(radius):
+    return np.asarray(O.iso3dfd_coeffs(radius), dtype=np.float64).astype(np.float32)
+
+
+def run_case(radius, variant, mode, n, ppad, vpad, grid, nchunks, lazy, seed=7):
+    """Returns (got1, got2, ref1, ref2): domain parts of p(t+1), p(t+2) from the emulator and from the oracle."""
+    n = list(n)
+    R = radius
+    # p arrays with pads >= halo; cells beyond the halo hold NaN (pad garbage must never reach a result)
+    pshape = [n[d] + 2 * ppad[d] for d in range(3)]
+    p = []
+    for t in (0, 1):
+        a = np.full(pshape, np.nan, dtype=np.float32)
+        core = hash_field(seed, var_salt("p", t), (-R, -R, -R), [n[d] + 2 * R for d in range(3)], -1, 1)
+        a[tuple(slice(ppad[d] - R, ppad[d] + n[d] + R) for d in range(3))] = core
+        p.append(a)
+    vshape = [n[d] + 2 * vpad[d] for d in range(3)]
+    v = np.full(vshape, np.nan, dtype=np.float32)
+    vcore = hash_field(seed, var_salt("v", 0), (0, 0, 0), n, 0.05, 0.3)
+    v[tuple(slice(vpad[d], vpad[d] + n[d]) for d in range(3))] = vcore
+    out1, out2 = p[0].copy(), p[1].copy()      # what begin_run() leaves in the two extra slots: the halo cells of t-1 / t
+    coef = _coef32(R)
+    i3 = lambda x: (ctypes.c_int * 3)(*x)
+    rc = emul().tt_emul_run(R, variant, mode, p[0].ctypes.data, p[1].ctypes.data, v.ctypes.data, out1.ctypes.data, out2.ctypes.data,
+                            ctypes.cast(i3(n), ctypes.c_void_p), ctypes.cast(i3(ppad), ctypes.c_void_p),
+                            ctypes.cast(i3(vpad), ctypes.c_void_p), coef.ctypes.data, grid, nchunks, int(lazy))
+    assert rc == 0, f"emulator protocol error {rc}"
+    halo = tuple(slice(ppad[d] - R, ppad[d] + n[d] + R) for d in range(3))
+    dom = tuple(slice(ppad[d], ppad[d] + n[d]) for d in range(3))
+    p0h, p1h = np.ascontiguousarray(p[0][halo]), np.ascontiguousarray(p[1][halo])
+    # the oracle's first argument is p(t), its second the slot that holds p(t-1) (yask_oracle.c: yo_iso3dfd_run_f32)
+    ref1 = O.iso3dfd_run(p1h, p0h, vcore, R, 1, mode)[R:-R, R:-R, R:-R]
+    ref2 = O.iso3dfd_run(p1h, p0h, vcore, R, 2, mode)[R:-R, R:-R, R:-R]
+    # halo cells of the outputs are untouched
+    for o, src in ((out1, p[0]), (out2, p[1])):
+        m = np.ones(pshape, dtype=bool)
+        m[dom] = False
+        assert np.array_equal(o[m].view(np.uint32), src[m].view(np.uint32))
+    return out1[dom], out2[dom], ref1, ref2
+
+
+def check(*a, **k):
+    g1, g2, r1, r2 = run_case(*a, **k)
+    assert np.array_equal(g1.view(np.uint32), np.ascontiguousarray(r1).view(np.uint32)), "p(t+1) differs from the oracle"
+    assert np.array_equal(g2.view(np.uint32), np.ascontiguousarray(r2).view(np.uint32)), "p(t+2) differs from the oracle"
+
+
+# small tile variant (4 x 16): many tiles, rounds and unit boundaries per CTA in a small domain
+@pytest.mark.parametrize("lazy", [0, 1])
+@pytest.mark.parametrize("radius", [1, 2])
+@pytest.mark.parametrize("n,grid,nchunks", [((13, 9, 40), 3, 2), ((6, 4, 16), 1, 1), ((20, 11, 37), 5, 4), ((9, 3, 7), 2, 3), ((31, 8, 32), 64, 2)])
+def test_small_tile_matches_oracle(radius, n, grid, nchunks, lazy):
+    check(radius, 1, 2, n, (radius, radius, 4), (0, 0, 0), grid, nchunks, lazy)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("radius", [1, 2])
+def test_fp_modes_and_wide_pads(radius, mode):
+    # pads wider than the halo (NaN beyond the halo) as the engine's 128-byte-aligned layout has them
+    check(radius, 1, mode, (10, 7, 21), (radius + 1, radius + 3, 8), (1, 2, 4), 2, 2, 1)
+    check(radius, 1, mode, (10, 7, 21), (radius + 1, radius + 3, 8), (1, 2, 4), 2, 2, 0)
+
+
+# the shipped tiles (16 x 128, 256 threads): ragged in y and z, one and several tiles, chunk boundaries
+@pytest.mark.parametrize("lazy", [0, 1])
+@pytest.mark.parametrize("radius", [1, 2])
+@pytest.mark.parametrize("n,grid,nchunks", [((12, 20, 150), 2, 1), ((17, 33, 260), 4, 2), ((9, 16, 128), 1, 3)])
+def test_shipped_tile_matches_oracle(radius, n, grid, nchunks, lazy):
+    check(radius, 0, 2, n, (radius, radius, 32), (0, 0, 32), grid, nchunks, lazy)

@@ -430,6 +430,9 @@ int yb_solution_prepare(yb_solution* s_, int device) {
     s->device = device;
     if (!s->own_stream) YB_CUDA(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     if (!s->comm_stream) YB_CUDA(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+    // extra storage slots serve the temporal tile, which runs on single-rank solutions only (the halo layer's peer
+    // addressing assumes the reference's slot count)
+    if (s->multi_rank()) for (auto& v : s->vars) if (!v.dev) v.extra_slots = 0;
     for (auto& v : s->vars) {
         const int64_t fvs = v.first_valid_step;
         const size_t had = v.dev ? v.bytes() : 0;
@@ -569,7 +572,7 @@ int yb_var_fuse(yb_solution* s_, int var, yb_solution* src_, int src_var) {
     }
     if (s->prepared || d.dev) {
         // geometry of `var` is known: it must match the source's allocation exactly
-        bool same = d.step_alloc() == o.step_alloc() && d.slot_elems == o.slot_elems;
+        bool same = d.step_alloc() == o.step_alloc() && d.extra_slots == o.extra_slots && d.slot_elems == o.slot_elems;
         for (size_t i = 0; i < d.dims.size() && same; i++)
             same = d.dims[i].alloc == o.dims[i].alloc && d.dims[i].pad_l == o.dims[i].pad_l && d.dims[i].stride == o.dims[i].stride &&
                    d.dims[i].domain == o.dims[i].domain;
@@ -577,6 +580,7 @@ int yb_var_fuse(yb_solution* s_, int var, yb_solution* src_, int src_var) {
     } else {
         // not prepared yet: adopt the source's geometry now; prepare() checks that it is what the solution needs
         d.spec.step_alloc = o.spec.step_alloc;
+        d.extra_slots = o.extra_slots;
         for (size_t i = 0; i < d.dims.size(); i++) {
             const DimSpec keep = d.dims[i].spec;
             d.dims[i] = o.dims[i];
@@ -657,7 +661,7 @@ int yb_var_set_all_same(yb_solution* s_, int var, double value) {
     if (!s->prepared) return set_error(YB_ESTATE, "var storage is not allocated: call prepare_solution first");
     Var& v = s->vars[var];
     YB_CUDA(cudaSetDevice(s->device));
-    if (int rc = launch_fill_all(v.dev, v.slot_elems * v.step_alloc(), v.elem_bytes, value, s->stream())) return rc;
+    if (int rc = launch_fill_all(v.dev, v.slot_elems * v.nslots(), v.elem_bytes, value, s->stream())) return rc;
     if (s->halo) halo_mark_dirty(*s, var);
     return 0;
 }
@@ -802,7 +806,27 @@ int yb_solution_run(yb_solution* s_, int64_t first_step, int64_t last_step) {
     if (s->halo) rc = halo_exchange_all(*s, st);  // initial exchange of everything dirty (context.cpp:346)
     // direction from the order of the arguments, as the reference does (context.cpp:237-246)
     const int64_t step_dir = last_step >= first_step ? 1 : -1;
-    for (int64_t t = first_step; t != last_step + step_dir && rc >= 0; t += step_dir) {
+    if (rc >= 0) rc = s->engine->begin_run(*s, first_step, st);
+    // Temporal tile (the reference's "-bt", context.cpp:657-681): a forward single-rank run goes through the engine's fused
+    // launch, `fs` steps at a time; what is left over (and every other kind of run) takes the one-step path below.
+    int64_t t_first = first_step;
+    const int fs = (step_dir > 0 && !s->halo && !s->tuner.enabled) ? s->engine->fused_steps(*s) : 1;
+    while (fs > 1 && rc >= 0 && last_step - t_first + 1 >= fs) {
+        rc = s->engine->launch_steps(*s, t_first, fs, whole, st);
+        if (rc < 0) break;
+        s->stats.kernel_launches += rc;
+        for (int k = 0; k < fs; k++) {
+            for (const StageSpec& sp : s->spec.stages) {
+                s->stats.num_writes_done += sp.writes * pts;
+                s->stats.num_reads_done += sp.reads * pts;
+                s->stats.est_fp_ops_done += sp.fp_ops * pts;
+                for (int vi : sp.outputs) s->vars[vi].update_valid_step(t_first + k + sp.out_step_off);
+            }
+            s->stats.num_steps_done++;
+        }
+        t_first += fs;
+    }
+    for (int64_t t = t_first; t != last_step + step_dir && rc >= 0; t += step_dir) {
         // in-run auto-tuner (/root/reference/src/kernel/lib/auto_tuner.cpp, context.cpp:592-600): this step runs with the next
         // untried launch variant and is timed on its own; once every variant has its samples the fastest stays selected
         cudaEvent_t te0 = nullptr, te1 = nullptr;

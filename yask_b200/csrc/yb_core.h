@@ -76,19 +76,27 @@ struct Var {
     int elem_bytes = 4;
     int64_t slot_elems = 0;
     int64_t first_valid_step = 0;  // local offset of the step dim
-    void* dev = nullptr;           // step_alloc * slot_elems elements
+    void* dev = nullptr;           // nslots() * slot_elems elements
     // Solution vars own their storage through `store` (cudaFree on the last release): yk_var::fuse_vars makes two vars --
     // possibly of two solutions -- share one allocation (/root/reference/src/kernel/lib/yk_var_apis.cpp:334-360).
     std::shared_ptr<void> store;
+    // Spare storage slots beyond the `step_alloc` steps the API can see.  A temporal tile writes steps t+1 and t+2 while
+    // overlapping tiles still read the halo cells of t-1 and t, so it cannot update in place: the engine asks for a second
+    // set of `step_alloc` slots (yb_iso3dfd.cu) and the fused launch ping-pongs between the two sets (`slot_bias` = first
+    // slot of the live set).  Everything else -- the API's valid-step window, the wrap of step indices onto `step_alloc`
+    // slots, in-place one-step launches -- sees exactly the reference's storage.
+    int extra_slots = 0;
+    int slot_bias = 0;
     bool has_step() const { return !dims.empty() && dims[0].spec.kind == DIM_STEP; }
     int step_alloc() const { return has_step() ? spec.step_alloc : 1; }
+    int nslots() const { return has_step() ? spec.step_alloc + extra_slots : 1; }
     int64_t last_valid_step() const { return first_valid_step + step_alloc() - 1; }
-    size_t bytes() const { return size_t(slot_elems) * step_alloc() * elem_bytes; }
+    size_t bytes() const { return size_t(slot_elems) * nslots() * elem_bytes; }
     // storage slot of a step index: imod_flr(t, alloc_t) (/root/reference/src/kernel/lib/yk_var.hpp:131-147)
     int slot_of(int64_t t) const {
         int a = step_alloc();
         int64_t c = t % a;
-        return int(c < 0 ? c + a : c);
+        return int(c < 0 ? c + a : c) + slot_bias;
     }
     char* slot_ptr(int slot) const { return static_cast<char*>(dev) + size_t(slot) * slot_elems * elem_bytes; }
     // element offset (within a slot) of the var's domain origin / first misc index
@@ -142,6 +150,13 @@ struct Engine {
     // result of a launch depends on what an earlier launch of the same stage wrote (scratch vars computed from vars the
     // stage updates in place).
     virtual bool can_split(const Solution&, int /*stage*/) const { return true; }
+    // Temporal tiling (the reference's block steps, "-bt"; /root/reference/src/kernel/lib/context.cpp:657-681): how many
+    // consecutive steps one launch_steps() call may fuse for a forward run over the whole rank box (1 = no temporal tile).
+    virtual int fused_steps(const Solution&) const { return 1; }
+    // called once per run_solution() before the first step (first_step = t of the first launch)
+    virtual int begin_run(Solution&, int64_t /*first_step*/, cudaStream_t) { return 0; }
+    // all stages of steps t+1 .. t+nsteps in one go; returns #kernels launched or <0
+    virtual int launch_steps(Solution&, int64_t /*t*/, int /*nsteps*/, const Box&, cudaStream_t) { return YB_EUNSUPPORTED; }
 };
 
 struct HaloState;  // yb_halo.cu

@@ -201,7 +201,7 @@ int halo_prepare(Solution& s) {
     YB_CUDA(cudaEventCreateWithFlags(&h->comm_ev, cudaEventDisableTiming));
     YB_CUDA(cudaEventCreateWithFlags(&h->ext_ev, cudaEventDisableTiming));
     h->dirty.resize(s.vars.size());
-    for (size_t i = 0; i < s.vars.size(); i++) h->dirty[i].assign(s.vars[i].step_alloc(), 1);  // everything starts dirty (context.hpp:545-549)
+    for (size_t i = 0; i < s.vars.size(); i++) h->dirty[i].assign(s.vars[i].nslots(), 1);  // everything starts dirty (context.hpp:545-549)
     int d[3];
     for (d[0] = -1; d[0] <= 1; d[0]++)
         for (d[1] = -1; d[1] <= 1; d[1]++)
@@ -351,7 +351,7 @@ static int halo_exchange_impl(Solution& s, cudaStream_t st, int skip_var, bool s
         for (size_t vi = 0; vi < s.vars.size(); vi++) {
             if (!var_talks_to(s.vars[vi], nb.dir)) continue;
             if (int(vi) == skip_var && pure_x) continue;   // done by the kernel
-            for (int slot = 0; slot < s.vars[vi].step_alloc(); slot++) {
+            for (int slot = 0; slot < s.vars[vi].nslots(); slot++) {
                 if (!h->dirty[vi][slot]) continue;
                 int rc = push_var_slot(s, nb, int(vi), slot, ps);
                 if (rc < 0) return rc;

@@ -11,6 +11,7 @@
 #include "yb_core.h"
 #include "yb_iso3dfd.cuh"
 #include "yb_iso3dfd_tiles.h"
+#include "yb_iso3dfd_tt.cuh"
 
 namespace yb {
 
@@ -198,6 +199,39 @@ const TileCfg& tile_cfg(int i) {
     return cfgs[i];
 }
 
+// ---- temporal tile (yb_iso3dfd_tt.cuh): compiled variants per radius and FP mode ----
+typedef void (*TTKernelFn)(const TTMaps, const TTParams);
+struct TTCfg {
+    const char* name;
+    int ty, tz, iy, iz, s1y, s1z, threads, warm;   // warm = 4R warm-up iterations per chunk
+    uint32_t smem;
+    TTKernelFn fn[3];
+};
+template <class T>
+TTCfg tt_cfg(const char* name) {
+    return TTCfg{name, T::TY, T::TZ, T::IY, T::IZ, T::S1Y, T::S1Z, T::THREADS, 4 * T::R, T::SMEM_BYTES,
+                 {iso3dfd_tt2_kernel<T, 0>, iso3dfd_tt2_kernel<T, 1>, iso3dfd_tt2_kernel<T, 2>}};
+}
+const TTCfg* tt_radius_cfg(int radius) {
+    static const TTCfg cfgs[TT_MAX_R] = {tt_cfg<TTile<1, 16, 128, 3, 256>>("r1 2 steps, tile 16x128, 3 planes ahead"),
+                                         tt_cfg<TTile<2, 16, 128, 2, 256>>("r2 2 steps, tile 16x128, 2 planes ahead")};
+    return (radius >= 1 && radius <= TT_MAX_R) ? &cfgs[radius - 1] : nullptr;
+}
+
+// Copies a box of cells from one step slot to another (same geometry): keeps the halo cells of the extra storage
+// slots of a temporally tiled var equal to those of the slot two steps earlier -- what the reference's two-slot storage
+// gives by construction (p(t+2) lives in the memory of p(t), halo cells included).
+__global__ void slot_box_copy_kernel(float* dst, const float* src, long long sx, long long sy, int bx, int by, int bz, int ex, int ey, int ez) {
+    const long long n = (long long)ex * ey * ez;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int z = int(i % ez);
+        const long long r = i / ez;
+        const int y = int(r % ey), x = int(r / ey);
+        const long long o = (long long)(bx + x) * sx + (long long)(by + y) * sy + (bz + z);
+        dst[o] = src[o];
+    }
+}
+
 struct IsoEngine : Engine {
     int radius = 8;
     double coef[ISO_MAX_R + 1] = {0};
@@ -213,10 +247,16 @@ struct IsoEngine : Engine {
     int pol_c = 2, pol_h = 2, pol_pv = 1, st_cs = 1;
     bool mem_probe = false;      // debug: fp_mode=3 style memory-only kernel
     int peer_probe = 0;          // debug: see IsoParams::peer_probe
-    IsoMaps maps[NTILES][2];       // [tile][cur slot]
+    IsoMaps maps[NTILES][4];       // [tile][slot of p(t)]; p(t-1) is its partner (slot ^ 1) in the live pair of slots
     bool maps_ok = false;
+    // temporal tile: option block_steps (the reference's -bt).  It needs two storage slots beyond the two the API sees
+    // (Var::extra_slots), so it must be asked for before prepare_solution(); later changes only switch the launch path.
+    int block_steps = 1;
+    bool tt_ok = false;            // extra slots allocated and tensor maps built
+    TTMaps tt_maps[4];             // [slot of p(t)]
+    bool tt_attr_set[3] = {};
 
-    int set_option(Solution&, const std::string& k, const std::string& v) override {
+    int set_option(Solution& s, const std::string& k, const std::string& v) override {
         if (k == "kernel") {
             if (v != "auto" && v != "tma" && v != "direct") return YB_EINVAL;
             kernel = v;
@@ -233,6 +273,23 @@ struct IsoEngine : Engine {
         else if (k == "pol_h") { pol_h = atoi(v.c_str()); }
         else if (k == "pol_pv") { pol_pv = atoi(v.c_str()); }
         else if (k == "st_cs") { st_cs = atoi(v.c_str()) != 0; }
+        else if (k == "block_steps") {
+            block_steps = std::max(1, atoi(v.c_str()));
+            if (!s.prepared && s.vars.size() >= 2) {
+                const bool on = block_steps >= 2 && s.spec.radius <= TT_MAX_R && s.spec.elem_bytes == 4;
+                s.vars[0].extra_slots = on ? 2 : 0;
+                if (on) {
+                    // the tile's boxes reach 2R rows / planes (p) and R rows / planes, one 16-byte vector in z (v) below the
+                    // domain origin: pad that far, so that no TMA coordinate is ever negative (boxes that stick out at the
+                    // upper end are zero-filled by the hardware, as in the one-step kernels on ragged domains)
+                    const int R = s.spec.radius;
+                    for (Dim& d : s.vars[0].dims)
+                        if (d.spec.kind == DIM_DOMAIN) d.min_pad_l = std::max<int64_t>(d.min_pad_l, d.spec.domain_index == 2 ? 8 : 2 * R);
+                    for (Dim& d : s.vars[1].dims)
+                        if (d.spec.kind == DIM_DOMAIN) d.min_pad_l = std::max<int64_t>(d.min_pad_l, d.spec.domain_index == 2 ? 4 : R);
+                }
+            }
+        }
         else return YB_EINVAL;
         return 0;
     }
@@ -241,6 +298,7 @@ struct IsoEngine : Engine {
         else if (k == "tile") v = std::to_string(tile);
         else if (k == "lx") v = std::to_string(lx);
         else if (k == "grid") v = std::to_string(grid_override);
+        else if (k == "block_steps") v = std::to_string(block_steps);
         else return false;
         return true;
     }
@@ -254,20 +312,34 @@ struct IsoEngine : Engine {
         YB_CUDA(cudaGetDeviceProperties(&prop, s.device));
         num_sms = prop.multiProcessorCount;
         maps_ok = false;
+        tt_ok = false;
+        const int nsl = s.vars[0].nslots();
+        if (nsl > 4) return set_error(YB_EUNSUPPORTED, "iso3dfd: at most 4 storage slots of p");
         if (prop.major >= 9 && (radius == 8 || iso_radius_cfg(radius))) {
             const Var& p = s.vars[0];
             const Var& v = s.vars[1];
             for (int tl = 0; tl < (radius == 8 ? NTILES : 1); tl++) {
                 const TileCfg& c = radius == 8 ? tile_cfg(tl) : *iso_radius_cfg(radius);
-                for (int cur = 0; cur < 2; cur++) {
+                for (int cur = 0; cur < nsl; cur++) {
                     IsoMaps& m = maps[tl][cur];
                     if (int rc = make_map(&m.h, p, cur, c.hp, c.hrows)) return rc;
                     if (int rc = make_map(&m.c, p, cur, c.tz, c.ty)) return rc;
-                    if (int rc = make_map(&m.p, p, 1 - cur, c.tz, c.ty)) return rc;
+                    if (int rc = make_map(&m.p, p, cur ^ 1, c.tz, c.ty)) return rc;
                     if (int rc = make_map(&m.v, v, 0, c.tz, c.ty)) return rc;
                 }
             }
             maps_ok = true;
+            if (const TTCfg* tc = (p.extra_slots == 2 && nsl == 4) ? tt_radius_cfg(radius) : nullptr) {
+                for (int cur = 0; cur < nsl; cur++) {
+                    TTMaps& m = tt_maps[cur];
+                    if (int rc = make_map(&m.pin, p, cur, tc->iz, tc->iy)) return rc;
+                    if (int rc = make_map(&m.prev, p, cur ^ 1, tc->s1z, tc->s1y)) return rc;
+                    if (int rc = make_map(&m.v, v, 0, tc->s1z, tc->s1y)) return rc;
+                }
+                tt_ok = true;
+                for (int m = 0; m < 3; m++) preload_kernel((const void*)tc->fn[m]);
+                preload_kernel((const void*)slot_box_copy_kernel);
+            }
             const TileCfg& c = radius == 8 ? tile_cfg(tile) : *iso_radius_cfg(radius);
             for (int m = 0; m < 4; m++) preload_kernel((const void*)c.fn[m]);
         }
@@ -277,12 +349,15 @@ struct IsoEngine : Engine {
         return 0;
     }
 
-    void fill_params(const Solution& s, int cur, const Box& box, IsoParams& P) const {
+    void fill_params(const Solution& s, int64_t t, const Box& box, IsoParams& P) const {
         const Var& p = s.vars[0];
         const Var& v = s.vars[1];
+        const int cur = p.slot_of(t);
         const Dim *px = p.domain_dim(0), *py = p.domain_dim(1), *pz = p.domain_dim(2);
         const Dim *vx = v.domain_dim(0), *vy = v.domain_dim(1), *vz = v.domain_dim(2);
-        P.out = reinterpret_cast<float*>(p.slot_ptr(1 - cur)) + p.origin_offset();
+        // p(t+1) is written over p(t-1) (/root/reference/src/compiler/lib/Var.cpp:435-464): slot_of(t+1) == slot_of(t-1)
+        P.out = reinterpret_cast<float*>(p.slot_ptr(p.slot_of(t + 1))) + p.origin_offset();
+        P.prev = reinterpret_cast<const float*>(p.slot_ptr(p.slot_of(t - 1))) + p.origin_offset();
         P.cur = reinterpret_cast<const float*>(p.slot_ptr(cur)) + p.origin_offset();
         P.vel = reinterpret_cast<const float*>(v.slot_ptr(0)) + v.origin_offset();
         P.out_sx = px->stride; P.out_sy = py->stride;
@@ -302,7 +377,7 @@ struct IsoEngine : Engine {
         const Var& p = s.vars[0];
         const int cur = p.slot_of(t);
         IsoParams P{};
-        fill_params(s, cur, box, P);
+        fill_params(s, t, box, P);
         int mode = s.fp_mode;
         bool use_tma = maps_ok && kernel != "direct";
         if (kernel == "auto") {
@@ -397,6 +472,99 @@ struct IsoEngine : Engine {
             }
         }
         YB_CUDA(cudaGetLastError());
+        return 1;
+    }
+
+    // ---- temporal tile -------------------------------------------------------------------------------------------
+    int fused_steps(const Solution& s) const override {
+        return (tt_ok && block_steps >= 2 && kernel != "direct" && !s.multi_rank()) ? 2 : 1;
+    }
+
+    // Halo cells of the spare pair of slots take those of the live pair, so that whichever pair a fused launch reads holds
+    // the halo cells the reference's two slots would (kernels never write halo cells; the API may, between runs).
+    int begin_run(Solution& s, int64_t, cudaStream_t st) override {
+        const Var& p = s.vars[0];
+        if (p.extra_slots != 2 || !p.dev) return 0;
+        const Dim* d[3] = {p.domain_dim(0), p.domain_dim(1), p.domain_dim(2)};
+        int64_t lo[3], hi[3], db[3], de[3];     // halo box and domain box in alloc coordinates
+        for (int k = 0; k < 3; k++) {
+            db[k] = d[k]->pad_l; de[k] = d[k]->pad_l + d[k]->domain;
+            lo[k] = db[k] - d[k]->spec.halo_l; hi[k] = de[k] + d[k]->spec.halo_r;
+        }
+        for (int pair = 0; pair < 2; pair++) {
+            const float* src = reinterpret_cast<const float*>(p.slot_ptr(p.slot_bias + pair));
+            float* dst = reinterpret_cast<float*>(p.slot_ptr((p.slot_bias ^ 2) + pair));
+            // shell = x slabs over the whole (y,z) halo box, y slabs over the domain's x range, z slabs over the domain's x and y ranges
+            const int64_t slabs[6][6] = {{lo[0], db[0], lo[1], hi[1], lo[2], hi[2]}, {de[0], hi[0], lo[1], hi[1], lo[2], hi[2]},
+                                         {db[0], de[0], lo[1], db[1], lo[2], hi[2]}, {db[0], de[0], de[1], hi[1], lo[2], hi[2]},
+                                         {db[0], de[0], db[1], de[1], lo[2], db[2]}, {db[0], de[0], db[1], de[1], de[2], hi[2]}};
+            for (auto& b : slabs) {
+                const int64_t ex = b[1] - b[0], ey = b[3] - b[2], ez = b[5] - b[4];
+                if (ex <= 0 || ey <= 0 || ez <= 0) continue;
+                const int64_t n = ex * ey * ez;
+                const int grid = int(std::min<int64_t>((n + 255) / 256, 16 * num_sms));
+                slot_box_copy_kernel<<<grid, 256, 0, st>>>(dst, src, d[0]->stride, d[1]->stride, int(b[0]), int(b[2]), int(b[4]), int(ex), int(ey), int(ez));
+            }
+        }
+        YB_CUDA(cudaGetLastError());
+        return 0;
+    }
+
+    // Steps t+1 and t+2 in one sweep (iso3dfd_tt2_kernel): reads the live pair of slots (p(t-1), p(t)), writes p(t+1) / p(t+2)
+    // into the partners of p(t-1) / p(t) in the spare pair, which then becomes the live one.
+    int launch_steps(Solution& s, int64_t t, int nsteps, const Box& box, cudaStream_t st) override {
+        if (nsteps != 2 || !tt_ok) return set_error(YB_EUNSUPPORTED, "iso3dfd: no temporal tile for %d steps in this configuration", nsteps);
+        if (box.empty()) return 0;
+        const TTCfg& c = *tt_radius_cfg(radius);
+        Var& p = s.vars[0];
+        const Var& v = s.vars[1];
+        const Dim *px = p.domain_dim(0), *py = p.domain_dim(1), *pz = p.domain_dim(2);
+        const Dim *vx = v.domain_dim(0), *vy = v.domain_dim(1), *vz = v.domain_dim(2);
+        for (int k = 0; k < 3; k++)
+            if (box.b[k] != 0 || box.e[k] != p.domain_dim(k)->domain) return set_error(YB_EUNSUPPORTED, "iso3dfd: the temporal tile runs on the whole rank domain");
+        TTParams P{};
+        const int cur = p.slot_of(t), prev = p.slot_of(t - 1);      // prev == cur ^ 1 (tensor maps)
+        P.out1 = reinterpret_cast<float*>(p.slot_ptr(prev ^ 2)) + p.origin_offset();
+        P.out2 = reinterpret_cast<float*>(p.slot_ptr(cur ^ 2)) + p.origin_offset();
+        P.vel = reinterpret_cast<const float*>(v.slot_ptr(0)) + v.origin_offset();
+        P.p_sx = px->stride; P.p_sy = py->stride; P.v_sx = vx->stride; P.v_sy = vy->stride;
+        P.nx = int(px->domain); P.ny = int(py->domain); P.nz = int(pz->domain);
+        P.pad_x = int(px->pad_l); P.pad_y = int(py->pad_l); P.pad_z = int(pz->pad_l);
+        P.vpad_x = int(vx->pad_l); P.vpad_y = int(vy->pad_l); P.vpad_z = int(vz->pad_l);
+        for (int r = 0; r <= TT_MAX_R; r++) P.c[r] = r <= radius ? float(coef[r]) : 0.f;
+        P.nty = (P.ny + c.ty - 1) / c.ty;
+        P.ntz = (P.nz + c.tz - 1) / c.tz;
+        // x chunks of (almost) equal length: minimise (rounds of units per CTA) x (chunk length + warm-up iterations;
+        // those of the first 2R only load, the next 2R only run step 1)
+        const int64_t ntile = int64_t(P.nty) * P.ntz;
+        const int gmax = grid_override > 0 ? grid_override : num_sms;
+        const int64_t max_nc = std::min<int64_t>(TT_MAX_CHUNKS, P.nx);
+        int nc_best = 1;
+        if (lx > 0) nc_best = int(std::max<int64_t>(1, std::min<int64_t>((P.nx + lx - 1) / lx, max_nc)));
+        else {
+            double best = 1e30;
+            for (int64_t nc = 1; nc <= max_nc; nc++) {
+                const int64_t l = (P.nx + nc - 1) / nc;
+                const int64_t rounds = (ntile * nc + gmax - 1) / gmax;
+                const double cost = double(rounds) * (double(l) + c.warm * 0.4);
+                if (cost < best * 0.999) { best = cost; nc_best = int(nc); }
+            }
+        }
+        P.nchunks = nc_best;
+        for (int k = 0; k < nc_best; k++) {
+            const int64_t x0 = int64_t(P.nx) * k / nc_best, x1 = int64_t(P.nx) * (k + 1) / nc_best;
+            P.cx0[k] = int(x0); P.clen[k] = int(x1 - x0);
+        }
+        const int64_t nunits = ntile * P.nchunks;
+        const int grid = int(std::min<int64_t>(nunits, gmax));
+        const int mode = std::min(std::max(s.fp_mode, 0), 2);
+        if (!tt_attr_set[mode]) {
+            YB_CUDA(cudaFuncSetAttribute(c.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
+            tt_attr_set[mode] = true;
+        }
+        c.fn[mode]<<<grid, c.threads, c.smem, st>>>(tt_maps[cur], P);
+        YB_CUDA(cudaGetLastError());
+        p.slot_bias ^= 2;       // steps t+1, t+2 (and every later access, stream-ordered) live in the other pair now
         return 1;
     }
 

@@ -15,6 +15,7 @@
 #include <type_traits>
 
 #include "yb_ptx.cuh"
+#include "yb_iso3dfd_math.cuh"
 
 namespace yb {
 
@@ -25,6 +26,7 @@ struct IsoParams {
     float* out;             // &p_next[domain origin]; written in place over p(t-1)
     long long out_sx, out_sy;  // element strides of the p arrays (z stride is 1)
     const float* cur;       // &p_cur[domain origin]  (naive kernel only)
+    const float* prev;      // &p_prev[domain origin] (naive kernel only): == out unless the var has extra storage slots
     const float* vel;       // &v[domain origin]      (naive kernel only)
     long long v_sx, v_sy;
     int nx, ny, nz;         // rank-domain sizes
@@ -64,34 +66,6 @@ struct IsoParams {
     float c[ISO_MAX_R + 1];
 };
 
-template <int MODE>
-__device__ __forceinline__ float iso_group(float acc, float pc, float c0, float cr, float xm, float xp, float ym, float yp,
-                                           float zm, float zp, bool first) {
-    float s = __fadd_rn(xm, xp);
-    s = __fadd_rn(s, ym);
-    s = __fadd_rn(s, yp);
-    s = __fadd_rn(s, zm);
-    s = __fadd_rn(s, zp);
-    if (MODE == 0) {
-        if (first) acc = __fmul_rn(pc, c0);
-        return __fadd_rn(acc, __fmul_rn(s, cr));
-    } else if (MODE == 1) {
-        if (first) acc = __fmul_rn(pc, c0);
-        return __fmaf_rn(s, cr, acc);
-    } else {
-        if (first) return __fmaf_rn(pc, c0, __fmul_rn(s, cr));
-        return __fmaf_rn(s, cr, acc);
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ float iso_final(float acc, float pc, float prev, float v) {
-    // 2*p is exact, so fma(2,p,-prev) == round((2*p) - prev): one instruction, same bits.
-    float lhs = __fmaf_rn(2.0f, pc, -prev);
-    if (MODE == 0) return __fadd_rn(lhs, __fmul_rn(acc, v));
-    return __fmaf_rn(acc, v, lhs);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Reference-order direct kernel: one thread per point, straight global loads (through L1/L2).
 // Used for radii/shapes the tiled kernel does not cover and as the on-device cross-check of the
@@ -112,7 +86,7 @@ __global__ void __launch_bounds__(256) iso3dfd_direct_kernel(IsoParams P, int R)
                               pc[r * P.out_sy], pc[-r], pc[r], r == 1);
     }
     const float v = P.vel[(long long)x * P.v_sx + (long long)y * P.v_sy + z];
-    P.out[o] = iso_final<MODE>(acc, center, P.out[o], v);
+    P.out[o] = iso_final<MODE>(acc, center, P.prev[o], v);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -48,6 +48,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// Same wait, but a barrier that does not complete within a few seconds traps (the launch fails with an error) instead of
+// hanging the GPU: used by kernels whose barrier protocol is newer than their test history.
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+    for (uint32_t spins = 0;; spins++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins == 64) t0 = clock64();
+        else if (spins > 64 && (spins & 63u) == 0 && clock64() - t0 > 6000000000LL) __trap();
+    }
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

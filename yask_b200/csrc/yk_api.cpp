@@ -511,8 +511,12 @@ struct B200Solution : yk_solution {
     idx_t get_overall_domain_size(const std::string& dim) const override { return yb_get_overall_domain_size(h->s, dpos(dim, "get_overall_domain_size")); }
     idx_t_vec get_overall_domain_size_vec() const override { return get_vec(yb_get_overall_domain_size); }
     // Block sizes steer the reference's CPU tiling only; they are recorded so that callers read back what they set.
+    // The STEP block size is the exception: it is the reference's temporal blocking (-bt, context.cpp:657-681) and selects
+    // the engine's temporal tile where one exists (iso3dfd radius <= 2: two steps per sweep; needs extra storage, so it has
+    // to be set before prepare_solution() to take effect).  Results never depend on it.
     void set_block_size(const std::string& dim, idx_t size) override {
         if (dim != get_step_dim_name()) dpos(dim, "set_block_size");
+        else (void)yb_set_option(h->s, "block_steps", std::to_string(size < 1 ? 1 : size).c_str());    // engines without one refuse: fine
         block_size[dim] = size;
     }
     void set_block_size_vec(const idx_t_vec& v) override { auto d = get_domain_dim_names(); if (v.size() != d.size()) fail("set_block_size_vec: wrong number of values"); for (size_t k = 0; k < d.size(); k++) block_size[d[k]] = v[k]; }
@@ -546,7 +550,7 @@ struct B200Solution : yk_solution {
                                              "force_scalar_exchange", "bundle_allocs", "bind_inner_threads", "allow_addl_padding", "use_device_mpi",
                                              "print_suffixes", "trace", "validate", "find_loc"};
         static const char* ignored_val[] = {"outer_threads", "inner_threads", "max_threads", "thread_divisor", "numa_pref", "msg_rank", "min_exterior",
-                                            "auto_tune_trial_secs", "auto_tune_radius", "auto_tune_targets", "Mbt", "bt", "mbt", "ep", "mp_extra"};
+                                            "auto_tune_trial_secs", "auto_tune_radius", "auto_tune_targets", "Mbt", "mbt", "ep", "mp_extra"};
         for (size_t a = 0; a < args.size(); a++) {
             const std::string& arg = args[a];
             bool used = false;
@@ -556,6 +560,7 @@ struct B200Solution : yk_solution {
                 // -[no-]overlap_comms (the reference's switch for exterior-first evaluation, settings.cpp) selects the same thing here
                 if (key == "auto_tune" || key == "no-auto_tune") { chk(yb_solution_reset_auto_tuner(h->s, key[0] == 'n' ? 0 : 1)); used = true; }
                 if (key == "overlap_comms" || key == "no-overlap_comms") { chk(yb_set_option(h->s, "overlap_comms", key[0] == 'n' ? "0" : "1")); used = true; }
+                if (key == "bt") { set_block_size(get_step_dim_name(), atoll(take().c_str())); used = true; }     // temporal tile
                 if (!used) for (auto* b : ignored_bool) if (key == b || key == std::string("no-") + b) used = true;
                 if (!used) for (auto* v : ignored_val) if (key == v) { take(); used = true; }
                 if (!used) {
@@ -598,6 +603,7 @@ struct B200Solution : yk_solution {
         return " -g<dim> <n>   overall domain size        -l<dim> <n>   rank domain size\n"
                " -nr<dim> <n>  ranks in dim               -ri<dim> <n>  rank index in dim\n"
                " -mp<dim> <n>  minimum padding            -b<dim> <n>   block size (recorded; no effect on the GPU)\n"
+               " -bt <n>       block steps: n >= 2 selects the temporal tile where the engine has one (iso3dfd radius <= 2)\n"
                " -fp_mode 0|1|2  FP contraction mode      -kernel auto|tma|direct   -tile <n>   -lx <n>   -device <n>\n";
     }
     std::string get_command_line_values() override {
