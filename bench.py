@@ -344,19 +344,21 @@ def run_secondary(args, dist, rank, world, local, peak, want_cpu):
     if world == 1 and rank == 0:
         # temporal tile (north_star: "temporal tiling applies multiple time-steps inside shared memory where the radius allows"):
         # iso3dfd radius 2, one-step sweep against two steps per sweep, in a subprocess of its own
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench_temporal.py"), str(args.size), "2", "20"], capture_output=True, text=True, timeout=240)
-            tl = json.loads(r.stdout.strip().splitlines()[-1])
-            tt = tl["temporal_tile"]
-            out.append({"workload": tl["workload"], "metric": "GPoints/s", "value": tt["gpoints_per_s"], "unit": "GPoints/s", "n_gpus": 1, "steps": tl["steps"],
-                        "ms_per_step": tt["ms_per_step"], "dtype": "f32", "gpu_launches": tt["kernel_launches"],
-                        "one_step_value": tl["one_step"]["gpoints_per_s"], "speedup_vs_one_step": tl["speedup"], "bit_identical_to_one_step": tl["bit_identical"],
-                        "roofline": {"bound": "hbm", "achieved": tt["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": tt["frac"], "traffic": None,
-                                     "algorithmic_bytes_per_point_step": 10, "frac_at_16B_per_point_step": tt["frac_16B"],
-                                     "note": "20 B per point and PAIR of steps (p(t-1), p(t), v in; p(t+1), p(t+2) out); the one-step sweep moves 16 B per step"},
-                        "one_step": tl["one_step"]})
-        except Exception as e:
-            out.append({"workload": "iso3dfd radius 2 fp32, temporal tile (2 steps per sweep)", "error": repr(e)[:300]})
+        for radius in (1, 2):
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "bench_temporal.py"), str(args.size), str(radius), "20"], capture_output=True, text=True, timeout=240)
+                tl = json.loads(r.stdout.strip().splitlines()[-1])
+                tt = tl["temporal_tile"]
+                out.append({"workload": tl["workload"], "metric": "GPoints/s", "value": tt["gpoints_per_s"], "unit": "GPoints/s", "n_gpus": 1, "steps": tl["steps"],
+                            "ms_per_step": tt["ms_per_step"], "dtype": "f32", "gpu_launches": tt["kernel_launches"],
+                            "one_step_value": tl["one_step"]["gpoints_per_s"], "speedup_vs_one_step": tl["speedup"], "bit_identical_to_one_step": tl["bit_identical"],
+                            "forms": tl.get("forms"),
+                            "roofline": {"bound": "hbm", "achieved": tt["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": tt["frac"], "traffic": None,
+                                         "algorithmic_bytes_per_point_step": 10, "frac_at_16B_per_point_step": tt["frac_16B"],
+                                         "note": "20 B per point and PAIR of steps (p(t-1), p(t), v in; p(t+1), p(t+2) out); the one-step sweep moves 16 B per step"},
+                            "one_step": tl["one_step"]})
+            except Exception as e:
+                out.append({"workload": f"iso3dfd radius {radius} fp32, temporal tile (2 steps per sweep)", "error": repr(e)[:300]})
     return out
 
 

@@ -14,10 +14,11 @@ from yask_b200 import capi
 from yask_b200.synth import var_salt
 
 
-def run(radius, n, block_steps, warm, steps):
+def run(radius, n, block_steps, warm, steps, variant=-1):
     s = capi.Solution("iso3dfd", radius=radius)
     s.set_overall_domain_size_vec((n, n, n))
     s.set_option("block_steps", block_steps)
+    s.set_option("tt_variant", variant)
     s.prepare_solution(0)
     p, v = s.get_var("p"), s.get_var("v")
     for t in (0, 1):
@@ -45,7 +46,11 @@ if __name__ == "__main__":
     except Exception:
         pass
     one = run(radius, n, 1, 4, steps)
-    tt = run(radius, n, 2, 4, steps)
+    forms = {"shared_memory": run(radius, n, 2, 4, steps, 0), "x_queues": run(radius, n, 2, 4, steps, 1)}
+    dflt = run(radius, n, 2, 4, steps)          # the engine's own choice of form
+    tt = dict(dflt)
+    for r in forms.values():
+        r["bit_identical"] = r["checksums"] == one["checksums"]
     for r, bpp in ((one, 16), (tt, 10)):
         r["algorithmic_bytes_per_point_step"] = bpp
         r["achieved_gbs"] = round(r["gpoints_per_s"] * bpp, 1)
@@ -53,4 +58,5 @@ if __name__ == "__main__":
     tt["frac_16B"] = round(tt["gpoints_per_s"] * 16 / peak, 4)
     print(json.dumps({"workload": f"iso3dfd radius {radius} fp32, {n}^3 points, 1 GPU: one-step sweep vs temporal tile (2 steps per sweep)",
                       "steps": steps, "warmup": 4, "peak_gbs": peak, "one_step": one, "temporal_tile": tt,
+                      "forms": {k: {"ms_per_step": v["ms_per_step"], "gpoints_per_s": v["gpoints_per_s"], "bit_identical": v["bit_identical"]} for k, v in forms.items()},
                       "bit_identical": one["checksums"] == tt["checksums"], "speedup": round(one["ms_per_step"] / tt["ms_per_step"], 4)}), flush=True)

@@ -149,7 +149,8 @@ int run_mode(int mode, const float* a, const float* b, const float* c, float* d,
 
 // p arrays: (nx+2*ppad[0], ny+2*ppad[1], nz+2*ppad[2]) floats, v: same with vpad.  out1 / out2 must arrive holding copies of
 // pprev / pcur (their halo cells are what the engine's begin_run() replicates); the domain parts are overwritten with
-// p(t+1) / p(t+2).  `variant`: 0 = the shipped tile of that radius, 1 = a small tile (more tiles and rounds per test).
+// p(t+1) / p(t+2).  `variant`: 0 = the shipped tile of that radius, 1 = a small tile (more tiles and rounds per test); 2, 3 = the same two
+// with the x neighbours in register queues (TTile XQ = 1).
 // Returns 0, or a protocol error code (see Emul).
 extern "C" int tt_emul_run(int radius, int variant, int mode, const float* pprev, const float* pcur, const float* vel, float* out1, float* out2,
                            const int* n, const int* ppad, const int* vpad, const float* coef, int grid, int nchunks, int lazy) {
@@ -157,5 +158,9 @@ extern "C" int tt_emul_run(int radius, int variant, int mode, const float* pprev
     if (radius == 2 && variant == 0) return run_mode<TTile<2, 16, 128, 2, 256>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
     if (radius == 1 && variant == 1) return run_mode<TTile<1, 4, 16, 2, 32>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
     if (radius == 2 && variant == 1) return run_mode<TTile<2, 4, 16, 1, 32>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 1 && variant == 2) return run_mode<TTile<1, 16, 128, 3, 256, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 2 && variant == 2) return run_mode<TTile<2, 16, 128, 3, 256, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 1 && variant == 3) return run_mode<TTile<1, 4, 16, 2, 32, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 2 && variant == 3) return run_mode<TTile<2, 4, 16, 1, 32, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
     return -2;
 }

@@ -79,23 +79,26 @@ def check(*a, **k):
 
 # small tile variant (4 x 16): many tiles, rounds and unit boundaries per CTA in a small domain
 @pytest.mark.parametrize("lazy", [0, 1])
+@pytest.mark.parametrize("xq", [0, 1])
 @pytest.mark.parametrize("radius", [1, 2])
 @pytest.mark.parametrize("n,grid,nchunks", [((13, 9, 40), 3, 2), ((6, 4, 16), 1, 1), ((20, 11, 37), 5, 4), ((9, 3, 7), 2, 3), ((31, 8, 32), 64, 2)])
-def test_small_tile_matches_oracle(radius, n, grid, nchunks, lazy):
-    check(radius, 1, 2, n, (radius, radius, 4), (0, 0, 0), grid, nchunks, lazy)
+def test_small_tile_matches_oracle(radius, n, grid, nchunks, lazy, xq):
+    check(radius, 1 + 2 * xq, 2, n, (radius, radius, 4), (0, 0, 0), grid, nchunks, lazy)
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("radius", [1, 2])
 def test_fp_modes_and_wide_pads(radius, mode):
     # pads wider than the halo (NaN beyond the halo) as the engine's 128-byte-aligned layout has them
-    check(radius, 1, mode, (10, 7, 21), (radius + 1, radius + 3, 8), (1, 2, 4), 2, 2, 1)
-    check(radius, 1, mode, (10, 7, 21), (radius + 1, radius + 3, 8), (1, 2, 4), 2, 2, 0)
+    for variant in (1, 3):
+        check(radius, variant, mode, (10, 7, 21), (radius + 1, radius + 3, 8), (1, 2, 4), 2, 2, 1)
+        check(radius, variant, mode, (10, 7, 21), (radius + 1, radius + 3, 8), (1, 2, 4), 2, 2, 0)
 
 
 # the shipped tiles (16 x 128, 256 threads): ragged in y and z, one and several tiles, chunk boundaries
 @pytest.mark.parametrize("lazy", [0, 1])
+@pytest.mark.parametrize("xq", [0, 1])
 @pytest.mark.parametrize("radius", [1, 2])
 @pytest.mark.parametrize("n,grid,nchunks", [((12, 20, 150), 2, 1), ((17, 33, 260), 4, 2), ((9, 16, 128), 1, 3)])
-def test_shipped_tile_matches_oracle(radius, n, grid, nchunks, lazy):
-    check(radius, 0, 2, n, (radius, radius, 32), (0, 0, 32), grid, nchunks, lazy)
+def test_shipped_tile_matches_oracle(radius, n, grid, nchunks, lazy, xq):
+    check(radius, 2 * xq, 2, n, (radius, radius, 32), (0, 0, 32), grid, nchunks, lazy)

@@ -39,12 +39,13 @@ def result(s):
     return p.get_elements_in_slice(*p.domain_box(tl)), p.get_elements_in_slice(*p.domain_box(tl - 1))
 
 
+@pytest.mark.parametrize("variant", [0, 1])     # 0: neighbours from shared memory, 1: x neighbours in register queues
 @pytest.mark.parametrize("fp_mode", [2, 0])
 @pytest.mark.parametrize("steps", [2, 3, 4, 7])
 @pytest.mark.parametrize("R,n", [(2, (40, 37, 150)), (1, (33, 20, 260)), (2, (9, 16, 128)), (1, (64, 48, 64))])
-def test_temporal_tile_bit_exact_vs_oracle(R, n, steps, fp_mode):
+def test_temporal_tile_bit_exact_vs_oracle(R, n, steps, fp_mode, variant):
     ins = synth(n, 21, R)
-    s = make(n, R, ins, 2, fp_mode)
+    s = make(n, R, ins, 2, fp_mode, {"tt_variant": variant})
     s.run_solution(0, steps - 1)
     got, got_prev = result(s)
     st = s.get_stats()
@@ -83,10 +84,11 @@ def test_temporal_equals_one_step_kernels_large(R):
     """Size-independent property at a size the oracle cannot reach: same bits as the one-step sweep kernel (checksum)."""
     n, steps = (200, 150, 300), 6
     sums = []
-    for bs in (2, 1):
+    for bs, variant in ((2, 0), (2, 1), (1, 0)):
         s = capi.Solution("iso3dfd", radius=R)
         s.set_overall_domain_size_vec(n)
         s.set_option("block_steps", bs)
+        s.set_option("tt_variant", variant)
         s.prepare_solution(0)
         p, v = s.get_var("p"), s.get_var("v")
         for t in (0, 1):
@@ -96,7 +98,26 @@ def test_temporal_equals_one_step_kernels_large(R):
         tl = p.get_last_valid_step_index()
         sums.append((p.checksum(tl), p.checksum(tl - 1)))
         s.close()
-    assert sums[0] == sums[1]
+    assert sums[0] == sums[2] and sums[1] == sums[2]
+
+
+def test_offline_tuner_chooses_between_one_and_two_steps_per_sweep():
+    """run_auto_tuner_now on a solution with a temporal tile times one step per sweep against both compiled two-step forms and keeps
+    the fastest (aux/yk_solution_api.hpp:858-882); whatever it keeps, results stay exact."""
+    R, n = 2, (96, 64, 256)
+    ins = synth(n, 9, R)
+    s = make(n, R, ins, 2)
+    rep = s.run_auto_tuner_now()
+    assert "one step per sweep" in rep and "x queues" in rep and "best:" in rep
+    assert s.get_option("block_steps") in ("1", "2")
+    p, v = s.get_var("p"), s.get_var("v")
+    for t in (0, 1):       # the tuner does not preserve var contents
+        p.set_elements_in_slice(ins[("p", t)], *p.halo_box(t))
+    s.run_solution(0, 3)
+    got, _ = result(s)
+    s.close()
+    ref = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], R, 4, 2)[R:-R, R:-R, R:-R]
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
 
 
 def test_block_steps_is_inert_where_no_tile_exists():

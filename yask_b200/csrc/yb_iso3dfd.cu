@@ -212,10 +212,17 @@ TTCfg tt_cfg(const char* name) {
     return TTCfg{name, T::TY, T::TZ, T::IY, T::IZ, T::S1Y, T::S1Z, T::THREADS, 4 * T::R, T::SMEM_BYTES,
                  {iso3dfd_tt2_kernel<T, 0>, iso3dfd_tt2_kernel<T, 1>, iso3dfd_tt2_kernel<T, 2>}};
 }
-const TTCfg* tt_radius_cfg(int radius) {
-    static const TTCfg cfgs[TT_MAX_R] = {tt_cfg<TTile<1, 16, 128, 3, 256>>("r1 2 steps, tile 16x128, 3 planes ahead"),
-                                         tt_cfg<TTile<2, 16, 128, 2, 256>>("r2 2 steps, tile 16x128, 2 planes ahead")};
-    return (radius >= 1 && radius <= TT_MAX_R) ? &cfgs[radius - 1] : nullptr;
+// Variants per radius (option tt_variant): 0 = every neighbour read from shared memory (the form first measured on the B200:
+// radius 1 1.32x the one-step sweep, radius 2 0.975x, shared-memory bound -- profiles/r2_temporal_tile.md), 1 = x neighbours of
+// both steps in register queues (38 % fewer shared-memory loads, smaller rings, one more plane of prefetch).
+constexpr int TT_VARIANTS = 2;
+const TTCfg* tt_radius_cfg(int radius, int variant) {
+    static const TTCfg cfgs[TT_MAX_R][TT_VARIANTS] = {
+        {tt_cfg<TTile<1, 16, 128, 3, 256, 0>>("r1 2 steps, tile 16x128, 3 planes ahead"),
+         tt_cfg<TTile<1, 16, 128, 3, 256, 1>>("r1 2 steps, tile 16x128, 3 planes ahead, x queues")},
+        {tt_cfg<TTile<2, 16, 128, 2, 256, 0>>("r2 2 steps, tile 16x128, 2 planes ahead"),
+         tt_cfg<TTile<2, 16, 128, 3, 256, 1>>("r2 2 steps, tile 16x128, 3 planes ahead, x queues")}};
+    return (radius >= 1 && radius <= TT_MAX_R && variant >= 0 && variant < TT_VARIANTS) ? &cfgs[radius - 1][variant] : nullptr;
 }
 
 // Copies a box of cells from one step slot to another (same geometry): keeps the halo cells of the extra storage
@@ -253,8 +260,12 @@ struct IsoEngine : Engine {
     // (Var::extra_slots), so it must be asked for before prepare_solution(); later changes only switch the launch path.
     int block_steps = 1;
     bool tt_ok = false;            // extra slots allocated and tensor maps built
-    TTMaps tt_maps[4];             // [slot of p(t)]
-    bool tt_attr_set[3] = {};
+    TTMaps tt_maps[4];             // [slot of p(t)]; the variants of one radius share their box shapes
+    int tt_variant = -1;           // option tt_variant: index into tt_radius_cfg(); -1 = the engine's choice (tt_var())
+    // radius 1: the shared-memory form is measured (1.32x) and already DRAM-bound; radius 2: the measured shared-memory form is
+    // bound by its shared-memory loads (0.975x), the register-queue form issues 38 % fewer of them
+    int tt_var() const { return tt_variant >= 0 ? tt_variant : (radius >= 2 ? 1 : 0); }
+    bool tt_attr_set[TT_VARIANTS][3] = {};
 
     int set_option(Solution& s, const std::string& k, const std::string& v) override {
         if (k == "kernel") {
@@ -273,6 +284,11 @@ struct IsoEngine : Engine {
         else if (k == "pol_h") { pol_h = atoi(v.c_str()); }
         else if (k == "pol_pv") { pol_pv = atoi(v.c_str()); }
         else if (k == "st_cs") { st_cs = atoi(v.c_str()) != 0; }
+        else if (k == "tt_variant") {
+            const int t = atoi(v.c_str());
+            if (t < -1 || t >= TT_VARIANTS) return YB_EINVAL;
+            tt_variant = t;
+        }
         else if (k == "block_steps") {
             block_steps = std::max(1, atoi(v.c_str()));
             if (!s.prepared && s.vars.size() >= 2) {
@@ -299,6 +315,7 @@ struct IsoEngine : Engine {
         else if (k == "lx") v = std::to_string(lx);
         else if (k == "grid") v = std::to_string(grid_override);
         else if (k == "block_steps") v = std::to_string(block_steps);
+        else if (k == "tt_variant") v = std::to_string(tt_var());
         else return false;
         return true;
     }
@@ -329,7 +346,7 @@ struct IsoEngine : Engine {
                 }
             }
             maps_ok = true;
-            if (const TTCfg* tc = (p.extra_slots == 2 && nsl == 4) ? tt_radius_cfg(radius) : nullptr) {
+            if (const TTCfg* tc = (p.extra_slots == 2 && nsl == 4) ? tt_radius_cfg(radius, 0) : nullptr) {
                 for (int cur = 0; cur < nsl; cur++) {
                     TTMaps& m = tt_maps[cur];
                     if (int rc = make_map(&m.pin, p, cur, tc->iz, tc->iy)) return rc;
@@ -337,7 +354,8 @@ struct IsoEngine : Engine {
                     if (int rc = make_map(&m.v, v, 0, tc->s1z, tc->s1y)) return rc;
                 }
                 tt_ok = true;
-                for (int m = 0; m < 3; m++) preload_kernel((const void*)tc->fn[m]);
+                for (int vr = 0; vr < TT_VARIANTS; vr++)
+                    for (int m = 0; m < 3; m++) preload_kernel((const void*)tt_radius_cfg(radius, vr)->fn[m]);
                 preload_kernel((const void*)slot_box_copy_kernel);
             }
             const TileCfg& c = radius == 8 ? tile_cfg(tile) : *iso_radius_cfg(radius);
@@ -515,7 +533,8 @@ struct IsoEngine : Engine {
     int launch_steps(Solution& s, int64_t t, int nsteps, const Box& box, cudaStream_t st) override {
         if (nsteps != 2 || !tt_ok) return set_error(YB_EUNSUPPORTED, "iso3dfd: no temporal tile for %d steps in this configuration", nsteps);
         if (box.empty()) return 0;
-        const TTCfg& c = *tt_radius_cfg(radius);
+        const int vr = tt_var();
+        const TTCfg& c = *tt_radius_cfg(radius, vr);
         Var& p = s.vars[0];
         const Var& v = s.vars[1];
         const Dim *px = p.domain_dim(0), *py = p.domain_dim(1), *pz = p.domain_dim(2);
@@ -558,9 +577,9 @@ struct IsoEngine : Engine {
         const int64_t nunits = ntile * P.nchunks;
         const int grid = int(std::min<int64_t>(nunits, gmax));
         const int mode = std::min(std::max(s.fp_mode, 0), 2);
-        if (!tt_attr_set[mode]) {
+        if (!tt_attr_set[vr][mode]) {
             YB_CUDA(cudaFuncSetAttribute(c.fn[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, int(c.smem)));
-            tt_attr_set[mode] = true;
+            tt_attr_set[vr][mode] = true;
         }
         c.fn[mode]<<<grid, c.threads, c.smem, st>>>(tt_maps[cur], P);
         YB_CUDA(cudaGetLastError());
@@ -584,10 +603,46 @@ struct IsoEngine : Engine {
         return b;
     }
 
+    // Offline tuner of a solution that has a temporal tile: one step per sweep against two steps per sweep in each compiled form,
+    // timed per STEP over the whole rank box; the fastest stays selected (block_steps / tt_variant).  All compute the same bits.
+    int auto_tune_temporal(Solution& s, cudaStream_t st, std::string& report) {
+        Box whole;
+        for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = s.rank_size[d]; }
+        int64_t t = s.vars[0].last_valid_step();
+        if (int rc = begin_run(s, t, st)) return rc;
+        const int keep_bs = block_steps, keep_var = tt_variant;
+        const int dflt_var = tt_var();
+        double best = 1e30;
+        int best_bs = 1, best_var = tt_var();
+        char line[200];
+        report.clear();
+        for (int cand = 0; cand <= TT_VARIANTS; cand++) {
+            double ms;
+            if (cand == 0) {
+                ms = time_launches(st, 4, [&]() { return launch(s, 0, t++, whole, st); });
+                snprintf(line, sizeof line, " one step per sweep: %.4f ms/step\n", ms);
+            } else {
+                tt_variant = cand - 1;
+                ms = time_launches(st, 3, [&]() { const int rc = launch_steps(s, t, 2, whole, st); t += 2; return rc; }) / 2;
+                snprintf(line, sizeof line, " two steps per sweep, %s: %.4f ms/step\n", tt_radius_cfg(radius, tt_variant)->name, ms);
+            }
+            if (ms < 0) { block_steps = keep_bs; tt_variant = keep_var; return set_error(YB_ECUDA, "auto-tuner: a trial launch failed"); }
+            report += line;
+            if (ms < best) { best = ms; best_bs = cand == 0 ? 1 : 2; best_var = cand == 0 ? dflt_var : cand - 1; }
+        }
+        block_steps = best_bs; tt_variant = best_var;
+        snprintf(line, sizeof line, "best: block_steps=%d tt_variant=%d (%.4f ms/step)\n", block_steps, tt_variant, best);
+        report += line;
+        s.options["block_steps"] = std::to_string(block_steps);
+        s.options["tt_variant"] = std::to_string(tt_variant);
+        return 0;
+    }
+
     // Offline tuner: the compiled sweep variants (tile shape, producer warpgroup, planes per trip) x sweep chunk
     // lengths, timed over the whole rank box; the analogue of the reference's block-size search
     // (/root/reference/src/kernel/lib/auto_tuner.cpp) for the knobs this engine has.
     int auto_tune(Solution& s, cudaStream_t st, std::string& report) override {
+        if (tt_ok && kernel != "direct" && !s.multi_rank()) return auto_tune_temporal(s, st, report);
         if (!maps_ok || radius != 8 || kernel == "direct") { report = "iso3dfd: no tiled variants to tune for this configuration"; return 0; }
         Box whole;
         for (int d = 0; d < 3; d++) { whole.b[d] = 0; whole.e[d] = s.rank_size[d]; }

@@ -61,18 +61,26 @@ struct TTParams {
 
 struct alignas(16) TTVec4 { float x, y, z, w; };
 
-template <int R_, int TY_, int TZ_, int PF_, int THREADS_>
+// XQ = 1: the x neighbours of BOTH steps live in per-thread register queues (2R+1 vectors per owned vector, shifted by one plane
+// per iteration), as in the one-step kernel: the p(t) ring then only spans the planes between arrival and use as the y/z
+// centre plane (R+1), the p1 ring R+2, and a thread issues 9 + 6 instead of 13 + 12 shared-memory loads per pair of vectors.
+template <int R_, int TY_, int TZ_, int PF_, int THREADS_, int XQ_ = 0>
 struct TTile {
-    static constexpr int R = R_, TY = TY_, TZ = TZ_, PF = PF_, THREADS = THREADS_;
+    static constexpr int R = R_, TY = TY_, TZ = TZ_, PF = PF_, THREADS = THREADS_, XQ = XQ_;
+    static constexpr int QN = 2 * R + 1;
     static constexpr int HZ1 = (R + 3) / 4 * 4;       // z reach of one step, in whole 16-byte vectors
     static constexpr int ZQ = HZ1 / 4;
     static constexpr int IY = TY + 4 * R, IZ = TZ + 4 * HZ1;     // p(t) box: every vector of the step-1 region finds its reach
     static constexpr int S1Y = TY + 2 * R, S1Z = TZ + 2 * HZ1;   // step-1 region = box of the p(t-1) and v loads
-    static constexpr int S1Q = S1Z / 4, S1_ITEMS = S1Y * S1Q, S1_ROUNDS = (S1_ITEMS + THREADS - 1) / THREADS;
+    static constexpr int S1Q = S1Z / 4, S1_ITEMS = S1Y * S1Q;
     static constexpr int S2Q = TZ / 4, S2_ITEMS = TY * S2Q, S2_ROUNDS = (S2_ITEMS + THREADS - 1) / THREADS;
-    static constexpr int NP = 2 * R + 1 + PF;   // p(t) ring
-    static constexpr int N1 = 2 * R + 2;        // p(t+1) ring: one more than the x window, so that step 1 of iteration g never
-                                                // writes a plane step 2 of iteration g-1 may still be reading
+    // XQ: a thread's first S2_ROUNDS step-1 vectors ARE its step-2 vectors (so that a step-1 result enters the step-2 queue
+    // without leaving the thread); the vectors of the ring around the tile are dealt out after them
+    static constexpr int S1_EXTRA = S1_ITEMS - S2_ITEMS;
+    static constexpr int S1_ROUNDS = XQ ? S2_ROUNDS + (S1_EXTRA + THREADS - 1) / THREADS : (S1_ITEMS + THREADS - 1) / THREADS;
+    static constexpr int NP = (XQ ? R + 1 : 2 * R + 1) + PF;   // p(t) ring
+    static constexpr int N1 = (XQ ? R : 2 * R) + 2;   // p(t+1) ring: one more than the planes step 2 reads, so that step 1 of iteration g
+                                                      // never writes a plane step 2 of iteration g-1 may still be reading
     static constexpr int NS = PF + 1;           // p(t-1) / v rings and full barriers
     static constexpr uint32_t P_BYTES = IY * IZ * 4, S_BYTES = S1Y * S1Z * 4;
     static constexpr uint32_t P_SLOT = (P_BYTES + 127) / 128 * 128, S_SLOT = (S_BYTES + 127) / 128 * 128;
@@ -174,6 +182,9 @@ struct TTThread {
     int nv2[T::S2_ROUNDS];          // lanes to store to p(t+2) = lanes of v to read
     long long g2[T::S2_ROUNDS];     // gy * p_sy + gz
     long long gv[T::S2_ROUNDS];     // gy * v_sy + gz
+    // XQ only: the thread's own vectors of p(t) planes xl-2R .. xl (q1) and of p(t+1) planes x1-2R .. x1 (q2), newest last
+    TTVec4 q1[T::S1_ROUNDS][T::QN];
+    TTVec4 q2[T::S2_ROUNDS][T::QN];
 };
 
 template <class T>
@@ -183,8 +194,23 @@ YB_DEVFN void tt_thread_setup(TTThread<T>& th, const TTParams& P, const TTCursor
     for (int k = 0; k < T::S1_ROUNDS; k++) {
         const int item = tid + k * T::THREADS;
         th.io1[k] = -1; th.so1[k] = 0; th.in1[k] = 0; th.nv1[k] = 0; th.g1[k] = 0;
-        if (item < T::S1_ITEMS) {
-            const int row = item / T::S1Q, q = item - row * T::S1Q;
+        int row = 0, q = 0;
+        bool have = false;
+        if (!T::XQ) {
+            have = item < T::S1_ITEMS;
+            row = item / T::S1Q; q = item - row * T::S1Q;
+        } else if (k < T::S2_ROUNDS) {          // the thread's step-2 vectors
+            have = item < T::S2_ITEMS;
+            row = item / T::S2Q + R; q = item % T::S2Q + T::ZQ;
+        } else {                                // ring around the tile: R rows above, R rows below, ZQ vectors left and right
+            int e = tid + (k - T::S2_ROUNDS) * T::THREADS;
+            have = e < T::S1_EXTRA;
+            constexpr int TOP = R * T::S1Q;
+            if (e < TOP) { row = e / T::S1Q; q = e % T::S1Q; }
+            else if (e < 2 * TOP) { e -= TOP; row = R + T::TY + e / T::S1Q; q = e % T::S1Q; }
+            else { e -= 2 * TOP; row = R + e / (2 * T::ZQ); const int c = e % (2 * T::ZQ); q = c < T::ZQ ? c : T::S2Q + c; }
+        }
+        if (have) {
             const int gy = cu.y0 - R + row, gz = cu.z0 - T::HZ1 + 4 * q;
             th.io1[k] = (row + R) * T::IZ + T::HZ1 + 4 * q;   // p(t) planes start at row y0-2R, column z0-2*HZ1
             th.so1[k] = row * T::S1Z + 4 * q;                 // step-1 planes start at row y0-R, column z0-HZ1
@@ -347,6 +373,107 @@ YB_DEVFN void tt_step2(uint8_t* sm, const TTParams& P, const TTCursor& cu, const
     }
 }
 
+// ---- XQ = 1 -------------------------------------------------------------------------------------------------------------
+// One vector of the star with the centre and the x neighbours taken from a register queue `qv` (qv[R] = centre plane, qv[R -/+ r]
+// = planes -/+ r); y and z neighbours from the shared-memory plane `pc`.
+template <class T, int MODE>
+YB_DEVFN void tt_star_q(const TTParams& P, const float* pc, int pitch, int o, const TTVec4* qv, float* acc, float* centre) {
+    constexpr int R = T::R, HZ1 = T::HZ1, ZQ = T::ZQ;
+    float zw[4 + 2 * HZ1];
+#pragma unroll
+    for (int kq = -ZQ; kq <= ZQ; kq++) {
+        if (kq == 0) tt_v2a(qv[R], &zw[4 * ZQ]);
+        else tt_v2a(tt_ld4(pc + o + 4 * kq), &zw[4 * (kq + ZQ)]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { centre[i] = zw[HZ1 + i]; acc[i] = 0.f; }
+#pragma unroll
+    for (int r = 1; r <= R; r++) {
+        float xm[4], xp[4], ym[4], yp[4];
+        tt_v2a(qv[R - r], xm);
+        tt_v2a(qv[R + r], xp);
+        tt_v2a(tt_ld4(pc + o - r * pitch), ym);
+        tt_v2a(tt_ld4(pc + o + r * pitch), yp);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            acc[i] = iso_group<MODE>(acc[i], centre[i], P.c[0], P.c[r], xm[i], xp[i], ym[i], yp[i], zw[HZ1 + i - r], zw[HZ1 + i + r], r == 1);
+    }
+}
+
+// Step 1, XQ: EVERY iteration pushes the thread's vectors of the newest p(t) plane (xl = cx0 + j - 2R) into q1; from
+// iteration 2R on p(t+1) at plane x1 = xl - R is computed (q1[R] = plane x1) and the results of the thread's step-2 vectors
+// are pushed into q2.
+template <class T, int MODE>
+YB_DEVFN void tt_step1_xq(uint8_t* sm, const TTParams& P, const TTCursor& cu, TTThread<T>& th, const TTRing<T>& rg, int j) {
+    constexpr int R = T::R, QN = T::QN;
+    const int x1 = cu.cx0 + j - 3 * R;
+    const float* pnew = rg.p(sm, 0);
+    const float* pc = rg.p(sm, R);
+    const float* prevp = reinterpret_cast<const float*>(sm + T::PV_OFF + rg.gs * T::S_SLOT);
+    const float* vp = reinterpret_cast<const float*>(sm + T::V_OFF + rg.gs * T::S_SLOT);
+    float* p1 = reinterpret_cast<float*>(sm + T::P1_OFF + rg.g1 * T::S_SLOT);
+    const bool x_in = x1 >= 0 && x1 < P.nx;
+    const bool x_store = x1 >= cu.cx0 && x1 < cu.cx0 + cu.len;
+    float* o1 = P.out1 + (long long)x1 * P.p_sx;
+#pragma unroll
+    for (int k = 0; k < T::S1_ROUNDS; k++) {
+        // The queues shift on EVERY iteration and for every k, outside all conditions (a queue that is modified under a
+        // branch costs a register move per entry at the join); a thread without this item shifts garbage it never uses.
+        const int io = th.io1[k];
+        const bool have = io >= 0;
+#pragma unroll
+        for (int i = 0; i + 1 < QN; i++) th.q1[k][i] = th.q1[k][i + 1];
+        th.q1[k][QN - 1] = tt_ld4(pnew + (have ? io : 0));
+        TTVec4 rv{0.f, 0.f, 0.f, 0.f};
+        if (have && j >= 2 * R) {
+            const int so = th.so1[k];
+            float acc[4], centre[4], pv[4], vv[4], res[4];
+            tt_star_q<T, MODE>(P, pc, T::IZ, io, th.q1[k], acc, centre);
+            tt_v2a(tt_ld4(prevp + so), pv);
+            tt_v2a(tt_ld4(vp + so), vv);
+            const int m = x_in ? th.in1[k] : 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = iso_final<MODE>(acc[i], centre[i], pv[i], vv[i]);
+            if (m != 15) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (!((m >> i) & 1)) res[i] = pv[i];
+            }
+            rv = TTVec4{res[0], res[1], res[2], res[3]};
+            *reinterpret_cast<TTVec4*>(p1 + so) = rv;
+            if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k]);
+        }
+        if (k < T::S2_ROUNDS) {
+#pragma unroll
+            for (int i = 0; i + 1 < QN; i++) th.q2[k][i] = th.q2[k][i + 1];
+            th.q2[k][QN - 1] = rv;
+        }
+    }
+}
+
+// Step 2, XQ: p(t+2) at plane x2 = x1 - R: centre and x neighbours from q2 (q2[R] = plane x2), y / z neighbours from the p1
+// plane produced R iterations ago, "prev" = p(t) at plane x2 = the oldest entry of q1.
+template <class T, int MODE>
+YB_DEVFN void tt_step2_xq(uint8_t* sm, const TTParams& P, const TTCursor& cu, const TTThread<T>& th, const TTRing<T>& rg, int j, const TTVec4* vreg) {
+    constexpr int R = T::R;
+    if (j < 4 * R) return;
+    const int x2 = cu.cx0 + j - 4 * R;
+    const float* pc = rg.p1(sm, R);
+    float* o2 = P.out2 + (long long)x2 * P.p_sx;
+#pragma unroll
+    for (int k = 0; k < T::S2_ROUNDS; k++) {
+        const int so = th.so2[k];
+        if (so >= 0 && th.nv2[k] > 0) {
+            float acc[4], centre[4], pv[4], vv[4], res[4];
+            tt_star_q<T, MODE>(P, pc, T::S1Z, so, th.q2[k], acc, centre);
+            tt_v2a(th.q1[k][0], pv);
+            tt_v2a(vreg[k], vv);
+#pragma unroll
+            for (int i = 0; i < 4; i++) res[i] = iso_final<MODE>(acc[i], centre[i], pv[i], vv[i]);
+            tt_store(o2 + th.g2[k], res, th.nv2[k]);
+        }
+    }
+}
+
 // The sweep of one CTA, written once for both back ends.  BE supplies the execution model:
 //   threads(f)   run f(tid) for every thread of the CTA        (device: f(threadIdx.x); emulator: a loop)
 //   once(f)      run f() on the producer thread                  (device: thread 0)
@@ -389,10 +516,16 @@ YB_DEVFN void tt_sweep(BE& be, uint8_t* sm, const TTParams& P, int first_unit, i
         for (int j = 0; j < cu.n_it; j++) {
             be.threads([&](int tid) { tt_load_v<T>(P, cu, be.thread(tid), j, be.vreg(tid)); });
             be.wait_full(rg.gs, rg.parity);
-            be.threads([&](int tid) { tt_step1<T, MODE>(sm, P, cu, be.thread(tid), rg, j); });
+            be.threads([&](int tid) {
+                if (T::XQ) tt_step1_xq<T, MODE>(sm, P, cu, be.thread(tid), rg, j);
+                else tt_step1<T, MODE>(sm, P, cu, be.thread(tid), rg, j);
+            });
             be.barrier();     // p1 plane of this iteration visible; every thread is done with iteration g-1
             be.once([&]() { if (pr_live) produce_one(); });     // loads of iteration g+PF
-            be.threads([&](int tid) { tt_step2<T, MODE>(sm, P, cu, be.thread(tid), rg, j, be.vreg(tid)); });
+            be.threads([&](int tid) {
+                if (T::XQ) tt_step2_xq<T, MODE>(sm, P, cu, be.thread(tid), rg, j, be.vreg(tid));
+                else tt_step2<T, MODE>(sm, P, cu, be.thread(tid), rg, j, be.vreg(tid));
+            });
             rg.advance();
         }
     }
