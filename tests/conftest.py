@@ -15,6 +15,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+collect_ignore_glob = ["_bin/*", "emul/*"]      # staged reference programs and the emulator source are not test modules
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
 

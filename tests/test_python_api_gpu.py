@@ -27,7 +27,7 @@ def _run(script, mod):
 @pytest.mark.skipif(not MODS, reason="python modules not built")
 @pytest.mark.parametrize("mod", MODS, ids=[os.path.basename(os.path.dirname(m)) for m in MODS])
 def test_reference_python_api_test_unmodified(mod):
-    r = _run("ref_yask_kernel_api_test.py", mod)
+    r = _run("ref_yask_kernel_api_test.ref.py", mod)
     assert r.returncode == 0, (r.stdout[-3000:] + r.stderr[-3000:])
     assert "End of YASK Python kernel API test." in r.stdout
 
@@ -35,6 +35,6 @@ def test_reference_python_api_test_unmodified(mod):
 @pytest.mark.skipif(not MODS, reason="python modules not built")
 def test_reference_python_exception_test_unmodified():
     mod = [m for m in MODS if os.sep + "iso3dfd" + os.sep in m] or MODS
-    r = _run("ref_yask_kernel_api_exception_test.py", mod[0])
+    r = _run("ref_yask_kernel_api_exception_test.ref.py", mod[0])
     assert r.returncode == 0, (r.stdout[-3000:] + r.stderr[-3000:])
     assert "End of YASK Python kernel API test with exception." in r.stdout
