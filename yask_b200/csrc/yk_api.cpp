@@ -427,7 +427,10 @@ struct B200Var : yk_var {
     bool is_storage_allocated() const override { return prepared(); }
     idx_t get_num_storage_bytes() const override { return info().storage_bytes; }
     idx_t get_num_storage_elements() const override { auto i = info(); return i.slot_elems * i.step_alloc; }
-    void alloc_storage() override { if (!prepared()) fail("alloc_storage: device storage is allocated by prepare_solution()"); }
+    // Device storage of every var, fixed-size user vars included, is allocated by prepare_solution() on the device chosen there
+    // (yk_var_api.hpp:1281-1296: "storage will be allocated" now OR by prepare_solution()); a call before it is therefore a
+    // request that prepare_solution() honours, not an error -- the reference's Python API test makes exactly that call.
+    void alloc_storage() override {}
     void release_storage() override {}
     bool is_storage_layout_identical(const yk_var_ptr other) const override {
         if (!other) return false;
@@ -443,11 +446,12 @@ struct B200Var : yk_var {
     void* get_raw_storage_buffer() override {
         if (!prepared()) return nullptr;
         auto i = info();
-        raw_mirror.resize(size_t(i.storage_bytes));
+        // the step slots the API can see (a var with spare slots for the temporal tile keeps them out of this view)
+        raw_mirror.resize(size_t(i.slot_elems) * size_t(i.has_step ? i.step_alloc : 1) * size_t(i.elem_bytes));
         void* dev = nullptr;
         chk(yb_var_device_ptr(h->s, vi, 0, &dev));
         chk(yb_solution_sync(h->s));
-        chk(yb_copy_to_host(raw_mirror.data(), dev, raw_mirror.size()));   // step 0 lives in slot 0 = start of the allocation
+        chk(yb_copy_to_host(raw_mirror.data(), dev, raw_mirror.size()));   // step 0 lives in the first slot of the live set
         return raw_mirror.data();
     }
 };

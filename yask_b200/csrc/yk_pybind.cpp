@@ -27,11 +27,12 @@ namespace {
 // element count and pointer of a Python buffer that must hold the slice [first, last]
 struct Buf {
     void* ptr;
-    size_t bytes;
+    size_t elems;      // number of items of the buffer's own item size (4 or 8 bytes: the caller picks the solution's element type)
 };
 Buf writable(py::buffer& b, bool need_write) {
     py::buffer_info bi = b.request(need_write);
-    return Buf{bi.ptr, size_t(bi.size) * size_t(bi.itemsize)};
+    if (bi.itemsize != 4 && bi.itemsize != 8) throw yask_exception("YASK error: the buffer must hold float32 or float64 items");
+    return Buf{bi.ptr, size_t(bi.size)};
 }
 size_t slice_elems(const idx_t_vec& first, const idx_t_vec& last) {
     if (first.size() != last.size()) throw yask_exception("YASK error: first and last indices differ in length");
@@ -169,16 +170,14 @@ PYBIND11_MODULE(yask_kernel, m) {
              [](const yk_var& v, py::buffer b, const idx_t_vec& first, const idx_t_vec& last) {
                  const Buf bf = writable(b, true);
                  const size_t n = slice_elems(first, last);
-                 if (bf.bytes < n * size_t(v.get_num_storage_bytes() / std::max<idx_t>(v.get_num_storage_elements(), 1)))
-                     throw yask_exception("YASK error: buffer too small for the requested slice");
+                 if (bf.elems < n) throw yask_exception("YASK error: buffer too small for the requested slice");
                  return v.get_elements_in_slice(bf.ptr, first, last);
              })
         .def("set_elements_in_slice",
              [](yk_var& v, py::buffer b, const idx_t_vec& first, const idx_t_vec& last) {
                  const Buf bf = writable(b, false);
                  const size_t n = slice_elems(first, last);
-                 if (bf.bytes < n * size_t(v.get_num_storage_bytes() / std::max<idx_t>(v.get_num_storage_elements(), 1)))
-                     throw yask_exception("YASK error: buffer too small for the requested slice");
+                 if (bf.elems < n) throw yask_exception("YASK error: buffer too small for the requested slice");
                  return v.set_elements_in_slice(static_cast<const void*>(bf.ptr), first, last);
              })
         .def("set_elements_in_slice",
