@@ -20,6 +20,7 @@
 #include <vector>
 
 #define YB_TT_HOST_EMUL 1
+#define YB_TT_SMEM_HOOKS 1
 #define YB_DEVFN static inline
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
@@ -28,6 +29,43 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 #include "../../yask_b200/csrc/yb_iso3dfd_tt.cuh"
 
 using namespace yb;
+
+// ---- race detector --------------------------------------------------------------------------------------------------------
+// Every generic-proxy access to shared memory reports here.  Between two CTA barriers ("epoch") a 16-byte vector that one thread
+// writes must not be read or written by another thread: the emulator runs the threads one after the other, so such a race
+// would go unnoticed in the data.  (TMA writes are ordered by the full barriers and are covered by the eager / lazy models.)
+namespace {
+struct RaceState {
+    const uint8_t* base = nullptr;
+    size_t nvec = 0;
+    std::vector<int> rd_epoch, rd_tid, wr_epoch, wr_tid;     // per 16-byte vector: last reader / writer and when
+    int epoch = 0, tid = -1, races = 0;
+    void reset(const uint8_t* b, size_t bytes) {
+        base = b; nvec = bytes / 16; epoch = 0; tid = -1; races = 0;
+        rd_epoch.assign(nvec, -1); rd_tid.assign(nvec, -1); wr_epoch.assign(nvec, -1); wr_tid.assign(nvec, -1);
+    }
+    long idx(const float* p) const {
+        const long off = reinterpret_cast<const uint8_t*>(p) - base;
+        return (off >= 0 && size_t(off) < nvec * 16) ? off / 16 : -1;
+    }
+} g_race;
+}  // namespace
+namespace yb {
+void tt_hook_smem_read(const float* p) {
+    const long i = g_race.idx(p);
+    if (i < 0) { g_race.races++; return; }                                   // read outside the CTA's shared memory
+    if (g_race.wr_epoch[i] == g_race.epoch && g_race.wr_tid[i] != g_race.tid) g_race.races++;    // read-after-write without a barrier
+    if (g_race.rd_epoch[i] != g_race.epoch) { g_race.rd_epoch[i] = g_race.epoch; g_race.rd_tid[i] = g_race.tid; }
+    else if (g_race.rd_tid[i] != g_race.tid) g_race.rd_tid[i] = -2;          // several readers in this epoch
+}
+void tt_hook_smem_write(const float* p) {
+    const long i = g_race.idx(p);
+    if (i < 0) { g_race.races++; return; }
+    if (g_race.rd_epoch[i] == g_race.epoch && g_race.rd_tid[i] != g_race.tid) g_race.races++;    // write-after-read without a barrier
+    if (g_race.wr_epoch[i] == g_race.epoch && g_race.wr_tid[i] != g_race.tid) g_race.races++;    // write-after-write
+    g_race.wr_epoch[i] = g_race.epoch; g_race.wr_tid[i] = g_race.tid;
+}
+}  // namespace yb
 
 namespace {
 
@@ -63,9 +101,9 @@ struct Emul {
                 dst[y * p.bz + z] = in ? p.t->base[gx * p.t->sx + gy * p.t->sy + gz] : 0.f;
             }
     }
-    template <class F> void threads(F f) { for (int t = 0; t < T::THREADS; t++) f(t); }
+    template <class F> void threads(F f) { for (int t = 0; t < T::THREADS; t++) { g_race.tid = t; f(t); } }
     template <class F> void once(F f) { f(); }
-    void barrier() {}
+    void barrier() { g_race.epoch++; }
     TTVec4* vreg(int tid) { return &vregs[size_t(tid) * T::S2_ROUNDS]; }
     void issue(const TTLoads& L, int b) {
         Bar& br = bars[b];
@@ -128,8 +166,10 @@ int run(const float* pprev, const float* pcur, const float* vel, float* out1, fl
         be.pin = Tensor{pcur, pz, py, px, P.p_sy, P.p_sx};
         be.prev = Tensor{pprev, pz, py, px, P.p_sy, P.p_sx};
         be.v = Tensor{vel, vz, vy, vx, P.v_sy, P.v_sx};
+        g_race.reset(be.smem.data(), be.smem.size());
         tt_sweep<T, MODE>(be, be.smem.data(), P, blk, grid);
         if (be.error) return be.error;
+        if (g_race.races) return 6;                        // data race between threads inside one barrier interval
         for (auto& b : be.bars) if (b.armed) return 5;     // loads still in flight when the CTA exits
     }
     return 0;

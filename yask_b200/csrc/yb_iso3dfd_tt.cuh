@@ -137,7 +137,17 @@ YB_DEVFN TTLoads tt_loads(const TTParams& P, const TTCursor& cu, unsigned g) {
     return L;
 }
 
+// Shared-memory vector load / store.  The emulator hooks both (YB_TT_SMEM_HOOKS) to detect data races between threads inside
+// one barrier interval -- the one class of error a sequential emulation of the threads cannot produce by itself.
+#ifdef YB_TT_SMEM_HOOKS
+void tt_hook_smem_read(const float* p);
+void tt_hook_smem_write(const float* p);
+YB_DEVFN TTVec4 tt_ld4(const float* p) { tt_hook_smem_read(p); return *reinterpret_cast<const TTVec4*>(p); }
+YB_DEVFN void tt_sts4(float* p, const TTVec4& v) { tt_hook_smem_write(p); *reinterpret_cast<TTVec4*>(p) = v; }
+#else
 YB_DEVFN TTVec4 tt_ld4(const float* p) { return *reinterpret_cast<const TTVec4*>(p); }
+YB_DEVFN void tt_sts4(float* p, const TTVec4& v) { *reinterpret_cast<TTVec4*>(p) = v; }
+#endif
 YB_DEVFN void tt_v2a(const TTVec4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
 #ifndef YB_TT_HOST_EMUL
@@ -151,7 +161,7 @@ YB_DEVFN TTVec4 tt_ldg4(const float* p) {
 }
 #else
 YB_DEVFN void tt_stg4(float* p, const TTVec4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
-YB_DEVFN TTVec4 tt_ldg4(const float* p) { return tt_ld4(p); }
+YB_DEVFN TTVec4 tt_ldg4(const float* p) { return *reinterpret_cast<const TTVec4*>(p); }
 #endif
 
 // Result vector -> global memory; `nv` leading lanes are inside the domain.
@@ -339,7 +349,7 @@ YB_DEVFN void tt_step1(uint8_t* sm, const TTParams& P, const TTCursor& cu, const
 #pragma unroll
                 for (int i = 0; i < 4; i++) if (!((m >> i) & 1)) res[i] = pv[i];
             }
-            *reinterpret_cast<TTVec4*>(p1 + so) = TTVec4{res[0], res[1], res[2], res[3]};
+            tt_sts4(p1 + so, TTVec4{res[0], res[1], res[2], res[3]});
             if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k]);
         }
     }
@@ -439,7 +449,7 @@ YB_DEVFN void tt_step1_xq(uint8_t* sm, const TTParams& P, const TTCursor& cu, TT
                 for (int i = 0; i < 4; i++) if (!((m >> i) & 1)) res[i] = pv[i];
             }
             rv = TTVec4{res[0], res[1], res[2], res[3]};
-            *reinterpret_cast<TTVec4*>(p1 + so) = rv;
+            tt_sts4(p1 + so, rv);
             if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k]);
         }
         if (k < T::S2_ROUNDS) {
