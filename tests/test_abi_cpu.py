@@ -49,3 +49,22 @@ def test_solution_settings_and_errors_without_device():
             s.prepare_solution(0)
         assert "no CUDA device" in str(e.value)
     s.close()
+
+
+def test_block_steps_option_and_geometry():
+    """The temporal tile's storage is decided before prepare: block_steps >= 2 on iso3dfd radius <= 2 adds a spare pair of slots
+    and the pads its boxes reach into; the API-visible step window stays two steps; other radii keep the reference's storage."""
+    from yask_b200 import capi
+    for radius, bs, want_slots in ((2, 2, 4), (1, 2, 4), (2, 1, 2), (8, 2, 2)):
+        s = capi.Solution("iso3dfd", radius=radius)
+        s.set_overall_domain_size_vec((64, 48, 96))
+        s.set_option("block_steps", bs)
+        assert s.get_option("block_steps") == str(bs)
+        s.plan_geometry()
+        p, v = s.get_var("p").info, s.get_var("v").info
+        assert p.step_alloc == 2
+        assert p.storage_bytes == want_slots * p.slot_elems * 4
+        if want_slots == 4:
+            assert p.dims[1].left_pad >= 2 * radius and p.dims[2].left_pad >= 2 * radius and p.dims[3].left_pad >= 8
+            assert v.dims[0].left_pad >= radius and v.dims[2].left_pad >= 4
+        s.close()

@@ -564,6 +564,11 @@ int yb_var_fuse(yb_solution* s_, int var, yb_solution* src_, int src_var) {
         if (d.dims[i].spec.name != o.dims[i].spec.name || d.dims[i].spec.kind != o.dims[i].spec.kind)
             return set_error(YB_EINVAL, "fuse_vars(): dim %zu of '%s' is '%s' but '%s' in '%s'", i, d.spec.name.c_str(), d.dims[i].spec.name.c_str(),
                              o.dims[i].spec.name.c_str(), o.spec.name.c_str());
+    // a var with spare slots (temporal tile) switches its live slot set at run time; a second view of the same storage would
+    // not follow
+    if (d.extra_slots || o.extra_slots)
+        return set_error(YB_EUNSUPPORTED, "fuse_vars(): '%s' / '%s' carry spare storage slots of a temporal tile (block_steps); fuse before selecting it or not at all",
+                         d.spec.name.c_str(), o.spec.name.c_str());
     if (!o.dev) {
         // source not allocated: this var becomes unallocated too (yk_var_api.hpp:1378-1383)
         if (s->prepared) return set_error(YB_ESTATE, "fuse_vars(): source var '%s' has no storage but '%s' belongs to a prepared solution", o.spec.name.c_str(), d.spec.name.c_str());
