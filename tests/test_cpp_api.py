@@ -119,7 +119,7 @@ def test_harness_prints_the_reference_report_keys(stencil, args):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     for key in ("num-trials:", "best-throughput (num-points/sec):", "mid-throughput (num-points/sec):", "best-elapsed-time (sec):",
-                "num-points-per-step:", "YASK DONE"):
+                "num-points-per-step:", "stencil-name:", "yask-version:", "Num MPI ranks:", "num-temporal-block-steps:", "YASK DONE"):
         assert key in r.stdout, key
     line = [l for l in r.stdout.splitlines() if "best-num-steps-done" in l][0]
     assert line.split()[-1] == "4"

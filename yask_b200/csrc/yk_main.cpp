@@ -99,6 +99,21 @@ int main(int argc, char** argv) {
                   << " local-domain-size:      " << ls.str() << "\n"
                   << " num-ranks:              " << env->get_num_ranks() << "\n"
                   << " num-points-per-step:    " << num_str(double(pts)) << "\n";
+        // the keys the reference's log tooling collects (utils/lib/YaskUtils.pm @log_keys; wording of setup.cpp:613-650,
+        // soln_apis.cpp:155), so that utils/bin/yask_log_to_csv.pl reads these logs like its own
+        idx_t alloc_bytes = 0;
+        for (auto& v : soln->get_vars()) alloc_bytes += v->get_num_storage_bytes();
+        out << "Num MPI ranks:             " << nranks << "\n"
+            << "Domain size in this rank (points):          " << num_str(double(pts)) << "\n"
+            << "Total allocation in this rank:              " << num_str(double(alloc_bytes)) << "B\n"
+            << "Overall problem size in " << nranks << " rank(s) (points): " << num_str(double(env->sum_over_ranks(pts))) << "\n"
+            << "Other settings:\n"
+            << " yask-version:           " << kfac.get_version_string() << "\n"
+            << " target:                 " << soln->get_target() << "\n"
+            << " stencil-name:           " << soln->get_name() << "\n"
+            << " stencil-description:    " << soln->get_description() << "\n"
+            << " element-size:           " << soln->get_element_bytes() << "B\n"
+            << " num-temporal-block-steps:  " << std::max<idx_t>(1, soln->get_block_size(soln->get_step_dim_name())) << "\n";
 
         // data: every var constant, slightly different per var (the reference's init_same pattern)
         int k = 0;
