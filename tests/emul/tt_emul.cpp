@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #define YB_TT_HOST_EMUL 1
@@ -40,6 +41,11 @@ struct RaceState {
     size_t nvec = 0;
     std::vector<int> rd_epoch, rd_tid, wr_epoch, wr_tid;     // per 16-byte vector: last reader / writer and when
     int epoch = 0, tid = -1, races = 0;
+    // bank-conflict model (optional): the addresses of every thread's shared-memory vector accesses of the current phase, in
+    // program order; a phase = one threads() call of the back end
+    bool model_banks = false;
+    std::vector<std::vector<long>> seq;      // [tid] -> 16-byte vector indices
+    unsigned long long n_inst = 0, n_wave = 0;   // warp-level vector accesses and their wavefronts (4 per conflict-free access)
     void reset(const uint8_t* b, size_t bytes) {
         base = b; nvec = bytes / 16; epoch = 0; tid = -1; races = 0;
         rd_epoch.assign(nvec, -1); rd_tid.assign(nvec, -1); wr_epoch.assign(nvec, -1); wr_tid.assign(nvec, -1);
@@ -55,6 +61,7 @@ void tt_hook_smem_read(const float* p) {
     const long i = g_race.idx(p);
     if (i < 0) { g_race.races++; return; }                                   // read outside the CTA's shared memory
     if (g_race.wr_epoch[i] == g_race.epoch && g_race.wr_tid[i] != g_race.tid) g_race.races++;    // read-after-write without a barrier
+    if (g_race.model_banks && g_race.tid >= 0) g_race.seq[g_race.tid].push_back(i);
     if (g_race.rd_epoch[i] != g_race.epoch) { g_race.rd_epoch[i] = g_race.epoch; g_race.rd_tid[i] = g_race.tid; }
     else if (g_race.rd_tid[i] != g_race.tid) g_race.rd_tid[i] = -2;          // several readers in this epoch
 }
@@ -64,6 +71,7 @@ void tt_hook_smem_write(const float* p) {
     if (g_race.rd_epoch[i] == g_race.epoch && g_race.rd_tid[i] != g_race.tid) g_race.races++;    // write-after-read without a barrier
     if (g_race.wr_epoch[i] == g_race.epoch && g_race.wr_tid[i] != g_race.tid) g_race.races++;    // write-after-write
     g_race.wr_epoch[i] = g_race.epoch; g_race.wr_tid[i] = g_race.tid;
+    if (g_race.model_banks && g_race.tid >= 0) g_race.seq[g_race.tid].push_back(i);
 }
 }  // namespace yb
 
@@ -101,7 +109,37 @@ struct Emul {
                 dst[y * p.bz + z] = in ? p.t->base[gx * p.t->sx + gy * p.t->sy + gz] : 0.f;
             }
     }
-    template <class F> void threads(F f) { for (int t = 0; t < T::THREADS; t++) { g_race.tid = t; f(t); } }
+    template <class F> void threads(F f) {
+        if (g_race.model_banks) g_race.seq.assign(T::THREADS, std::vector<long>());
+        for (int t = 0; t < T::THREADS; t++) { g_race.tid = t; f(t); }
+        g_race.tid = -1;
+        if (!g_race.model_banks) return;
+        // 128-bit accesses are served per quarter-warp: 8 lanes x 16 B cover the 32 banks once; two different vectors in the same
+        // 16-byte bank group (vector index mod 8) cost one more wavefront, the same vector twice is a broadcast
+        for (int w = 0; w < T::THREADS; w += 32) {
+            size_t ni = 0;
+            for (int l = 0; l < 32 && w + l < T::THREADS; l++) ni = std::max(ni, g_race.seq[w + l].size());
+            for (size_t i = 0; i < ni; i++) {
+                bool any = false;
+                for (int qw = 0; qw < 4; qw++) {
+                    long seen[8][8]; int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int l = qw * 8; l < qw * 8 + 8 && w + l < T::THREADS; l++) {
+                        if (i >= g_race.seq[w + l].size()) continue;
+                        const long v = g_race.seq[w + l][i];
+                        const int g = int(v & 7);
+                        bool dup = false;
+                        for (int c = 0; c < cnt[g]; c++) dup = dup || seen[g][c] == v;
+                        if (!dup) seen[g][cnt[g]++] = v;
+                    }
+                    int mx = 0;
+                    for (int g = 0; g < 8; g++) mx = std::max(mx, cnt[g]);
+                    g_race.n_wave += mx;
+                    any = any || mx > 0;
+                }
+                g_race.n_inst += any;
+            }
+        }
+    }
     template <class F> void once(F f) { f(); }
     void barrier() { g_race.epoch++; }
     TTVec4* vreg(int tid) { return &vregs[size_t(tid) * T::S2_ROUNDS]; }
@@ -186,6 +224,10 @@ int run_mode(int mode, const float* a, const float* b, const float* c, float* d,
 }
 
 }  // namespace
+
+// Bank-conflict model: switch recording on / off and read (warp-level vector accesses, wavefronts) since the last reset.
+extern "C" void tt_emul_bank_model(int on) { g_race.model_banks = on != 0; g_race.n_inst = g_race.n_wave = 0; }
+extern "C" void tt_emul_bank_stats(unsigned long long* inst, unsigned long long* waves) { *inst = g_race.n_inst; *waves = g_race.n_wave; }
 
 // p arrays: (nx+2*ppad[0], ny+2*ppad[1], nz+2*ppad[2]) floats, v: same with vpad.  out1 / out2 must arrive holding copies of
 // pprev / pcur (their halo cells are what the engine's begin_run() replicates); the domain parts are overwritten with

@@ -102,3 +102,21 @@ def test_fp_modes_and_wide_pads(radius, mode):
 @pytest.mark.parametrize("n,grid,nchunks", [((12, 20, 150), 2, 1), ((17, 33, 260), 4, 2), ((9, 16, 128), 1, 3)])
 def test_shipped_tile_matches_oracle(radius, n, grid, nchunks, lazy, xq):
     check(radius, 2 * xq, 2, n, (radius, radius, 32), (0, 0, 32), grid, nchunks, lazy)
+
+
+def test_register_queue_form_needs_fewer_shared_memory_wavefronts():
+    """The point of the second form (TTile XQ = 1): at least 30 % fewer shared-memory wavefronts per plane than the form whose
+    neighbours all come from shared memory -- the resource ncu showed saturated at radius 2 (profiles/r2_temporal_tile.md).
+    Counted by the emulator's first-order bank model (quarter-warp service of 128-bit accesses; ncu measured 17 % conflicts on the
+    first form where this model says 6 %, so the absolute numbers are indicative only -- the ratio is what is asserted)."""
+    L = emul()
+    L.tt_emul_bank_stats.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    waves = {}
+    for variant in (0, 2):
+        L.tt_emul_bank_model(1)
+        run_case(2, variant, 2, (24, 32, 256), (4, 4, 32), (2, 2, 32), 1, 1, 0)
+        a, b = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        L.tt_emul_bank_stats(ctypes.byref(a), ctypes.byref(b))
+        L.tt_emul_bank_model(0)
+        waves[variant] = b.value
+    assert waves[2] < 0.7 * waves[0], waves
