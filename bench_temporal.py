@@ -46,7 +46,8 @@ if __name__ == "__main__":
     except Exception:
         pass
     one = run(radius, n, 1, 4, steps)
-    forms = {"shared_memory": run(radius, n, 2, 4, steps, 0), "x_queues": run(radius, n, 2, 4, steps, 1)}
+    forms = {"shared_memory": run(radius, n, 2, 4, steps, 0), "x_queues": run(radius, n, 2, 4, steps, 1),
+             "shared_memory_512_threads": run(radius, n, 2, 4, steps, 2), "x_queues_512_threads": run(radius, n, 2, 4, steps, 3)}
     dflt = run(radius, n, 2, 4, steps)          # the engine's own choice of form
     tt = dict(dflt)
     for r in forms.values():

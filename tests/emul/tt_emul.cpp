@@ -232,7 +232,7 @@ extern "C" void tt_emul_bank_stats(unsigned long long* inst, unsigned long long*
 // p arrays: (nx+2*ppad[0], ny+2*ppad[1], nz+2*ppad[2]) floats, v: same with vpad.  out1 / out2 must arrive holding copies of
 // pprev / pcur (their halo cells are what the engine's begin_run() replicates); the domain parts are overwritten with
 // p(t+1) / p(t+2).  `variant`: 0 = the shipped tile of that radius, 1 = a small tile (more tiles and rounds per test); 2, 3 = the same two
-// with the x neighbours in register queues (TTile XQ = 1).
+// with the x neighbours in register queues (TTile XQ = 1); 4, 5 = the shipped tile with 512 threads, XQ = 0 / 1.
 // Returns 0, or a protocol error code (see Emul).
 extern "C" int tt_emul_run(int radius, int variant, int mode, const float* pprev, const float* pcur, const float* vel, float* out1, float* out2,
                            const int* n, const int* ppad, const int* vpad, const float* coef, int grid, int nchunks, int lazy) {
@@ -244,5 +244,9 @@ extern "C" int tt_emul_run(int radius, int variant, int mode, const float* pprev
     if (radius == 2 && variant == 2) return run_mode<TTile<2, 16, 128, 3, 256, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
     if (radius == 1 && variant == 3) return run_mode<TTile<1, 4, 16, 2, 32, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
     if (radius == 2 && variant == 3) return run_mode<TTile<2, 4, 16, 1, 32, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 1 && variant == 4) return run_mode<TTile<1, 16, 128, 3, 512, 0>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 2 && variant == 4) return run_mode<TTile<2, 16, 128, 2, 512, 0>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 1 && variant == 5) return run_mode<TTile<1, 16, 128, 3, 512, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
+    if (radius == 2 && variant == 5) return run_mode<TTile<2, 16, 128, 3, 512, 1>>(mode, pprev, pcur, vel, out1, out2, n, ppad, vpad, coef, grid, nchunks, lazy);
     return -2;
 }

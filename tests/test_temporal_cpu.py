@@ -97,11 +97,11 @@ def test_fp_modes_and_wide_pads(radius, mode):
 
 # the shipped tiles (16 x 128, 256 threads): ragged in y and z, one and several tiles, chunk boundaries
 @pytest.mark.parametrize("lazy", [0, 1])
-@pytest.mark.parametrize("xq", [0, 1])
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])     # the four compiled forms: 256 / 512 threads x neighbours from shared memory / x queues
 @pytest.mark.parametrize("radius", [1, 2])
 @pytest.mark.parametrize("n,grid,nchunks", [((12, 20, 150), 2, 1), ((17, 33, 260), 4, 2), ((9, 16, 128), 1, 3)])
-def test_shipped_tile_matches_oracle(radius, n, grid, nchunks, lazy, xq):
-    check(radius, 2 * xq, 2, n, (radius, radius, 32), (0, 0, 32), grid, nchunks, lazy)
+def test_shipped_tile_matches_oracle(radius, n, grid, nchunks, lazy, variant):
+    check(radius, variant, 2, n, (radius, radius, 32), (0, 0, 32), grid, nchunks, lazy)
 
 
 def test_register_queue_form_needs_fewer_shared_memory_wavefronts():

@@ -39,7 +39,7 @@ def result(s):
     return p.get_elements_in_slice(*p.domain_box(tl)), p.get_elements_in_slice(*p.domain_box(tl - 1))
 
 
-@pytest.mark.parametrize("variant", [0, 1])     # 0: neighbours from shared memory, 1: x neighbours in register queues
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])     # 0: neighbours from shared memory, 1: x neighbours in register queues; 2, 3: the same with 512 threads
 @pytest.mark.parametrize("fp_mode", [2, 0])
 @pytest.mark.parametrize("steps", [2, 3, 4, 7])
 @pytest.mark.parametrize("R,n", [(2, (40, 37, 150)), (1, (33, 20, 260)), (2, (9, 16, 128)), (1, (64, 48, 64))])
@@ -84,7 +84,7 @@ def test_temporal_equals_one_step_kernels_large(R):
     """Size-independent property at a size the oracle cannot reach: same bits as the one-step sweep kernel (checksum)."""
     n, steps = (200, 150, 300), 6
     sums = []
-    for bs, variant in ((2, 0), (2, 1), (1, 0)):
+    for bs, variant in ((2, 0), (2, 1), (2, 2), (2, 3), (1, 0)):
         s = capi.Solution("iso3dfd", radius=R)
         s.set_overall_domain_size_vec(n)
         s.set_option("block_steps", bs)
@@ -98,7 +98,7 @@ def test_temporal_equals_one_step_kernels_large(R):
         tl = p.get_last_valid_step_index()
         sums.append((p.checksum(tl), p.checksum(tl - 1)))
         s.close()
-    assert sums[0] == sums[2] and sums[1] == sums[2]
+    assert all(x == sums[-1] for x in sums[:-1])
 
 
 def test_offline_tuner_chooses_between_one_and_two_steps_per_sweep():

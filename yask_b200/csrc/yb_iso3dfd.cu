@@ -215,13 +215,17 @@ TTCfg tt_cfg(const char* name) {
 // Variants per radius (option tt_variant): 0 = every neighbour read from shared memory (the form first measured on the B200:
 // radius 1 1.32x the one-step sweep, radius 2 0.975x, shared-memory bound -- profiles/r2_temporal_tile.md), 1 = x neighbours of
 // both steps in register queues (38 % fewer shared-memory loads, smaller rings, one more plane of prefetch).
-constexpr int TT_VARIANTS = 2;
+constexpr int TT_VARIANTS = 4;       // 2, 3 = forms 0, 1 with 512 threads (16 warps per SM to hide the shared-memory latency: short_scoreboard was 32 % of the stalls)
 const TTCfg* tt_radius_cfg(int radius, int variant) {
     static const TTCfg cfgs[TT_MAX_R][TT_VARIANTS] = {
         {tt_cfg<TTile<1, 16, 128, 3, 256, 0>>("r1 2 steps, tile 16x128, 3 planes ahead"),
-         tt_cfg<TTile<1, 16, 128, 3, 256, 1>>("r1 2 steps, tile 16x128, 3 planes ahead, x queues")},
+         tt_cfg<TTile<1, 16, 128, 3, 256, 1>>("r1 2 steps, tile 16x128, 3 planes ahead, x queues"),
+         tt_cfg<TTile<1, 16, 128, 3, 512, 0>>("r1 2 steps, tile 16x128, 3 planes ahead, 512 threads"),
+         tt_cfg<TTile<1, 16, 128, 3, 512, 1>>("r1 2 steps, tile 16x128, 3 planes ahead, x queues, 512 threads")},
         {tt_cfg<TTile<2, 16, 128, 2, 256, 0>>("r2 2 steps, tile 16x128, 2 planes ahead"),
-         tt_cfg<TTile<2, 16, 128, 3, 256, 1>>("r2 2 steps, tile 16x128, 3 planes ahead, x queues")}};
+         tt_cfg<TTile<2, 16, 128, 3, 256, 1>>("r2 2 steps, tile 16x128, 3 planes ahead, x queues"),
+         tt_cfg<TTile<2, 16, 128, 2, 512, 0>>("r2 2 steps, tile 16x128, 2 planes ahead, 512 threads"),
+         tt_cfg<TTile<2, 16, 128, 3, 512, 1>>("r2 2 steps, tile 16x128, 3 planes ahead, x queues, 512 threads")}};
     return (radius >= 1 && radius <= TT_MAX_R && variant >= 0 && variant < TT_VARIANTS) ? &cfgs[radius - 1][variant] : nullptr;
 }
 
