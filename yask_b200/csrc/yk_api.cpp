@@ -466,8 +466,20 @@ struct B200Solution : yk_solution {
     bool step_wrap = false;
     int device = -1;
 
-    explicit B200Solution(const char* stencil) {
-        chk(yb_solution_create(&h->s, stencil, 0, 0));
+    // The reference fixes a solution's radius when it builds the kernel library (`make stencil=iso3dfd radius=2`,
+    // /root/reference/src/kernel/Makefile); here the library name carries it the same way: libyask_kernel.iso3dfd_r2.b200.so
+    // (-DYK_STENCIL_NAME=iso3dfd_r2) is iso3dfd with radius 2.  YASK_B200_RADIUS overrides it at run time.
+    explicit B200Solution(const char* stencil_) {
+        std::string stencil = stencil_;
+        int radius = 0;
+        const size_t us = stencil.rfind("_r");
+        if (us != std::string::npos && us + 2 < stencil.size() && stencil.compare(0, us, "iso3dfd") == 0 &&
+            stencil.find_first_not_of("0123456789", us + 2) == std::string::npos) {
+            radius = atoi(stencil.c_str() + us + 2);
+            stencil.resize(us);
+        }
+        if (const char* e = getenv("YASK_B200_RADIUS")) radius = atoi(e);
+        chk(yb_solution_create(&h->s, stencil.c_str(), radius, 0));
         name = yb_solution_name(h->s);
         descr = "B200-native engine for solution '" + name + "'";
     }
