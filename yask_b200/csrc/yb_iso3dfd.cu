@@ -555,6 +555,7 @@ struct IsoEngine : Engine {
         P.pad_x = int(px->pad_l); P.pad_y = int(py->pad_l); P.pad_z = int(pz->pad_l);
         P.vpad_x = int(vx->pad_l); P.vpad_y = int(vy->pad_l); P.vpad_z = int(vz->pad_l);
         for (int r = 0; r <= TT_MAX_R; r++) P.c[r] = r <= radius ? float(coef[r]) : 0.f;
+        P.pol_p = pol_h; P.st_cs = st_cs;       // same options (pol_h, st_cs) and defaults as the one-step kernel's haloed p(t) stream / stores
         P.nty = (P.ny + c.ty - 1) / c.ty;
         P.ntz = (P.nz + c.tz - 1) / c.tz;
         // x chunks of (almost) equal length: minimise (rounds of units per CTA) x (chunk length + warm-up iterations;

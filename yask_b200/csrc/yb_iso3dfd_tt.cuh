@@ -57,6 +57,9 @@ struct TTParams {
     int nty, ntz, nchunks;     // tiles in y and z, chunks along x
     int cx0[TT_MAX_CHUNKS], clen[TT_MAX_CHUNKS];   // first plane and number of planes of every chunk
     float c[TT_MAX_R + 1];
+    // L2 policy, as in the one-step kernel (profiles/r2_iso3dfd.md): the p(t) box is the stream whose halo rows the neighbouring
+    // tiles re-read (0 normal, 1 evict_first, 2 evict_last); results are not read again during the launch (st_cs: streaming stores)
+    int pol_p, st_cs;
 };
 
 struct alignas(16) TTVec4 { float x, y, z, w; };
@@ -151,8 +154,9 @@ YB_DEVFN void tt_sts4(float* p, const TTVec4& v) { *reinterpret_cast<TTVec4*>(p)
 YB_DEVFN void tt_v2a(const TTVec4& v, float* a) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
 
 #ifndef YB_TT_HOST_EMUL
-YB_DEVFN void tt_stg4(float* p, const TTVec4& v) {
-    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+YB_DEVFN void tt_stg4(float* p, const TTVec4& v, int cs) {
+    if (cs) asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    else asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 YB_DEVFN TTVec4 tt_ldg4(const float* p) {
     TTVec4 v;
@@ -160,15 +164,15 @@ YB_DEVFN TTVec4 tt_ldg4(const float* p) {
     return v;
 }
 #else
-YB_DEVFN void tt_stg4(float* p, const TTVec4& v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
+YB_DEVFN void tt_stg4(float* p, const TTVec4& v, int) { p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; }
 YB_DEVFN TTVec4 tt_ldg4(const float* p) { return *reinterpret_cast<const TTVec4*>(p); }
 #endif
 
 // Result vector -> global memory; `nv` leading lanes are inside the domain.
-YB_DEVFN void tt_store(float* o, const float* r, int nv) {
+YB_DEVFN void tt_store(float* o, const float* r, int nv, int cs) {
     if (nv >= 4 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
         TTVec4 v{r[0], r[1], r[2], r[3]};
-        tt_stg4(o, v);
+        tt_stg4(o, v, cs);
     } else {
         if (nv > 0) o[0] = r[0];
         if (nv > 1) o[1] = r[1];
@@ -350,7 +354,7 @@ YB_DEVFN void tt_step1(uint8_t* sm, const TTParams& P, const TTCursor& cu, const
                 for (int i = 0; i < 4; i++) if (!((m >> i) & 1)) res[i] = pv[i];
             }
             tt_sts4(p1 + so, TTVec4{res[0], res[1], res[2], res[3]});
-            if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k]);
+            if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k], P.st_cs);
         }
     }
 }
@@ -378,7 +382,7 @@ YB_DEVFN void tt_step2(uint8_t* sm, const TTParams& P, const TTCursor& cu, const
             tt_v2a(vreg[k], vv);
 #pragma unroll
             for (int i = 0; i < 4; i++) res[i] = iso_final<MODE>(acc[i], centre[i], pv[i], vv[i]);
-            tt_store(o2 + th.g2[k], res, th.nv2[k]);
+            tt_store(o2 + th.g2[k], res, th.nv2[k], P.st_cs);
         }
     }
 }
@@ -450,7 +454,7 @@ YB_DEVFN void tt_step1_xq(uint8_t* sm, const TTParams& P, const TTCursor& cu, TT
             }
             rv = TTVec4{res[0], res[1], res[2], res[3]};
             tt_sts4(p1 + so, rv);
-            if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k]);
+            if (x_store && th.nv1[k] > 0) tt_store(o1 + th.g1[k], res, th.nv1[k], P.st_cs);
         }
         if (k < T::S2_ROUNDS) {
 #pragma unroll
@@ -479,7 +483,7 @@ YB_DEVFN void tt_step2_xq(uint8_t* sm, const TTParams& P, const TTCursor& cu, co
             tt_v2a(vreg[k], vv);
 #pragma unroll
             for (int i = 0; i < 4; i++) res[i] = iso_final<MODE>(acc[i], centre[i], pv[i], vv[i]);
-            tt_store(o2 + th.g2[k], res, th.nv2[k]);
+            tt_store(o2 + th.g2[k], res, th.nv2[k], P.st_cs);
         }
     }
 }
@@ -559,6 +563,7 @@ struct TTDevice {
     uint8_t* sbase;
     uint64_t* full_bar;
     const TTMaps* M;
+    uint64_t pol_p;        // L2 policy of the p(t) box
     TTVec4 v[T::S2_ROUNDS];
     TTThread<T> th;
     __device__ __forceinline__ TTThread<T>& thread(int) { return th; }
@@ -570,7 +575,7 @@ struct TTDevice {
     __device__ __forceinline__ void issue(const TTLoads& L, int b) {
         uint64_t* fb = &full_bar[b];
         mbar_arrive_expect_tx(fb, L.bytes);
-        tma_load_3d(sbase + L.p_off, &M->pin, fb, L.pz, L.py, L.px);
+        tma_load_3d_hint(sbase + L.p_off, &M->pin, fb, L.pz, L.py, L.px, pol_p);
         if (L.step1) {
             tma_load_3d(sbase + L.pv_off, &M->prev, fb, L.sz, L.sy, L.sx);
             tma_load_3d(sbase + L.v_off, &M->v, fb, L.vz, L.vy, L.vx);
@@ -587,6 +592,7 @@ iso3dfd_tt2_kernel(const __grid_constant__ TTMaps M, const __grid_constant__ TTP
     be.sbase = smem_raw + (base - smem_u32(smem_raw));
     be.full_bar = reinterpret_cast<uint64_t*>(be.sbase + T::BAR_OFF);
     be.M = &M;
+    be.pol_p = l2_policy(P.pol_p);
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&M.pin); tma_prefetch_desc(&M.prev); tma_prefetch_desc(&M.v);
         for (int s = 0; s < T::NS; s++) mbar_init(&be.full_bar[s], 1);
