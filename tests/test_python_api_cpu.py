@@ -46,4 +46,6 @@ def test_module_mirrors_reference_python_api(mod):
     r = subprocess.run([sys.executable, "-c", SCRIPT], env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     stencil = os.path.basename(os.path.dirname(mod))
+    if stencil.startswith("iso3dfd_r"):          # radius-suffixed library of iso3dfd (the reference fixes the radius at build time)
+        stencil = "iso3dfd"
     assert r.stdout.strip().startswith("OK " + stencil)
