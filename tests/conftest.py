@@ -15,7 +15,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
-collect_ignore_glob = ["_bin/*", "emul/*"]      # staged reference programs and the emulator source are not test modules
+collect_ignore_glob = ["_bin/*", "emul/*", "unit/*"]      # staged reference programs and the emulator source are not test modules
 
 
 def pytest_configure(config):

@@ -68,3 +68,13 @@ def test_block_steps_option_and_geometry():
             assert p.dims[1].left_pad >= 2 * radius and p.dims[2].left_pad >= 2 * radius and p.dims[3].left_pad >= 8
             assert v.dims[0].left_pad >= radius and v.dims[2].left_pad >= 4
         s.close()
+
+
+def test_step_to_slot_map_with_spare_slots(tmp_path):
+    """tests/unit/slot_test.cpp: Var::slot_of / nslots / valid-step window with the temporal tile's spare pair of slots."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "slot_test")
+    subprocess.run(["g++", "-std=c++17", "-I/usr/local/cuda/include", os.path.join(root, "tests", "unit", "slot_test.cpp"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
