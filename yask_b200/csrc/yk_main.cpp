@@ -42,7 +42,9 @@ void usage(const char* exe, yk_solution_ptr soln) {
               << "                         (RANK / WORLD_SIZE / LOCAL_RANK as torchrun, mpirun or srun export them)\n"
               << " -warmup_steps <n>       untimed steps before the trials (default 5)\n"
               << " -init_val <x>           value every var is initialised to (default 0.1, var k gets x*(1+k/16))\n"
-              << " -validate               iso3dfd only: cross-check the tiled kernel against the direct kernel on the device\n"
+              << " -validate               cross-check on the device: sweep kernels (temporal tile included) against the one-thread-per-point\n"
+              << "                         kernels of a second solution, every written var, element for element\n"
+              << " -[no-]pre_auto_tune     time the engine's launch variants before the trials and keep the fastest (default on; 1 rank)\n"
               << "Solution options:\n" << soln->get_command_line_help();
 }
 
@@ -55,6 +57,7 @@ int main(int argc, char** argv) {
         auto soln = kfac.new_solution(env);
         idx_t trial_steps = 50, num_trials = 3, warmup_steps = 5, msg_rank = 0;
         double init_val = 0.1, init_seed = 0.1;
+        bool pre_auto_tune = true;
         bool validate = false;
         // harness options first; everything else goes to the solution (as yask_main.cpp:199-259 does)
         string_vec rest;
@@ -74,6 +77,8 @@ int main(int argc, char** argv) {
             else if (a == "-init_seed") init_seed = atof(val().c_str());   // spread of the per-var values (the reference seeds its varying sequence with it)
             else if (a == "-trial_time" || a == "-sleep") val();      // reference options with no meaning here
             else if (a == "-validate" || a == "-v") validate = true;
+            else if (a == "-pre_auto_tune") pre_auto_tune = true;          // yask_main.cpp:53: on by default
+            else if (a == "-no-pre_auto_tune") pre_auto_tune = false;
             else rest.push_back(a);
         }
         // only one rank of a job prints (yask_main.cpp -msg_rank)
@@ -244,6 +249,15 @@ int main(int argc, char** argv) {
             return bad ? 1 : 0;
         }
 
+        // The reference tunes before the trials unless told not to (yask_main.cpp:53,440-478).  Here the tuner times the engine's
+        // launch variants -- sweep tile / chunk length, direct vs sweep kernels, one or two steps per sweep where a temporal tile
+        // exists -- and keeps the fastest; every variant computes the same bits.  Single-rank runs only.
+        if (pre_auto_tune && nranks == 1) {
+            out << DIV << "Running the auto-tuner before the trials (-no-pre_auto_tune skips it)...\n";
+            soln->run_auto_tuner_now(false);
+            k = 0;
+            for (auto& v : soln->get_vars()) v->set_all_elements_same(var_val(k++));      // the tuner does not preserve var contents
+        }
         if (warmup_steps > 0) soln->run_solution(0, warmup_steps - 1);
         idx_t first_t = warmup_steps;
         std::vector<Trial> trials;
