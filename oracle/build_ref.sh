@@ -15,7 +15,8 @@
 # usage: [REF_ALL=1] oracle/build_ref.sh [arch]     (arch: avx512 (default) | avx2 | intel64)
 #   default: the references bench.py's CPU arms and the live-reference tests need: iso3dfd (default + strict),
 #            awp_elastic fp32 and ssg fp64 (default flags), ~4 min;
-#   REF_ALL=1: every solution the golden fixtures were generated from (~90 kernel builds, over an hour).
+#   REF_ALL=1: every solution the golden fixtures were generated from (~90 kernel builds, over an hour);
+#   REF_RADII=1: only iso3dfd at radius 1 and 2 (fixtures of the temporal tile), ~3 min.
 #
 # Outputs: oracle/_ref/yask/  the reference's own output tree (stays in the build container);
 #          oracle/_ref/ship/  the few binaries the GPU box runs (copied from the tree; travels with gpurun);
@@ -70,6 +71,13 @@ build_kernel iso3dfd "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off
 if [ "$ARCH" = "avx512" ]; then
     build_kernel awp_elastic ""        4
     build_kernel ssg "-fp64"        8
+fi
+if [ "${REF_ALL:-0}" = "1" ] || [ "${REF_RADII:-0}" = "1" ]; then
+    # iso3dfd at the radii of the temporal tile (the reference fixes the radius at build time): fixtures for tests/test_temporal_*
+    for r in 1 2; do
+        build_kernel iso3dfd "-r$r"        4 radius=$r
+        build_kernel iso3dfd "-r$r-strict" 4 radius=$r EXTRA_YK_CXXFLAGS=-ffp-contract=off
+    done
 fi
 if [ "${REF_ALL:-0}" = "1" ]; then
     build_kernel awp_elastic "-strict" 4 EXTRA_YK_CXXFLAGS=-ffp-contract=off

@@ -74,3 +74,20 @@ def test_generated_oracle_vs_reference(path):
             assert np.array_equal(got.view(it), ref.view(it)), name
         else:
             assert field_ulps(got, ref) <= 4.0, (name, field_ulps(got, ref))
+
+
+@pytest.mark.parametrize("path", golden_cases("iso3dfd-r"))
+def test_iso3dfd_small_radius_oracle_bit_exact_vs_reference(path):
+    """iso3dfd built by the reference at radius 1 and 2 (`make stencil=iso3dfd radius=<r>`, both FP builds): the radii of the
+    temporal tile.  Pins the oracle -- and through it the CTA emulator and the GPU tests of the tile -- to the unmodified
+    reference at these radii too."""
+    meta, arrays = load_golden(path)
+    radius = int(meta["ref_tag"].split("-r")[1][0])
+    ins = regen_inputs(meta)
+    mode = contract_mode_of(meta["ref_tag"])
+    out = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], radius, meta["steps"], mode)
+    t_last = meta["vars"]["p"]["steps"][1]
+    ref = arrays[f"p.t{t_last}"]
+    got = out[radius:-radius, radius:-radius, radius:-radius]
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))

@@ -120,3 +120,34 @@ def test_register_queue_form_needs_fewer_shared_memory_wavefronts():
         L.tt_emul_bank_model(0)
         waves[variant] = b.value
     assert waves[2] < 0.7 * waves[0], waves
+
+
+@pytest.mark.parametrize("variant", [0, 2, 4, 5])
+@pytest.mark.parametrize("path", [p for p in __import__("tests.helpers", fromlist=["golden_cases"]).golden_cases("iso3dfd-r") if "_s4" in p])
+def test_emulated_tile_bit_exact_vs_reference_fixture(path, variant):
+    """Two emulated fused pairs (4 steps) against the outputs of the UNMODIFIED reference built at radius 1 / 2, both FP builds."""
+    from tests.helpers import contract_mode_of, load_golden, regen_inputs
+    meta, arrays = load_golden(path)
+    R = int(meta["ref_tag"].split("-r")[1][0])
+    mode = contract_mode_of(meta["ref_tag"])
+    ins = regen_inputs(meta)
+    n = meta["n"]
+    # API step 0 is p(t), API step 1 holds p(t-1) (two-slot wrap): the emulator's "cur" and "prev"
+    ppad, vpad = (2 * R, 2 * R, 8), (R, R, 4)
+    def padded(a, pad, h):
+        out = np.full([n[d] + 2 * pad[d] for d in range(3)], np.nan, dtype=np.float32)
+        out[tuple(slice(pad[d] - h, pad[d] + n[d] + h) for d in range(3))] = a
+        return out
+    prev, cur = padded(ins[("p", 1)], ppad, R), padded(ins[("p", 0)], ppad, R)
+    v = padded(ins[("v", 0)], vpad, 0)
+    coef = _coef32(R)
+    i3 = lambda x: ctypes.cast((ctypes.c_int * 3)(*x), ctypes.c_void_p)
+    for _ in range(2):
+        o1, o2 = prev.copy(), cur.copy()
+        rc = emul().tt_emul_run(R, variant, mode, prev.ctypes.data, cur.ctypes.data, v.ctypes.data, o1.ctypes.data, o2.ctypes.data,
+                                i3(n), i3(ppad), i3(vpad), coef.ctypes.data, 3, 2, 1)
+        assert rc == 0
+        prev, cur = o1, o2
+    got = cur[tuple(slice(ppad[d], ppad[d] + n[d]) for d in range(3))]
+    ref = arrays[f"p.t{meta['vars']['p']['steps'][1]}"]
+    assert np.array_equal(np.ascontiguousarray(got).view(np.uint32), ref.view(np.uint32))

@@ -131,3 +131,25 @@ def test_block_steps_is_inert_where_no_tile_exists():
     s.close()
     ref = O.iso3dfd_run(ins[("p", 0)], ins[("p", 1)], ins[("v", 0)], R, 2, 2)[R:-R, R:-R, R:-R]
     assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(ref).view(np.uint32))
+
+
+from tests.helpers import contract_mode_of, golden_cases, load_golden, regen_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("path", golden_cases("iso3dfd-r"))
+def test_temporal_tile_bit_exact_vs_reference_fixture(path, variant):
+    """Against the outputs of the UNMODIFIED reference built at radius 1 / 2 (`make stencil=iso3dfd radius=<r>`), default GCC build
+    (fp_mode 2) and -ffp-contract=off build (fp_mode 0): 4 steps = two fused launches, 5 steps = two fused + one one-step launch."""
+    meta, arrays = load_golden(path)
+    R = int(meta["ref_tag"].split("-r")[1][0])
+    ins = regen_inputs(meta)
+    s = make(meta["n"], R, ins, 2, contract_mode_of(meta["ref_tag"]), {"tt_variant": variant})
+    s.run_solution(0, meta["steps"] - 1)
+    got, _ = result(s)
+    st = s.get_stats()
+    s.close()
+    ref = arrays[f"p.t{meta['vars']['p']['steps'][1]}"]
+    assert got.shape == ref.shape
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert st.kernel_launches == meta["steps"] // 2 + meta["steps"] % 2
