@@ -18,11 +18,17 @@
 //   step 2  : p(t+2) at plane x2 = x1 - R over the tile, from the p1 ring (x2-R..x2+R), p(t) plane x2 (the oldest plane of
 //             the p ring, "prev") and v(x2) (read from global/L2 into a register before step 1) -> HBM (slot of t+2).
 //
-// HBM traffic per point and PAIR of steps: read p(t-1), p(t), v, write p(t+1), p(t+2) = 20 B (+ halo overlap, served
-// mostly by L2) against 2 x 16 B for two one-step sweeps.  Overlapping tiles read halo cells of BOTH input steps, so the
-// two results cannot overwrite them in place: the var gets two extra storage slots (yb_iso3dfd.cu).
-// Shared memory bounds the radius: R = 2 needs 227 KB at tile 16 x 128 (R = 3 would leave an 8-row tile that recomputes
-// 86 % of step 1) -- hence "where the radius allows" = R <= 2.
+// (Form XQ = 1, below: the x neighbours of both steps come from per-thread register queues instead of the rings, which then
+// only span R+1 / R+2 planes.)
+//
+// HBM traffic per point and PAIR of steps: read p(t-1), p(t), v, write p(t+1), p(t+2) = 20 B (+ halo overlap) against
+// 2 x 16 B for two one-step sweeps.  Overlapping tiles read halo cells of BOTH input steps, so the two results cannot
+// overwrite them in place: the var gets a spare pair of storage slots and fused launches ping-pong between the pairs
+// (yb_core.h Var::extra_slots / slot_bias, yb_iso3dfd.cu).
+// Shared memory bounds the radius: R = 2 needs 227 KB at tile 16 x 128 in the first form (R = 3 would leave an 8-row tile
+// that recomputes 86 % of step 1) -- hence "where the radius allows" = R <= 2.
+// Measured on a B200 at 1024^3 (profiles/r2_temporal_tile.md): radius 1 1.32x the one-step sweep (472 GPts/s), radius 2 first
+// form 0.975x (shared-memory bound; the XQ form answers that reading).
 //
 // Every function that touches tile data is written once (YB_DEVFN) and is ALSO compiled by g++ into the test suite's CTA
 // emulator (tests/emul/tt_emul.cpp: threads run in a loop, TMA boxes are copied by the host), which checks the ring /
