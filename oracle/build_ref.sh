@@ -74,7 +74,7 @@ if [ "$ARCH" = "avx512" ]; then
 fi
 if [ "${REF_ALL:-0}" = "1" ] || [ "${REF_RADII:-0}" = "1" ]; then
     # iso3dfd at the radii of the temporal tile (the reference fixes the radius at build time): fixtures for tests/test_temporal_*
-    for r in 1 2; do
+    for r in 1 2 4; do        # 4: the usual 8th-order stencil, served by the one-step kernel of that radius
         build_kernel iso3dfd "-r$r"        4 radius=$r
         build_kernel iso3dfd "-r$r-strict" 4 radius=$r EXTRA_YK_CXXFLAGS=-ffp-contract=off
     done

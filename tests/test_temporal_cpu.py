@@ -123,7 +123,7 @@ def test_register_queue_form_needs_fewer_shared_memory_wavefronts():
 
 
 @pytest.mark.parametrize("variant", [0, 2, 4, 5])
-@pytest.mark.parametrize("path", [p for p in __import__("tests.helpers", fromlist=["golden_cases"]).golden_cases("iso3dfd-r") if "_s4" in p])
+@pytest.mark.parametrize("path", [p for p in __import__("tests.helpers", fromlist=["golden_cases"]).golden_cases("iso3dfd-r") if "_s4" in p and int(p.split("iso3dfd-r")[1][0]) <= 2])
 def test_emulated_tile_bit_exact_vs_reference_fixture(path, variant):
     """Two emulated fused pairs (4 steps) against the outputs of the UNMODIFIED reference built at radius 1 / 2, both FP builds."""
     from tests.helpers import contract_mode_of, load_golden, regen_inputs

@@ -136,8 +136,27 @@ def test_block_steps_is_inert_where_no_tile_exists():
 from tests.helpers import contract_mode_of, golden_cases, load_golden, regen_inputs  # noqa: E402
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def _radius_of(path):
+    return int(path.split("iso3dfd-r")[1][0])
+
+
+@pytest.mark.parametrize("kernel", ["tma", "direct"])
 @pytest.mark.parametrize("path", golden_cases("iso3dfd-r"))
+def test_one_step_kernels_bit_exact_vs_reference_fixture_at_small_radii(path, kernel):
+    """The one-step sweep kernel of each radius and the direct kernel against the unmodified reference built at radius 1, 2, 4."""
+    meta, arrays = load_golden(path)
+    R = _radius_of(path)
+    ins = regen_inputs(meta)
+    s = make(meta["n"], R, ins, 1, contract_mode_of(meta["ref_tag"]), {"kernel": kernel})
+    s.run_solution(0, meta["steps"] - 1)
+    got, _ = result(s)
+    s.close()
+    ref = arrays[f"p.t{meta['vars']['p']['steps'][1]}"]
+    assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("path", [p for p in golden_cases("iso3dfd-r") if _radius_of(p) <= 2])
 def test_temporal_tile_bit_exact_vs_reference_fixture(path, variant):
     """Against the outputs of the UNMODIFIED reference built at radius 1 / 2 (`make stencil=iso3dfd radius=<r>`), default GCC build
     (fp_mode 2) and -ffp-contract=off build (fp_mode 0): 4 steps = two fused launches, 5 steps = two fused + one one-step launch."""
